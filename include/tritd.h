@@ -1,0 +1,182 @@
+/* libtritd -- C ABI of the B200-native TriTD-ADMM hot path.
+ *
+ * This is the drop-in boundary for ONE path of the reference
+ * (dangnq2501/Triple-Tensor-Decomposition-with-ADMM):
+ *
+ *   [A,B,C,O,errHist] = triple_decomp_ADMM(D, r, opts)
+ *       fast_robust_triple_tensor/triple_decomp_ADMM.m:1-70
+ *
+ * plus the L2 helpers that path calls and its callers use afterwards
+ * (triple_product.m:1-8, unfold.m:1-14, buildF.m/buildG.m/buildH.m,
+ * soft_threshold.m:1-3).  The reference has no FFI of its own (it is pure
+ * MATLAB); the entry points below are what a MEX gateway named
+ * triple_decomp_ADMM.mex* binds -- see INTEGRATION.md and
+ * triple-tensor-decomposition-with-admm_b200/mex/.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every function returns a tritd_status
+ *    (0 = OK) and never throws; tritd_last_error() gives the message of the
+ *    last failure on the calling thread.
+ *  - all matrices/tensors are IEEE-754 float64 in MATLAB (column-major)
+ *    layout: D, O, L are n1 x n2 x n3; A is n1 x r x r, B is r x n2 x r,
+ *    C is r x r x n3; errHist has room for opts->maxIter doubles.
+ *  - "_host" pointers are host memory (pageable or pinned), "_dev" pointers
+ *    are device memory on the context's GPU.
+ *  - there is no CPU fallback: without a CUDA device every compute entry
+ *    point fails with TRITD_ERR_CUDA.
+ *  - a context is bound to one calling thread at a time; calls on it are
+ *    serialised by the caller.
+ *
+ * Multi-GPU: the tensor is sharded along its slowest mode (t, mode 3) into
+ * contiguous slabs, one per rank (tritd_slab_bounds).  A context created
+ * with tritd_create_rank() is one rank of an NCCL communicator (one process
+ * per GPU; the 128-byte unique id is exchanged by the caller, e.g. through
+ * torch.distributed); every rank then passes only ITS slab of D / C0 and
+ * receives its slab of O / C, while A and B are replicated.
+ */
+#ifndef TRITD_H
+#define TRITD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tritd_ctx tritd_ctx;
+typedef struct tritd_problem tritd_problem;
+
+typedef enum {
+    TRITD_OK = 0,
+    TRITD_ERR_INVALID = 1,      /* bad argument (NULL, non-positive size, r out of range, ...) */
+    TRITD_ERR_CUDA = 2,         /* CUDA runtime/driver failure or no device */
+    TRITD_ERR_NCCL = 3,         /* NCCL missing or a collective failed */
+    TRITD_ERR_NUMERIC = 4,      /* ridge system not positive definite (Cholesky pivot <= 0 or non-finite) */
+    TRITD_ERR_UNSUPPORTED = 5   /* r > TRITD_MAX_R */
+} tritd_status;
+
+#define TRITD_MAX_R 8           /* triple rank r (R = r^2 <= 64 columns per factor) */
+#define TRITD_NCCL_ID_BYTES 128
+
+/* opts struct of triple_decomp_ADMM.m:16-20 (field names as in the reference; `lambda_`
+ * because lambda is reserved in some bindings).  mu_max = 1e6*mu and the fixed 1e-9 ridge of
+ * update_C (:93) are part of the algorithm, not options. */
+typedef struct {
+    double mu;        /* opts.mu      initial penalty (muL = muO)          */
+    double rho;       /* opts.rho     penalty growth factor                */
+    double lambda_;   /* opts.lambda  weight of ||E||_1                    */
+    double lambda2;   /* opts.lambda2 ridge of the A and B updates         */
+    double tol;       /* opts.tol     relative-change stopping tolerance   */
+    int32_t maxIter;  /* opts.maxIter                                      */
+    int32_t disp;     /* opts.disp    print "Iter %d, errL=%.2e, errO=%.2e" every 10th iteration */
+} tritd_opts;
+
+/* Wall-clock / device timing of one tritd_admm_f64 call, milliseconds. */
+typedef struct {
+    double h2d_ms;        /* host -> device copies of D and the initial factors */
+    double iterate_ms;    /* the ADMM loop, CUDA-event time on the compute stream */
+    double d2h_ms;        /* device -> host copies of the outputs */
+    double total_ms;      /* entry to return, host clock */
+    int32_t iters;        /* iterations executed (== length of errHist) */
+    int32_t launches;     /* kernels this library launched during the call */
+} tritd_timing;
+
+/* ---- contexts ---------------------------------------------------------- */
+
+/* Single-rank context on CUDA device `device`. */
+int tritd_create(int device, tritd_ctx** out);
+
+/* One rank of an `nranks`-way mode-3 sharded solve (one process per GPU).
+ * `nccl_id` is the TRITD_NCCL_ID_BYTES blob produced by tritd_nccl_unique_id()
+ * on rank 0 and distributed by the caller. */
+int tritd_nccl_unique_id(void* id_out);
+int tritd_create_rank(int device, int rank, int nranks, const void* nccl_id, tritd_ctx** out);
+
+void tritd_destroy(tritd_ctx* ctx);
+const char* tritd_last_error(void);
+const char* tritd_version(void);
+
+/* Use an existing CUDA stream (a cudaStream_t passed as void*) for all work of this
+ * context, so the caller can bracket it with its own events; NULL restores the
+ * context's private stream. */
+int tritd_set_stream(tritd_ctx* ctx, void* cuda_stream);
+
+/* Slab [t0,t1) of rank `rank` when n3 slices are split over nranks ranks. */
+int tritd_slab_bounds(int64_t n3, int nranks, int rank, int64_t* t0, int64_t* t1);
+
+/* ---- the solver, one call (what the MEX gateway binds) ----------------- */
+
+/* [A,B,C,O,errHist] = triple_decomp_ADMM(D, r, opts) with injected initial factors
+ * (the reference draws them with randn at :23 in the order A, B, C; the gateway
+ * does that in MATLAB and passes them in so the caller's rng stream is preserved).
+ * n3 is the number of slices held by THIS rank (== global n3 on a single-rank
+ * context); D_host/C0/C/O/L are this rank's slab.  O and L_or_null may be NULL
+ * (then they are not copied back).  errHist must hold opts->maxIter doubles;
+ * *iters_out receives the executed iteration count. */
+int tritd_admm_f64(tritd_ctx* ctx, const double* D_host, int64_t n1, int64_t n2, int64_t n3, int r,
+                   const tritd_opts* opts, const double* A0, const double* B0, const double* C0,
+                   double* A, double* B, double* C, double* O, double* L_or_null,
+                   double* errHist, int32_t* iters_out, tritd_timing* timing_or_null);
+
+/* ---- the solver, staged (device-resident state; used by benchmarks and by
+ *      callers that keep L/O on the GPU) ------------------------------------ */
+
+int tritd_problem_create(tritd_ctx* ctx, int64_t n1, int64_t n2, int64_t n3_local, int r, tritd_problem** out);
+void tritd_problem_destroy(tritd_problem* p);
+
+/* Load this rank's slab of D (dense column-major n1 x n2 x n3_local). */
+int tritd_problem_set_D_host(tritd_problem* p, const double* D_host);
+int tritd_problem_set_D_dev(tritd_problem* p, const double* D_dev);
+
+/* Reset the ADMM state (O = E = Y_L = Y_O = 0, mu = opts.mu, k = 0), install the
+ * initial factors (host pointers, MATLAB 3-D shapes; C0 is this rank's slab) and
+ * compute ||D|| (all-reduced over ranks). */
+int tritd_problem_init(tritd_problem* p, const tritd_opts* opts, const double* A0, const double* B0,
+                       const double* C0);
+
+/* Run up to `max_more` further iterations (<= remaining maxIter); stops early when the
+ * reference's stopping rule fires.  Asynchronous work is complete on return.
+ * *iters_total receives the number of iterations executed since init. */
+int tritd_problem_iterate(tritd_problem* p, int32_t max_more, int32_t* iters_total);
+
+/* Enqueue exactly `n` iterations on the context's stream WITHOUT synchronising or
+ * checking the stopping rule on the host (the device-side rule still turns later
+ * iterations into no-ops).  For benchmarks that time with their own CUDA events. */
+int tritd_problem_enqueue(tritd_problem* p, int32_t n);
+int tritd_problem_sync(tritd_problem* p);
+
+/* Copy results to host (any pointer may be NULL).  errHist/errL/errO receive
+ * `iters` doubles each. */
+int tritd_problem_get(tritd_problem* p, double* A, double* B, double* C, double* O, double* L,
+                      double* errHist, double* errL, double* errO, int32_t* iters);
+/* Device-side views (dense column-major copies written to caller-owned device memory). */
+int tritd_problem_get_O_dev(tritd_problem* p, double* O_dev);
+int tritd_problem_get_L_dev(tritd_problem* p, double* L_dev);
+/* Number of kernels launched by this library on this context so far. */
+int64_t tritd_launch_count(const tritd_ctx* ctx);
+
+/* ---- standalone L2 helpers (host pointers, MATLAB shapes) --------------- */
+
+/* Xhat = triple_product(A,B,C)                      triple_product.m:1-8   */
+int tritd_triple_product_f64(tritd_ctx* ctx, const double* A, const double* B, const double* C,
+                             int64_t n1, int64_t n2, int64_t n3, int r, double* Xhat);
+/* Xn = unfold(X, mode), mode in {1,2,3}             unfold.m:1-14          */
+int tritd_unfold_f64(tritd_ctx* ctx, const double* X, int64_t n1, int64_t n2, int64_t n3, int mode, double* Xn);
+/* F = buildF(B,C)  r^2 x (n2 n3)                    buildF.m:17-21         */
+int tritd_buildF_f64(tritd_ctx* ctx, const double* B, const double* C, int64_t n2, int64_t n3, int r, double* F);
+/* G = buildG(A,C)  r^2 x (n1 n3)                    buildG.m:17-21         */
+int tritd_buildG_f64(tritd_ctx* ctx, const double* A, const double* C, int64_t n1, int64_t n3, int r, double* G);
+/* H = buildH(A,B)  r^2 x (n1 n2)                    buildH.m:17-21         */
+int tritd_buildH_f64(tritd_ctx* ctx, const double* A, const double* B, int64_t n1, int64_t n2, int r, double* H);
+/* O = soft_threshold(X, lam), n elements            soft_threshold.m:2     */
+int tritd_soft_threshold_f64(tritd_ctx* ctx, const double* X, int64_t n, double lam, double* out);
+/* The three contractions of one sweep at fixed factors (what update_A/B/C feed to pinv):
+ * rhsA = X1*F' (n1 x r^2), rhsB = X2*G' (n2 x r^2), rhsC = X3*H' (n3 x r^2), column-major. */
+int tritd_mttkrp_f64(tritd_ctx* ctx, const double* X, const double* A, const double* B, const double* C,
+                     int64_t n1, int64_t n2, int64_t n3, int r, int mode, double* rhs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRITD_H */

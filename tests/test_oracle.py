@@ -1,0 +1,120 @@
+"""CPU tests of the oracle: definitional pins from the reference, algebraic identities the CUDA
+design relies on, and the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+import make_golden
+import tritd_oracle as orc
+import tritd_oracle_sharded as orcs
+from conftest import rel_err
+from tritd import synth
+
+
+def _rand_factors(n1, n2, n3, r, seed=0):
+    rng = np.random.default_rng(seed)
+    return (np.asfortranarray(rng.standard_normal((n1, r, r))), np.asfortranarray(rng.standard_normal((r, n2, r))),
+            np.asfortranarray(rng.standard_normal((r, r, n3))))
+
+
+@pytest.mark.parametrize("shape,r", [((7, 6, 5), 3), ((4, 9, 3), 2), ((5, 5, 5), 1)])
+def test_definitional_loops(shape, r):
+    """Vectorised buildF/G/H/triple_product == the scalar loops the reference holds as comments
+    (buildF.m:5-16, buildG.m:5-16, buildH.m:5-16, origin_triple_tensor/triple_decomp_ADMM.m:125-143)."""
+    A, B, C = _rand_factors(*shape, r)
+    assert np.array_equal(orc.buildF(B, C), orc.buildF_loops(B, C))
+    assert np.array_equal(orc.buildG(A, C), orc.buildG_loops(A, C))
+    assert np.array_equal(orc.buildH(A, B), orc.buildH_loops(A, B))
+    assert rel_err(orc.triple_product(A, B, C), orc.triple_product_loops(A, B, C)) < 1e-14
+
+
+def test_unfold_index_maps():
+    n1, n2, n3 = 4, 3, 5
+    X = np.asfortranarray(np.arange(n1 * n2 * n3, dtype=float).reshape((n1, n2, n3), order="F"))
+    X2, X3 = orc.unfold(X, 2), orc.unfold(X, 3)
+    for i in range(n1):
+        for j in range(n2):
+            for t in range(n3):
+                assert orc.unfold(X, 1)[i, j + t * n2] == X[i, j, t]
+                assert X2[j, i + t * n1] == X[i, j, t]
+                assert X3[t, i + j * n1] == X[i, j, t]
+    with pytest.raises(ValueError):
+        orc.unfold(X, 4)
+
+
+def test_cp_identities():
+    """X_(k) M' is an MTTKRP and M M' is a Hadamard product of small Grams."""
+    n1, n2, n3, r = 9, 8, 7, 3
+    A, B, C = _rand_factors(n1, n2, n3, r, 1)
+    T = np.asfortranarray(np.random.default_rng(2).standard_normal((n1, n2, n3)))
+    A1, B2, C3 = orc.factors_to_unfolded(A, B, C)
+    F, G, H = orc.buildF(B, C), orc.buildG(A, C), orc.buildH(A, B)
+    assert rel_err(orc.mttkrp(T, A1, B2, C3, 1), orc.unfold(T, 1) @ F.T) < 1e-13
+    assert rel_err(orc.mttkrp(T, A1, B2, C3, 2), orc.unfold(T, 2) @ G.T) < 1e-13
+    assert rel_err(orc.mttkrp(T, A1, B2, C3, 3), orc.unfold(T, 3) @ H.T) < 1e-13
+    assert rel_err((B2.T @ B2) * (C3.T @ C3), F @ F.T) < 1e-13
+    assert rel_err((A1.T @ A1) * (C3.T @ C3), G @ G.T) < 1e-13
+    assert rel_err((A1.T @ A1) * (B2.T @ B2), H @ H.T) < 1e-13
+
+
+def test_soft_threshold_and_pinv():
+    x = np.array([-3.0, -1.0, -0.5, 0.0, 0.5, 1.0, 3.0])
+    assert np.array_equal(orc.soft_threshold(x, 1.0), np.array([-2.0, 0.0, 0.0, 0.0, 0.0, 0.0, 2.0]))
+    G = np.diag([1.0, 1e-20, 2.0])
+    P = orc.pinv_matlab(G)
+    assert P[1, 1] == 0.0 and P[0, 0] == 1.0 and P[2, 2] == 0.5       # MATLAB cutoff zeroes the tiny one
+    assert orc.pinv_truncations(G) == 1
+
+
+def test_missing_opts_field_is_an_error():
+    w = synth.make_config("cfg1", shrink=(6, 5, 4))
+    o = dict(w["opts"]); del o["lambda2"]
+    with pytest.raises(KeyError, match="lambda2"):
+        orc.triple_decomp_ADMM(w["D"], 2, o, *synth.init_factors(6, 5, 4, 2, 0))
+
+
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_oracle_matches_golden(name, golden_dir):
+    """The committed vectors pin the oracle (regenerated inputs, stored outputs)."""
+    D, r, o, A0, B0, C0 = make_golden.case_inputs(name)
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    assert np.allclose([D.sum(), np.abs(D).sum()], g["D_checksum"], rtol=1e-12)
+    A, B, C, O, eh = orc.triple_decomp_ADMM(D, r, o, A0, B0, C0)
+    assert len(eh) == len(g["errHist"])
+    assert rel_err(eh, g["errHist"]) < 1e-10
+    for x, key in ((A, "A"), (B, "B"), (C, "C"), (O, "O")):
+        assert rel_err(x, g[key]) < 1e-9, key
+
+
+def test_stop_rule_fires_with_margin(golden_dir):
+    g = np.load(os.path.join(golden_dir, "stop_30x30x30_r3.npz"))
+    eh = g["errHist"]
+    assert 1 < len(eh) < 100
+    rel = np.abs(np.diff(eh)) / eh[:-1]
+    assert rel[-1] < 0.5 * 2e-2 and np.all(rel[:-1] > 1.05 * 2e-2)      # robust to 1e-12-level noise
+
+
+def test_sharded_restatement_equals_plain_oracle():
+    """The CP / Hadamard / shared-P form the CUDA library uses is the same algorithm."""
+    D, r, o, A0, B0, C0 = make_golden.case_inputs("small_40x36x24_r5")
+    o["maxIter"] = 8
+    A, B, C, O, eh = orc.triple_decomp_ADMM(D, r, o, A0, B0, C0)
+    A1, B2, C3, O2, eh2 = orcs.admm_sharded(D, r, o, *orc.factors_to_unfolded(A0, B0, C0))
+    assert rel_err(eh2, eh) < 1e-10
+    assert rel_err(A1, orc.unfold(A, 1)) < 1e-9 and rel_err(B2, orc.unfold(B, 2)) < 1e-9
+    assert rel_err(C3, orc.unfold(C, 3)) < 1e-9 and rel_err(O2, O) < 1e-9
+
+
+def test_als_runs_and_decreases():
+    w = synth.make_config("cfg1", shrink=(12, 11, 10), with_truth=True)
+    A, B, C, eh = orc.triple_decomp_ALS(w["L0"], 5, dict(maxIter=15, tol=0.0), w["A0"], w["B0"], w["C0"])
+    assert len(eh) == 15 and eh[-1] < eh[0]
+
+
+def test_synth_slabs_and_bounds():
+    full = synth.make_lowrank_sparse(20, 10, 2000, 2, 0.1, 7)
+    part = synth.make_lowrank_sparse(20, 10, 2000, 2, 0.1, 7, t0=0, t1=2000)
+    assert np.array_equal(full, part)
+    assert synth.slab_bounds(300, 8) == [(0, 38), (38, 76), (76, 114), (114, 152), (152, 189), (189, 226), (226, 263), (263, 300)]
+    assert synth.slab_bounds(5, 2) == [(0, 3), (3, 5)]

@@ -1,0 +1,50 @@
+// Standalone L2 helpers of the reference (API completeness; the solver itself never
+// materialises these): unfold.m:1-14, buildF/G/H.m:17-21, soft_threshold.m:2.
+// All are single-pass, coalesced, HBM-bound kernels.
+#pragma once
+#include "common.cuh"
+
+namespace tritd {
+
+// Batched 2-D transpose through a padded 32x32 shared tile:
+//   out[b][c][r] = in[b][r][c]   (r fastest on input, c fastest on output)
+// unfold(X,2): rows = n1, cols = n2, batch = n3;  unfold(X,3): rows = n1*n2, cols = n3, batch = 1.
+__global__ void __launch_bounds__(256) k_transpose(const double* in, double* out, long rows, long cols) {
+    __shared__ double tile[32][33];
+    const size_t boff = (size_t)blockIdx.z * rows * cols;
+    const long r0 = (long)blockIdx.x * 32, c0 = (long)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const long r = r0 + tx, c = c0 + k;
+        if (r < rows && c < cols) tile[k][tx] = in[boff + (size_t)c * rows + r];
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const long c = c0 + tx, r = r0 + k;
+        if (r < rows && c < cols) out[boff + (size_t)r * cols + c] = tile[tx][k];
+    }
+}
+
+// Transposed Khatri-Rao product, the common form of buildF/G/H:
+//   out[k + R*(a + na*b)] = Xa[a][k] * Xb[b][k]      (Xa: na x RS, Xb: nb x RS row-major)
+// buildF: (Xa,Xb) = (B2,C3); buildG: (A1,C3); buildH: (A1,B2).
+__global__ void __launch_bounds__(256) k_khatri_rao_t(const double* Xa, const double* Xb, double* out, long na,
+                                                      long nb, int R, int RS) {
+    const size_t total = (size_t)R * na * nb;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        const int k = (int)(e % R);
+        const size_t col = e / R;
+        const long aa = (long)(col % na), bb = (long)(col / na);
+        out[e] = Xa[(size_t)aa * RS + k] * Xb[(size_t)bb * RS + k];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_soft_threshold(const double* x, double* out, size_t n, double lam) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const double v = x[i];
+        const double mx = fmax(fabs(v) - lam, 0.0);
+        out[i] = v > 0.0 ? mx : (v < 0.0 ? -mx : 0.0);
+    }
+}
+
+}  // namespace tritd

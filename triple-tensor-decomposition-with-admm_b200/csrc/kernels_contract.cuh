@@ -1,0 +1,350 @@
+// Mode-wise contractions X_(k) * M^T of the TriTD-ADMM factor updates
+// (reference: fast_robust_triple_tensor/triple_decomp_ADMM.m:73-95, the dgemm
+// calls at :78, :86, :93), as FP64 DMMA kernels fed by TMA.  The design
+// matrices F/G/H (buildF/G/H, :132-160) and the permuted unfold copies
+// (:97-109) are never materialised: with A1 = unfold(A,1), B2 = unfold(B,2),
+// C3 = unfold(C,3) (n x R, R = r^2)
+//     X1*F' [i,k] = sum_{j,t} T(i,j,t) B2(j,k) C3(t,k)            (k_mttkrp1)
+//     P[t][j][k]  = sum_i     T(i,j,t) A1(i,k)                     (k_ppass)
+//     X2*G' [j,k] = sum_t C3(t,k) P[t][j][k]                       (k_rhsB)
+//     X3*H' [t,k] = sum_j B2(j,k) P[t][j][k]                       (k_rhsC)
+// P depends on T and the *new* A only, so one pass over T serves both the B and
+// the C update (Gauss-Seidel order is preserved: k_rhsC runs after B is solved).
+//
+// Device layout: every N-sized array is column-major n1 x n2 x n3 with leading
+// dimension ld1 = n1 rounded up to even (16-byte columns for TMA / v2 access);
+// factor matrices are row-major n x RS with RS = R rounded up to a multiple of 8,
+// zero padded.
+#pragma once
+#include "common.cuh"
+
+namespace tritd {
+
+constexpr int kCW = 8;            // consumer warps per contraction CTA
+constexpr int kBoxRows = 32;      // rows (j) of one TMA box
+constexpr int kBoxBytes = kBoxRows * 16 * 8;   // [32][16] doubles = 4 KB
+constexpr int kStages = 4;
+constexpr int kPJ = kBoxRows + 8; // pitch of the transposed factor chunk; == 8 (mod 16) -> conflict-free LDS.128
+
+// ---------------------------------------------------------------------------
+// k_mttkrp1: partial RHS of the A update.
+// CTA = 8 consumer warps x 16 rows i (one 128-row i-tile) + 1 TMA producer warp.
+// Work unit = (i-tile, j-chunk of 32, slice t): 8 TMA boxes [32 j][16 i], 128B-swizzled.
+// Units are linearised u = (itile * n_jc + jc) * n3 + t and each CTA takes one
+// contiguous range, so the split is balanced to one unit.  A CTA's range touches at
+// most two i-tiles; it writes one partial per touched tile into slot 0 / slot 1.
+// MMA roles: M = i (two m-tiles: even/odd i of the warp's 16), K = j, N = k.
+// ---------------------------------------------------------------------------
+struct Mttkrp1Args {
+    const double* B2;   // [n2][RS]
+    const double* C3;   // [n3][RS]
+    double* part;       // [grid][2][128][RS]
+    const int* stop;
+    int n1, n2, n3, RS;
+    int n_it, n_jc;     // tiles along i (128) and j (32)
+    long units;         // n_it * n_jc * n3
+};
+
+template <int NT>
+__global__ void __launch_bounds__((kCW + 1) * 32, 1)
+k_mttkrp1(const __grid_constant__ CUtensorMap mapT, const Mttkrp1Args a) {
+    if (*a.stop) return;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double* stage_base = reinterpret_cast<double*>(smem_raw);                       // kStages * 8 boxes
+    double* B2T = reinterpret_cast<double*>(smem_raw + kStages * kCW * kBoxBytes);  // [NT*8][kPJ]
+    uint64_t* full = reinterpret_cast<uint64_t*>(B2T + NT * 8 * kPJ);
+    uint64_t* empty = full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const long u0 = a.units * blockIdx.x / gridDim.x;
+    const long u1 = a.units * (blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kCW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long per_it = (long)a.n_jc * a.n3;
+    if (warp == kCW) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            tma_prefetch_desc(&mapT);
+            int s = 0; uint32_t ph = 0;
+            for (long u = u0; u < u1; ++u) {
+                const int it = (int)(u / per_it);
+                const long rem = u - it * per_it;
+                const int jc = (int)(rem / a.n3), t = (int)(rem - (long)jc * a.n3);
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], kCW * kBoxBytes);
+                double* dst = stage_base + (size_t)s * kCW * (kBoxBytes / 8);
+#pragma unroll
+                for (int w = 0; w < kCW; ++w)
+                    tma_load_3d(dst + w * (kBoxBytes / 8), &mapT, &full[s], it * 128 + w * 16, jc * kBoxRows, t);
+                if (++s == kStages) { s = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    double acc[2][NT][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+
+    int s = 0; uint32_t ph = 0;
+    int cur_it = -1, cur_jc = -1, slot = 0;
+    double* part_cta = a.part + (size_t)blockIdx.x * 2 * 128 * a.RS;
+
+    auto flush = [&](int sl) {
+        double* p = part_cta + (size_t)sl * 128 * a.RS;
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+                const int il = warp * 16 + 2 * g + m;
+                *reinterpret_cast<double2*>(p + (size_t)il * a.RS + 8 * n + 2 * tig) =
+                    make_double2(acc[m][n][0], acc[m][n][1]);
+                acc[m][n][0] = acc[m][n][1] = 0.0;
+            }
+    };
+
+    for (long u = u0; u < u1; ++u) {
+        const int it = (int)(u / per_it);
+        const long rem = u - it * per_it;
+        const int jc = (int)(rem / a.n3), t = (int)(rem - (long)jc * a.n3);
+        if (it != cur_it) {
+            if (cur_it >= 0) { flush(slot); slot = 1; }
+            cur_it = it; cur_jc = -1;
+        }
+        if (jc != cur_jc) {
+            // (re)load the transposed chunk B2T[k][j] = B2[jc*32 + j][k]; consumer-only barrier
+            asm volatile("bar.sync 1, %0;" ::"n"(kCW * 32));
+            for (int e = threadIdx.x; e < NT * 8 * kBoxRows; e += kCW * 32) {
+                const int j = e / (NT * 8), k = e - j * (NT * 8);
+                const int jj = jc * kBoxRows + j;
+                B2T[k * kPJ + j] = (jj < a.n2) ? a.B2[(size_t)jj * a.RS + k] : 0.0;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kCW * 32));
+            cur_jc = jc;
+        }
+        double c3s[NT];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) c3s[n] = __ldg(a.C3 + (size_t)t * a.RS + 8 * n + g);
+
+        mbar_wait(&full[s], ph);
+        const double* box = stage_base + (size_t)s * kCW * (kBoxBytes / 8) + warp * (kBoxBytes / 8);
+        if (it * 128 + warp * 16 < a.n1) {
+#pragma unroll
+            for (int jg = 0; jg < kBoxRows / 8; ++jg) {
+                // k-step e covers j = jg*8 + 2*tig + e; lane's two doubles are i = 2g (m-tile 0), 2g+1 (m-tile 1)
+                const double2 a0 = lds_swz128(box, jg * 8 + 2 * tig, g);
+                const double2 a1 = lds_swz128(box, jg * 8 + 2 * tig + 1, g);
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const double2 b = *reinterpret_cast<const double2*>(B2T + (8 * n + g) * kPJ + jg * 8 + 2 * tig);
+                    const double b0 = b.x * c3s[n], b1 = b.y * c3s[n];
+                    dmma884(acc[0][n][0], acc[0][n][1], a0.x, b0);
+                    dmma884(acc[1][n][0], acc[1][n][1], a0.y, b0);
+                    dmma884(acc[0][n][0], acc[0][n][1], a1.x, b1);
+                    dmma884(acc[1][n][0], acc[1][n][1], a1.y, b1);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == kStages) { s = 0; ph ^= 1; }
+    }
+    if (cur_it >= 0) flush(slot);
+}
+
+// Sum the per-CTA partials of k_mttkrp1 in CTA order (deterministic).  One thread per
+// (i, k); CTA c contributes to row i's tile `it` through slot 0 if its range starts in
+// `it`, through slot 1 if it started in the previous tile and crossed into `it`.
+__global__ void k_mttkrp1_reduce(const double* part, double* rhs, int n1, int RS, int n_it, int n_jc, int n3,
+                                 int grid_m, const int* stop) {
+    if (*stop) return;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n1 * RS) return;
+    const int i = (int)(idx / RS), k = (int)(idx - (long)i * RS);
+    const int it = i >> 7, il = i & 127;
+    const long per_it = (long)n_jc * n3, units = per_it * n_it;
+    double sum = 0.0;
+    for (int c = 0; c < grid_m; ++c) {
+        const long u0 = units * c / grid_m, u1 = units * (c + 1) / grid_m;
+        if (u1 <= u0) continue;
+        const int it0 = (int)(u0 / per_it), it1 = (int)((u1 - 1) / per_it);
+        if (it < it0 || it > it1) continue;
+        const int sl = it - it0;   // 0 or 1 (a range never spans three tiles: see host-side grid choice)
+        sum += part[((size_t)c * 2 + sl) * 128 * RS + (size_t)il * RS + k];
+    }
+    rhs[idx] = sum;
+}
+
+// ---------------------------------------------------------------------------
+// k_ppass: P[t][j][k] = sum_i T(i,j,t) * A1(i,k)      (shared by the B and C updates)
+// CTA = 8 consumer warps + 1 TMA producer warp.  Row blocks rb = t * n_jb + jb (32 rows j
+// of slice t); a work unit is 8 consecutive row blocks, one per warp.  Per K-chunk of 16 i
+// a stage holds 8 T boxes [32 j][16 i] and one factor box A1T[RS k][16 i], all 128B-swizzled.
+// MMA roles: M = j (4 m-tiles per warp, rows permuted by rho8), K = i, N = k (columns permuted by rho8).
+// ---------------------------------------------------------------------------
+struct PpassArgs {
+    double* P;          // [n3][n2][RS]
+    const int* stop;
+    int n1, n2, n3, RS;
+    int n_jb;           // ceil(n2 / 32)
+    long n_rb;          // n3 * n_jb
+    long units;         // ceil(n_rb / 8)
+};
+
+template <int NT>
+__global__ void __launch_bounds__((kCW + 1) * 32, 1)
+k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapA1T, const PpassArgs a) {
+    if (*a.stop) return;
+    constexpr int kStageDoubles = kCW * (kBoxBytes / 8) + NT * 8 * 16;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double* stage_base = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + (size_t)kStages * kStageDoubles);
+    uint64_t* empty = full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int nkc = (a.n1 + 15) >> 4;
+    const long u0 = a.units * blockIdx.x / gridDim.x;
+    const long u1 = a.units * (blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kCW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kCW) {
+        if (lane == 0) {
+            tma_prefetch_desc(&mapT);
+            tma_prefetch_desc(&mapA1T);
+            int s = 0; uint32_t ph = 0;
+            for (long u = u0; u < u1; ++u) {
+                const long rb0 = u * kCW;
+                const int nvalid = (int)min((long)kCW, a.n_rb - rb0);
+                for (int kc = 0; kc < nkc; ++kc) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], nvalid * kBoxBytes + NT * 8 * 128);
+                    double* dst = stage_base + (size_t)s * kStageDoubles;
+                    for (int w = 0; w < nvalid; ++w) {
+                        const long rb = rb0 + w;
+                        const int t = (int)(rb / a.n_jb), jb = (int)(rb - (long)t * a.n_jb);
+                        tma_load_3d(dst + w * (kBoxBytes / 8), &mapT, &full[s], kc * 16, jb * kBoxRows, t);
+                    }
+                    tma_load_2d(dst + kCW * (kBoxBytes / 8), &mapA1T, &full[s], kc * 16, 0);
+                    if (++s == kStages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+
+    int s = 0; uint32_t ph = 0;
+    const int rg = rho8(g);
+    for (long u = u0; u < u1; ++u) {
+        const long rb = u * kCW + warp;
+        const bool valid = rb < a.n_rb;
+        double acc[4][NT][2];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+
+        for (int kc = 0; kc < nkc; ++kc) {
+            mbar_wait(&full[s], ph);
+            const double* st = stage_base + (size_t)s * kStageDoubles;
+            const double* box = st + warp * (kBoxBytes / 8);
+            const double* fbox = st + kCW * (kBoxBytes / 8);
+            if (valid) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    // k-steps (h,e) cover i = kc*16 + 8h + 2*tig + e
+                    double2 af[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) af[m] = lds_swz128(box, 8 * m + rg, 4 * h + tig);
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        const double2 b = lds_swz128(fbox, 8 * n + rg, 4 * h + tig);
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            dmma884(acc[m][n][0], acc[m][n][1], af[m].x, b.x);
+                            dmma884(acc[m][n][0], acc[m][n][1], af[m].y, b.y);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+        if (valid) {
+            const int t = (int)(rb / a.n_jb), jb = (int)(rb - (long)t * a.n_jb);
+            // C fragment: row = 8m + rho8(g); columns n = 2*tig + c map to k = 8n' + rho8(2*tig + c) = 8n' + tig + 4c
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int j = jb * kBoxRows + 8 * m + rg;
+                if (j < a.n2) {
+                    double* p = a.P + ((size_t)t * a.n2 + j) * a.RS;
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        p[8 * n + tig] = acc[m][n][0];
+                        p[8 * n + tig + 4] = acc[m][n][1];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// rhsB[j][k] = sum_t C3[t][k] * P[t][j][k]: one thread per (j,k), t in order.
+__global__ void k_rhsB(const double* P, const double* C3, double* rhsB, int n2, int n3, int RS, const int* stop) {
+    if (*stop) return;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nrk = (long)n2 * RS;
+    if (idx >= nrk) return;
+    const int k = (int)(idx % RS);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int t = 0;
+    for (; t + 3 < n3; t += 4) {
+        s0 += C3[(size_t)t * RS + k] * P[(size_t)t * nrk + idx];
+        s1 += C3[(size_t)(t + 1) * RS + k] * P[(size_t)(t + 1) * nrk + idx];
+        s2 += C3[(size_t)(t + 2) * RS + k] * P[(size_t)(t + 2) * nrk + idx];
+        s3 += C3[(size_t)(t + 3) * RS + k] * P[(size_t)(t + 3) * nrk + idx];
+    }
+    for (; t < n3; ++t) s0 += C3[(size_t)t * RS + k] * P[(size_t)t * nrk + idx];
+    rhsB[idx] = (s0 + s1) + (s2 + s3);
+}
+
+// rhsC[t][k] = sum_j B2[j][k] * P[t][j][k]: one CTA per slice t, 256 threads = 8 j-lanes x 32 k
+// (RS/32 column passes), fixed-order tree over the j-lanes.
+__global__ void __launch_bounds__(256) k_rhsC(const double* P, const double* B2, double* rhsC, int n2, int n3,
+                                               int RS, const int* stop) {
+    if (*stop) return;
+    __shared__ double red[8][33];
+    const int t = blockIdx.x;
+    const int kl = threadIdx.x & 31, jl = threadIdx.x >> 5;
+    for (int k0 = 0; k0 < RS; k0 += 32) {
+        const int k = k0 + kl;
+        double s = 0.0;
+        if (k < RS)
+            for (int j = jl; j < n2; j += 8) s += B2[(size_t)j * RS + k] * P[((size_t)t * n2 + j) * RS + k];
+        red[jl][kl] = s;
+        __syncthreads();
+        if (jl == 0 && k < RS) {
+            double v = ((red[0][kl] + red[1][kl]) + (red[2][kl] + red[3][kl])) +
+                       ((red[4][kl] + red[5][kl]) + (red[6][kl] + red[7][kl]));
+            rhsC[(size_t)t * RS + k] = v;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace tritd

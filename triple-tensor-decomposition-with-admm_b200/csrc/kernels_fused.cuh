@@ -1,0 +1,220 @@
+// The fused HBM-bound kernel of one TriTD-ADMM iteration: reconstruction
+// L = triple_product(A,B,C) on the fly (never stored), O update, soft-threshold
+// of E, dual updates, next-iteration target T and both residual norms.
+// Reference: fast_robust_triple_tensor/triple_decomp_ADMM.m:38-59 and :33
+// (triple_product.m:6-7, soft_threshold.m:2), same statement order and the same
+// floating-point association as the MATLAB expressions; every add/mul/div is an
+// explicit round-to-nearest intrinsic so nvcc cannot contract them into FMAs.
+#pragma once
+#include "common.cuh"
+
+namespace tritd {
+
+// Iteration scalars, kept on the device so a whole iteration replays without the host.
+struct IterState {
+    double muL, muO, muL_max, muO_max, rhoL, rhoO, lambda, tol, normD;
+    double rmuL, rmuO, thr, musum, rmuL_next;   // (1/muL), (1/muO), lambda/muO, muL+muO, 1/muL of the next iteration
+    int k;         // iterations completed
+    int stop;      // stopping rule fired or maxIter reached: all later launches are no-ops
+    int status;    // != 0: numerical failure (non-positive Cholesky pivot), see tritd.h
+    int maxIter;
+};
+
+__host__ __device__ inline void iter_state_derive(IterState& s) {
+    s.rmuL = 1.0 / s.muL;
+    s.rmuO = 1.0 / s.muO;
+    s.thr = s.lambda / s.muO;
+    s.musum = s.muL + s.muO;
+    const double nL = s.muL * s.rhoL;
+    s.rmuL_next = 1.0 / (nL < s.muL_max ? nL : s.muL_max);
+}
+
+struct FusedArgs {
+    const double* D;
+    double *E, *YL, *YO, *T, *O;       // mode 0: all N-sized state arrays; mode 1: O = output L, others unused
+    const double *A1, *B2, *C3;        // [n][RS]
+    const IterState* st;
+    double* norm_part;                 // [grid][2]
+    int n1, n2, n3, ld1, RS;
+    int n_it, n_jc, gi;                // i-tiles (128), j-chunks (32), CTAs per i-tile
+};
+
+// One element of triple_decomp_ADMM.m:41-53 and the next T (:33).
+__device__ __forceinline__ void admm_point(const IterState& p, double d, double l, double& yl, double& e, double& yo,
+                                           double& o, double& tn, double& sL, double& sO) {
+    const double dl = __dsub_rn(d, l);                                   // D - L
+    const double r1 = __dadd_rn(dl, __dmul_rn(p.rmuL, yl));              // R1 = D - L + (1/muL)*Y_L
+    const double my = __dmul_rn(p.rmuO, yo);                             // (1/muO)*Y_O
+    const double r2 = __dsub_rn(e, my);                                  // R2 = E - (1/muO)*Y_O
+    o = __ddiv_rn(__dadd_rn(__dmul_rn(p.muL, r1), __dmul_rn(p.muO, r2)), p.musum);
+    const double r3 = __dadd_rn(o, my);                                  // R3 = O + (1/muO)*Y_O
+    const double mx = fmax(__dsub_rn(fabs(r3), p.thr), 0.0);
+    const double en = r3 > 0.0 ? mx : (r3 < 0.0 ? -mx : 0.0);            // sign(R3).*max(|R3|-lambda/muO,0)
+    const double resL = __dsub_rn(dl, o);                                // D - L - O
+    const double resO = __dsub_rn(o, en);                                // O - E
+    yl = __dadd_rn(yl, __dmul_rn(p.muL, resL));
+    yo = __dadd_rn(yo, __dmul_rn(p.muO, resO));
+    e = en;
+    tn = __dadd_rn(__dsub_rn(d, o), __dmul_rn(p.rmuL_next, yl));         // next T = D - O + (1/muL')*Y_L
+    sL = fma(resL, resL, sL);
+    sO = fma(resO, resO, sO);
+}
+
+template <int KS> struct FusedCfg {
+    static constexpr int PL = (KS & 1) ? 4 * KS : 4 * KS + 4;   // pitch of the B2 chunk: == 4 (mod 8) doubles
+    static constexpr int kMinBlocks = KS <= 8 ? 2 : 1;
+};
+
+// CTA = 8 warps x 16 rows i (i-tile of 128).  CTA c owns i-tile c % n_it and a contiguous
+// range of column blocks v = jc * n3 + t (32 columns j of slice t).  Each warp walks the
+// block in four groups of 8 columns; per group it forms a 16 x 8 patch of L with 2*KS DMMAs
+// (M = i, two m-tiles = even/odd i; N = j; K = k) whose accumulator layout is exactly the
+// 16-byte-vector layout of the element-wise pass, so the five state arrays are touched with
+// 128-byte-per-row coalesced v2 accesses straight from/to registers.
+template <int KS, int MODE>
+__global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const FusedArgs a) {
+    constexpr int PL = FusedCfg<KS>::PL;
+    if (MODE == 0 && a.st->stop) return;
+    __shared__ double B2s[32 * PL];
+    __shared__ double red[64];
+    __shared__ IterState prm_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const int it = blockIdx.x % a.n_it, x = blockIdx.x / a.n_it;
+    const long V = (long)a.n_jc * a.n3;
+    const long v0 = V * x / a.gi, v1 = V * (x + 1) / a.gi;
+    const int i0 = it * 128 + warp * 16 + 2 * g;          // this lane's even row; it also owns i0 + 1
+    const bool i_ok = i0 < a.ld1;
+
+    if (MODE == 0 && threadIdx.x == 0) prm_s = *a.st;
+
+    // rows of A1 this lane feeds into the A fragments (clamped; rows >= n1 are zeroed below)
+    const double* a1r0 = a.A1 + (size_t)min(i0, a.n1 - 1) * a.RS + tig;
+    const double* a1r1 = a.A1 + (size_t)min(i0 + 1, a.n1 - 1) * a.RS + tig;
+    const double z0 = (i0 < a.n1) ? 1.0 : 0.0, z1 = (i0 + 1 < a.n1) ? 1.0 : 0.0;
+
+    struct Buf { double2 d[2], yl[2], e[2], yo[2]; };
+    auto load = [&](Buf& b, long v, int jg) {
+        const int jc = (int)(v / a.n3), t = (int)(v - (long)jc * a.n3);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int j = jc * 32 + jg * 8 + 2 * tig + c;
+            const bool ok = i_ok && j < a.n2;
+            const size_t off = ((size_t)t * a.n2 + j) * a.ld1 + i0;
+            b.d[c] = ok ? ldg_stream2(a.D + off) : make_double2(0.0, 0.0);
+            if (MODE == 0) {
+                b.yl[c] = ok ? ldg_stream2(a.YL + off) : make_double2(0.0, 0.0);
+                b.e[c] = ok ? ldg_stream2(a.E + off) : make_double2(0.0, 0.0);
+                b.yo[c] = ok ? ldg_stream2(a.YO + off) : make_double2(0.0, 0.0);
+            }
+        }
+    };
+
+    double sL = 0.0, sO = 0.0;
+    int cur_jc = -1;
+    Buf cur, nxt;
+    if (MODE == 0 && v0 < v1) load(cur, v0, 0);
+
+    for (long v = v0; v < v1; ++v) {
+        const int jc = (int)(v / a.n3), t = (int)(v - (long)jc * a.n3);
+        if (jc != cur_jc) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < 32 * 4 * KS; e += 256) {
+                const int j = e / (4 * KS), k = e - j * (4 * KS);
+                const int jj = jc * 32 + j;
+                B2s[j * PL + k] = (jj < a.n2) ? a.B2[(size_t)jj * a.RS + k] : 0.0;
+            }
+            __syncthreads();
+            cur_jc = jc;
+        }
+        // A fragments with C3[t,:] folded in: aS[m][s] = A1(i0+m, 4s+tig) * C3(t, 4s+tig)  (L1/L2-resident factors)
+        double aS[2][KS];
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const double c3 = __ldg(a.C3 + (size_t)t * a.RS + 4 * s + tig);
+            aS[0][s] = __ldg(a1r0 + 4 * s) * c3 * z0;
+            aS[1][s] = __ldg(a1r1 + 4 * s) * c3 * z1;
+        }
+
+#pragma unroll
+        for (int jg = 0; jg < 4; ++jg) {
+            if (MODE == 0) {
+                if (jg < 3) load(nxt, v, jg + 1);
+                else if (v + 1 < v1) load(nxt, v + 1, 0);
+            }
+            double l[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                const double b = B2s[(jg * 8 + g) * PL + 4 * s + tig];
+                dmma884(l[0][0], l[0][1], aS[0][s], b);
+                dmma884(l[1][0], l[1][1], aS[1][s], b);
+            }
+            // l[m][c] = L(i0 + m, jc*32 + jg*8 + 2*tig + c, t)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int j = jc * 32 + jg * 8 + 2 * tig + c;
+                if (!(i_ok && j < a.n2)) continue;
+                const size_t off = ((size_t)t * a.n2 + j) * a.ld1 + i0;
+                if (MODE == 1) {
+                    stg_stream2(a.O + off, make_double2(l[0][c], l[1][c]));
+                } else {
+                    double2 o, tn;
+                    admm_point(prm_s, cur.d[c].x, l[0][c], cur.yl[c].x, cur.e[c].x, cur.yo[c].x, o.x, tn.x, sL, sO);
+                    admm_point(prm_s, cur.d[c].y, l[1][c], cur.yl[c].y, cur.e[c].y, cur.yo[c].y, o.y, tn.y, sL, sO);
+                    stg_stream2(a.O + off, o);
+                    stg_stream2(a.E + off, cur.e[c]);
+                    stg_stream2(a.YL + off, cur.yl[c]);
+                    stg_stream2(a.YO + off, cur.yo[c]);
+                    stg_stream2(a.T + off, tn);
+                }
+            }
+            if (MODE == 0) cur = nxt;
+        }
+    }
+    if (MODE == 0) {
+        block_sum2(sL, sO, red);
+        if (threadIdx.x == 0) { a.norm_part[2 * blockIdx.x] = sL; a.norm_part[2 * blockIdx.x + 1] = sO; }
+    }
+}
+
+// Fixed-order sum of `n` pairs (per-CTA partials) into out[0..1]; one CTA.
+__global__ void __launch_bounds__(256) k_sum_pairs(const double* part, int n, double* out, const int* stop) {
+    if (stop && *stop) return;
+    __shared__ double red[64];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) { a += part[2 * i]; b += part[2 * i + 1]; }
+    block_sum2(a, b, red);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+
+// Per-CTA partial of sum(x^2) over a padded N-array (pad entries are zero).
+__global__ void __launch_bounds__(256) k_sumsq_part(const double* x, size_t n, double* part) {
+    __shared__ double red[64];
+    double s = 0.0, z = 0.0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) s = fma(x[i], x[i], s);
+    block_sum2(s, z, red);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = s; part[2 * blockIdx.x + 1] = 0.0; }
+}
+
+// errHist / mu schedule / stopping rule (triple_decomp_ADMM.m:56-65), one thread.
+// norms[0..1] = global sum(resL^2), sum(resO^2) of the iteration just finished.
+__global__ void k_finalize(IterState* st, const double* norms, double* errHist, double* errL, double* errO) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (st->stop) return;
+    const int k = st->k;
+    st->muL = fmin(st->muL * st->rhoL, st->muL_max);
+    st->muO = fmin(st->muO * st->rhoO, st->muO_max);
+    iter_state_derive(*st);
+    const double eL = sqrt(norms[0]) / st->normD, eO = sqrt(norms[1]) / st->normD;
+    errL[k] = eL; errO[k] = eO; errHist[k] = eL + eO;
+    st->k = k + 1;
+    if (k >= 1 && fabs(errHist[k] - errHist[k - 1]) < st->tol * errHist[k - 1]) st->stop = 1;
+    if (k + 1 >= st->maxIter) st->stop = 1;
+}
+
+__global__ void k_set_normD(IterState* st, const double* sumsq) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) st->normD = sqrt(sumsq[0]);
+}
+
+}  // namespace tritd

@@ -1,0 +1,920 @@
+// libtritd: C ABI (include/tritd.h), contexts, device state and the iteration driver of
+// the B200-native TriTD-ADMM path.  Reference call being replaced:
+//   [A,B,C,O,errHist] = triple_decomp_ADMM(D, r, opts)
+//   fast_robust_triple_tensor/triple_decomp_ADMM.m:1-70
+#include "../../include/tritd.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels_aux.cuh"
+#include "kernels_contract.cuh"
+#include "kernels_fused.cuh"
+#include "kernels_solve.cuh"
+
+using namespace tritd;
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                  \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(TRITD_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define ST_TRY(expr)                 \
+    do {                             \
+        int _s = (expr);             \
+        if (_s != TRITD_OK) return _s; \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved at run time (single-rank use needs no NCCL at all; in a process that
+// already loaded torch this resolves to torch's bundled libnccl.so.2)
+// ---------------------------------------------------------------------------
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.h) return TRITD_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(TRITD_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define NCCL_SYM(field, name)                                                     \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                                    \
+    if (!g_nccl.field) return fail(TRITD_ERR_NCCL, "libnccl: missing symbol %s", name);
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+    NCCL_SYM(CommInitRank, "ncclCommInitRank");
+    NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    NCCL_SYM(AllReduce, "ncclAllReduce");
+    NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef NCCL_SYM
+    g_nccl.h = h;
+    return TRITD_OK;
+}
+
+#define NCCL_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        ncclResult_t _r = (expr);                                                                            \
+        if (_r != ncclSuccess)                                                                               \
+            return fail(TRITD_ERR_NCCL, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, g_nccl.GetErrorString(_r)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct tritd_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    ncclComm_t comm = nullptr;
+    int num_sms = 0;
+    int64_t launches = 0;
+    PFN_encodeTiled encode = nullptr;
+};
+
+struct RankCfg { int NT, KS; };
+static RankCfg rank_cfg(int r) {
+    const int R = r * r;
+    return RankCfg{((R + 7) / 8), (R + 3) / 4};
+}
+
+static int ctx_common_init(tritd_ctx* c, int device) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(TRITD_ERR_CUDA, "no CUDA device available (%s); libtritd has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(TRITD_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    c->device = device;
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(TRITD_ERR_CUDA, "device %d is sm_%d%d; libtritd is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    c->num_sms = prop.multiProcessorCount;
+    CU_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(TRITD_ERR_CUDA, "cuTensorMapEncodeTiled not found");
+    c->encode = (PFN_encodeTiled)fn;
+    return TRITD_OK;
+}
+
+extern "C" int tritd_create(int device, tritd_ctx** out) {
+    if (!out) return fail(TRITD_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    tritd_ctx* c = new tritd_ctx();
+    int s = ctx_common_init(c, device);
+    if (s != TRITD_OK) { delete c; return s; }
+    *out = c;
+    return TRITD_OK;
+}
+
+extern "C" int tritd_nccl_unique_id(void* id_out) {
+    if (!id_out) return fail(TRITD_ERR_INVALID, "id_out is NULL");
+    ST_TRY(nccl_load());
+    static_assert(sizeof(ncclUniqueId) == TRITD_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));
+    return TRITD_OK;
+}
+
+extern "C" int tritd_create_rank(int device, int rank, int nranks, const void* nccl_id, tritd_ctx** out) {
+    if (!out) return fail(TRITD_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(TRITD_ERR_INVALID, "bad rank %d / nranks %d", rank, nranks);
+    if (nranks > 1 && !nccl_id) return fail(TRITD_ERR_INVALID, "nccl_id is NULL");
+    tritd_ctx* c = new tritd_ctx();
+    int s = ctx_common_init(c, device);
+    if (s != TRITD_OK) { delete c; return s; }
+    c->rank = rank;
+    c->nranks = nranks;
+    if (nranks > 1) {
+        s = nccl_load();
+        if (s != TRITD_OK) { tritd_destroy(c); return s; }
+        ncclUniqueId id;
+        memcpy(&id, nccl_id, sizeof(id));
+        ncclResult_t r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+        if (r != ncclSuccess) {
+            tritd_destroy(c);
+            return fail(TRITD_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+        }
+    }
+    *out = c;
+    return TRITD_OK;
+}
+
+extern "C" void tritd_destroy(tritd_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" const char* tritd_last_error(void) { return g_err; }
+extern "C" const char* tritd_version(void) { return "tritd-b200 0.1 (sm_100a)"; }
+extern "C" int64_t tritd_launch_count(const tritd_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int tritd_set_stream(tritd_ctx* c, void* cuda_stream) {
+    if (!c) return fail(TRITD_ERR_INVALID, "ctx is NULL");
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return TRITD_OK;
+}
+
+extern "C" int tritd_slab_bounds(int64_t n3, int nranks, int rank, int64_t* t0, int64_t* t1) {
+    if (n3 < 0 || nranks < 1 || rank < 0 || rank >= nranks || !t0 || !t1) return fail(TRITD_ERR_INVALID, "bad slab query");
+    const int64_t base = n3 / nranks, extra = n3 % nranks;
+    *t0 = rank * base + (rank < extra ? rank : extra);
+    *t1 = *t0 + base + (rank < extra ? 1 : 0);
+    return TRITD_OK;
+}
+
+static int allreduce_sum(tritd_ctx* c, double* buf, size_t n) {
+    if (c->nranks == 1) return TRITD_OK;
+    NCCL_TRY(g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, c->comm, c->stream));
+    return TRITD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// problem (device-resident state of one solve)
+// ---------------------------------------------------------------------------
+struct tritd_problem {
+    tritd_ctx* ctx = nullptr;
+    int n1 = 0, n2 = 0, n3 = 0, r = 0, R = 0, RS = 0, NT = 0, KS = 0;
+    int ld1 = 0, ldt = 0;
+    size_t Np = 0;                       // padded elements of one N-array: ld1 * n2 * n3
+    double *D = nullptr, *E = nullptr, *YL = nullptr, *YO = nullptr, *T = nullptr, *O = nullptr;
+    double *A1 = nullptr, *B2 = nullptr, *C3 = nullptr, *A1T = nullptr;
+    double *SA = nullptr, *SB = nullptr;
+    double *bufA = nullptr;              // [rhsA (n1*RS) ; SC (RS*RS)] -- one all-reduce
+    double *rhsB = nullptr, *rhsC = nullptr, *P = nullptr, *partM = nullptr;
+    double *norm_part = nullptr, *norms = nullptr;
+    IterState* st = nullptr;
+    double *errHist = nullptr, *errL = nullptr, *errO = nullptr;
+    IterState* st_host = nullptr;        // pinned mirror
+    CUtensorMap mapT, mapA1T;
+    int n_it = 0, n_jc = 0, gridM = 0, gridP = 0, gridF = 0, gi = 0;
+    long unitsM = 0, unitsP = 0;
+    size_t smemM = 0, smemP = 0;
+    tritd_opts opts{};
+    bool has_D = false, initialized = false;
+    int printed_k = 0;
+    std::vector<void*> allocs;
+};
+
+template <typename Tp>
+static int dalloc(tritd_problem* p, Tp** ptr, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(Tp) + 256);
+    if (e != cudaSuccess) return fail(TRITD_ERR_CUDA, "cudaMalloc(%zu bytes): %s", count * sizeof(Tp), cudaGetErrorString(e));
+    p->allocs.push_back(q);
+    *ptr = (Tp*)q;
+    return TRITD_OK;
+}
+
+static int make_map(tritd_ctx* c, CUtensorMap* map, void* base, int rank, const cuuint64_t* dims,
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(TRITD_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return TRITD_OK;
+}
+
+// ---- kernel dispatch on the triple rank r (1..8) ---------------------------
+#define TRITD_DISPATCH_R(r, CALL)                       \
+    switch (r) {                                        \
+        case 1: { CALL(1, 1); } break;                  \
+        case 2: { CALL(1, 1); } break;                  \
+        case 3: { CALL(2, 3); } break;                  \
+        case 4: { CALL(2, 4); } break;                  \
+        case 5: { CALL(4, 7); } break;                  \
+        case 6: { CALL(5, 9); } break;                  \
+        case 7: { CALL(7, 13); } break;                 \
+        case 8: { CALL(8, 16); } break;                 \
+        default: return fail(TRITD_ERR_UNSUPPORTED, "r=%d unsupported (1..%d)", r, TRITD_MAX_R); \
+    }
+
+static size_t smem_mttkrp1(int NT) { return (size_t)kStages * kCW * kBoxBytes + (size_t)NT * 8 * kPJ * 8 + 2 * kStages * 8; }
+static size_t smem_ppass(int NT) { return (size_t)kStages * (kCW * kBoxBytes + NT * 8 * 128) + 2 * kStages * 8; }
+
+static int launch_mttkrp1(tritd_problem* p, const CUtensorMap& map, const double* B2, const double* C3, double* rhs_out) {
+    tritd_ctx* c = p->ctx;
+    Mttkrp1Args a;
+    a.B2 = B2; a.C3 = C3; a.part = p->partM; a.stop = &p->st->stop;
+    a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_it = p->n_it; a.n_jc = p->n_jc; a.units = p->unitsM;
+#define CALL(NT_, KS_)                                                                                         \
+    CU_TRY(cudaFuncSetAttribute(k_mttkrp1<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemM)); \
+    k_mttkrp1<NT_><<<p->gridM, (kCW + 1) * 32, p->smemM, c->stream>>>(map, a);
+    TRITD_DISPATCH_R(p->r, CALL)
+#undef CALL
+    CU_TRY(cudaGetLastError());
+    const long tot = (long)p->n1 * p->RS;
+    k_mttkrp1_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(p->partM, rhs_out, p->n1, p->RS, p->n_it,
+                                                                         p->n_jc, p->n3, p->gridM, &p->st->stop);
+    CU_TRY(cudaGetLastError());
+    c->launches += 2;
+    return TRITD_OK;
+}
+
+static int launch_ppass(tritd_problem* p, const CUtensorMap& mapT) {
+    tritd_ctx* c = p->ctx;
+    PpassArgs a;
+    a.P = p->P; a.stop = &p->st->stop;
+    a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS;
+    a.n_jb = p->n_jc; a.n_rb = (long)p->n3 * p->n_jc; a.units = p->unitsP;
+#define CALL(NT_, KS_)                                                                                       \
+    CU_TRY(cudaFuncSetAttribute(k_ppass<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemP)); \
+    k_ppass<NT_><<<p->gridP, (kCW + 1) * 32, p->smemP, c->stream>>>(mapT, p->mapA1T, a);
+    TRITD_DISPATCH_R(p->r, CALL)
+#undef CALL
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+static int launch_fused(tritd_problem* p, int mode, double* Lout) {
+    tritd_ctx* c = p->ctx;
+    FusedArgs a;
+    a.D = p->D; a.E = p->E; a.YL = p->YL; a.YO = p->YO; a.T = p->T; a.O = mode == 0 ? p->O : Lout;
+    a.A1 = p->A1; a.B2 = p->B2; a.C3 = p->C3; a.st = p->st; a.norm_part = p->norm_part;
+    a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.ld1 = p->ld1; a.RS = p->RS;
+    a.n_it = p->n_it; a.n_jc = p->n_jc; a.gi = p->gi;
+#define CALL(NT_, KS_)                                                              \
+    if (mode == 0) k_fused<KS_, 0><<<p->gridF, 256, 0, c->stream>>>(a);             \
+    else k_fused<KS_, 1><<<p->gridF, 256, 0, c->stream>>>(a);
+    TRITD_DISPATCH_R(p->r, CALL)
+#undef CALL
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+static int launch_solve(tritd_problem* p, const double* rhs, const double* S1, const double* S2, double alpha, double* X,
+                        double* XT, int n) {
+    tritd_ctx* c = p->ctx;
+    SolveArgs a;
+    a.rhs = rhs; a.S1 = S1; a.S2 = S2; a.alpha = alpha; a.X = X; a.XT = XT; a.st = p->st;
+    a.n = n; a.R = p->R; a.RS = p->RS; a.ldt = p->ldt;
+    const int P = p->R | 1;
+    const size_t smem = (size_t)(p->R + 64) * P * sizeof(double);
+    k_solve<<<(n + 63) / 64, 256, smem, c->stream>>>(a);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+static int launch_small_gram(tritd_problem* p, const double* X, int n, double* S) {
+    tritd_ctx* c = p->ctx;
+    k_small_gram<<<(p->RS * p->RS + 255) / 256, 256, 0, c->stream>>>(X, n, p->RS, S, &p->st->stop);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+extern "C" void tritd_problem_destroy(tritd_problem* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    for (void* q : p->allocs) cudaFree(q);
+    if (p->st_host) cudaFreeHost(p->st_host);
+    delete p;
+}
+
+extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int r, tritd_problem** out) {
+    if (!c || !out) return fail(TRITD_ERR_INVALID, "ctx/out is NULL");
+    *out = nullptr;
+    if (n1 < 1 || n2 < 1 || n3 < 1) return fail(TRITD_ERR_INVALID, "tensor size %lld x %lld x %lld", (long long)n1, (long long)n2, (long long)n3);
+    if (r < 1) return fail(TRITD_ERR_INVALID, "triple rank r=%d", r);
+    if (r > TRITD_MAX_R) return fail(TRITD_ERR_UNSUPPORTED, "r=%d unsupported (1..%d)", r, TRITD_MAX_R);
+    if (n1 > (1 << 24) || n2 > (1 << 24) || n3 > (1 << 24)) return fail(TRITD_ERR_INVALID, "mode size above 2^24");
+    CU_TRY(cudaSetDevice(c->device));
+    tritd_problem* p = new tritd_problem();
+    p->ctx = c;
+    p->n1 = (int)n1; p->n2 = (int)n2; p->n3 = (int)n3; p->r = r; p->R = r * r;
+    p->RS = (p->R + 7) / 8 * 8;
+    const RankCfg rc = rank_cfg(r);
+    p->NT = rc.NT; p->KS = rc.KS;
+    p->ld1 = (p->n1 + 1) & ~1;
+    p->ldt = p->ld1;
+    p->Np = (size_t)p->ld1 * p->n2 * p->n3;
+    p->n_it = (p->n1 + 127) / 128;
+    p->n_jc = (p->n2 + kBoxRows - 1) / kBoxRows;
+
+    int s = TRITD_OK;
+    auto bail = [&](int code) { tritd_problem_destroy(p); return code; };
+#define PALLOC(ptr, count) if ((s = dalloc(p, &p->ptr, (count))) != TRITD_OK) return bail(s)
+    PALLOC(D, p->Np); PALLOC(E, p->Np); PALLOC(YL, p->Np); PALLOC(YO, p->Np); PALLOC(T, p->Np); PALLOC(O, p->Np);
+    PALLOC(A1, (size_t)p->n1 * p->RS); PALLOC(B2, (size_t)p->n2 * p->RS); PALLOC(C3, (size_t)p->n3 * p->RS);
+    PALLOC(A1T, (size_t)p->RS * p->ldt);
+    PALLOC(SA, (size_t)p->RS * p->RS); PALLOC(SB, (size_t)p->RS * p->RS);
+    PALLOC(bufA, (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS);
+    PALLOC(rhsB, (size_t)p->n2 * p->RS); PALLOC(rhsC, (size_t)p->n3 * p->RS);
+    PALLOC(P, (size_t)p->n3 * p->n2 * p->RS);
+
+    // grids: one contraction CTA per SM (its pipeline fills shared memory); the fused kernel by occupancy
+    p->unitsM = (long)p->n_it * p->n_jc * p->n3;
+    p->gridM = (int)std::min<long>(p->unitsM, std::max(2 * p->n_it, c->num_sms));
+    p->unitsP = ((long)p->n3 * p->n_jc + kCW - 1) / kCW;
+    p->gridP = (int)std::min<long>(p->unitsP, c->num_sms);
+    p->smemM = smem_mttkrp1(p->NT);
+    p->smemP = smem_ppass(p->NT);
+    int occ = 1;
+#define CALL(NT_, KS_) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused<KS_, 0>, 256, 0));
+    {
+        auto q = [&]() -> int { TRITD_DISPATCH_R(r, CALL) return TRITD_OK; };
+        if ((s = q()) != TRITD_OK) return bail(s);
+    }
+#undef CALL
+    if (occ < 1) occ = 1;
+    p->gi = std::max(1, c->num_sms * occ / p->n_it);
+    p->gridF = p->gi * p->n_it;
+
+    PALLOC(partM, (size_t)p->gridM * 2 * 128 * p->RS);
+    PALLOC(norm_part, (size_t)2 * std::max(p->gridF, 1024));
+    PALLOC(norms, 8);
+    PALLOC(st, 1);
+#undef PALLOC
+    if (cudaMallocHost((void**)&p->st_host, sizeof(IterState)) != cudaSuccess) return bail(fail(TRITD_ERR_CUDA, "cudaMallocHost failed"));
+
+    // zero everything once: pad rows / pad columns must be exact zeros forever
+    cudaStream_t st = c->stream;
+    for (double* q : {p->D, p->E, p->YL, p->YO, p->T, p->O})
+        if (cudaMemsetAsync(q, 0, p->Np * sizeof(double), st) != cudaSuccess) return bail(fail(TRITD_ERR_CUDA, "memset failed"));
+    cudaMemsetAsync(p->A1T, 0, (size_t)p->RS * p->ldt * sizeof(double), st);
+    cudaMemsetAsync(p->st, 0, sizeof(IterState), st);
+
+    // tensor maps: T as (i, j, t) with 128B-swizzled boxes [32 j][16 i]; A1T as (i, k) with boxes [RS k][16 i]
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)p->n1, (cuuint64_t)p->n2, (cuuint64_t)p->n3};
+        cuuint64_t str[2] = {(cuuint64_t)p->ld1 * 8, (cuuint64_t)p->ld1 * p->n2 * 8};
+        cuuint32_t box[3] = {16, (cuuint32_t)kBoxRows, 1};
+        if ((s = make_map(c, &p->mapT, p->T, 3, dims, str, box)) != TRITD_OK) return bail(s);
+        cuuint64_t dims2[2] = {(cuuint64_t)p->n1, (cuuint64_t)p->RS};
+        cuuint64_t str2[1] = {(cuuint64_t)p->ldt * 8};
+        cuuint32_t box2[2] = {16, (cuuint32_t)p->RS};
+        if ((s = make_map(c, &p->mapA1T, p->A1T, 2, dims2, str2, box2)) != TRITD_OK) return bail(s);
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) return bail(fail(TRITD_ERR_CUDA, "sync failed"));
+    *out = p;
+    return TRITD_OK;
+}
+
+// dense column-major (ld = n1) <-> padded (ld = ld1) copies; kind = cudaMemcpyDefault works for host and device
+static int copy_in(tritd_problem* p, double* dst_padded, const double* src_dense) {
+    cudaStream_t st = p->ctx->stream;
+    if (p->ld1 == p->n1) CU_TRY(cudaMemcpyAsync(dst_padded, src_dense, p->Np * sizeof(double), cudaMemcpyDefault, st));
+    else CU_TRY(cudaMemcpy2DAsync(dst_padded, (size_t)p->ld1 * 8, src_dense, (size_t)p->n1 * 8, (size_t)p->n1 * 8,
+                                  (size_t)p->n2 * p->n3, cudaMemcpyDefault, st));
+    return TRITD_OK;
+}
+static int copy_out(tritd_problem* p, double* dst_dense, const double* src_padded) {
+    cudaStream_t st = p->ctx->stream;
+    if (p->ld1 == p->n1) CU_TRY(cudaMemcpyAsync(dst_dense, src_padded, p->Np * sizeof(double), cudaMemcpyDefault, st));
+    else CU_TRY(cudaMemcpy2DAsync(dst_dense, (size_t)p->n1 * 8, src_padded, (size_t)p->ld1 * 8, (size_t)p->n1 * 8,
+                                  (size_t)p->n2 * p->n3, cudaMemcpyDefault, st));
+    return TRITD_OK;
+}
+
+extern "C" int tritd_problem_set_D_host(tritd_problem* p, const double* D_host) {
+    if (!p || !D_host) return fail(TRITD_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    ST_TRY(copy_in(p, p->D, D_host));
+    CU_TRY(cudaStreamSynchronize(p->ctx->stream));
+    p->has_D = true; p->initialized = false;
+    return TRITD_OK;
+}
+extern "C" int tritd_problem_set_D_dev(tritd_problem* p, const double* D_dev) {
+    if (!p || !D_dev) return fail(TRITD_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    ST_TRY(copy_in(p, p->D, D_dev));
+    p->has_D = true; p->initialized = false;
+    return TRITD_OK;
+}
+
+// MATLAB 3-D factor shapes <-> row-major n x RS "unfolded" layout (reshape_*_from_*, :111-130, run backwards)
+static void pack_A(const double* A, int n1, int R, int RS, std::vector<double>& out) {
+    out.assign((size_t)n1 * RS, 0.0);
+    for (int k = 0; k < R; ++k) for (int i = 0; i < n1; ++i) out[(size_t)i * RS + k] = A[(size_t)k * n1 + i];
+}
+static void pack_B(const double* B, int n2, int r, int RS, std::vector<double>& out) {
+    out.assign((size_t)n2 * RS, 0.0);   // B(p,j,s) at p + r*(j + n2*s)  ->  B2[j][p + r*s]
+    for (int s = 0; s < r; ++s) for (int j = 0; j < n2; ++j) for (int q = 0; q < r; ++q)
+        out[(size_t)j * RS + q + r * s] = B[(size_t)q + (size_t)r * (j + (size_t)n2 * s)];
+}
+static void pack_C(const double* C, int n3, int R, int RS, std::vector<double>& out) {
+    out.assign((size_t)n3 * RS, 0.0);   // C(p,s,t) at (p + r*s) + R*t  ->  C3[t][p + r*s]
+    for (int t = 0; t < n3; ++t) for (int k = 0; k < R; ++k) out[(size_t)t * RS + k] = C[(size_t)t * R + k];
+}
+static void unpack_A(const std::vector<double>& in, int n1, int R, int RS, double* A) {
+    for (int k = 0; k < R; ++k) for (int i = 0; i < n1; ++i) A[(size_t)k * n1 + i] = in[(size_t)i * RS + k];
+}
+static void unpack_B(const std::vector<double>& in, int n2, int r, int RS, double* B) {
+    for (int s = 0; s < r; ++s) for (int j = 0; j < n2; ++j) for (int q = 0; q < r; ++q)
+        B[(size_t)q + (size_t)r * (j + (size_t)n2 * s)] = in[(size_t)j * RS + q + r * s];
+}
+static void unpack_C(const std::vector<double>& in, int n3, int R, int RS, double* C) {
+    for (int t = 0; t < n3; ++t) for (int k = 0; k < R; ++k) C[(size_t)t * R + k] = in[(size_t)t * RS + k];
+}
+
+static int upload_factors(tritd_problem* p, const double* A0, const double* B0, const double* C0) {
+    cudaStream_t st = p->ctx->stream;
+    std::vector<double> h;
+    pack_A(A0, p->n1, p->R, p->RS, h);
+    CU_TRY(cudaMemcpyAsync(p->A1, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    pack_B(B0, p->n2, p->r, p->RS, h);
+    CU_TRY(cudaMemcpyAsync(p->B2, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    pack_C(C0, p->n3, p->R, p->RS, h);
+    CU_TRY(cudaMemcpyAsync(p->C3, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return TRITD_OK;
+}
+
+extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const double* A0, const double* B0,
+                                  const double* C0) {
+    if (!p || !o || !A0 || !B0 || !C0) return fail(TRITD_ERR_INVALID, "NULL argument");
+    if (!p->has_D) return fail(TRITD_ERR_INVALID, "tritd_problem_set_D_* must be called first");
+    if (o->maxIter < 1) return fail(TRITD_ERR_INVALID, "opts.maxIter = %d", o->maxIter);
+    if (!(o->mu > 0.0)) return fail(TRITD_ERR_INVALID, "opts.mu must be positive");
+    tritd_ctx* c = p->ctx;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    p->opts = *o;
+    ST_TRY(upload_factors(p, A0, B0, C0));
+
+    // O = E = Y_L = Y_O = 0 (:24-26); the first target T = D - O + (1/muL)*Y_L is D itself (:33)
+    for (double* q : {p->E, p->YL, p->YO, p->O}) CU_TRY(cudaMemsetAsync(q, 0, p->Np * sizeof(double), st));
+    CU_TRY(cudaMemcpyAsync(p->T, p->D, p->Np * sizeof(double), cudaMemcpyDeviceToDevice, st));
+
+    IterState h;
+    memset(&h, 0, sizeof(h));
+    h.muL = o->mu; h.muO = o->mu; h.muL_max = o->mu * 1e6; h.muO_max = o->mu * 1e6;
+    h.rhoL = o->rho; h.rhoO = o->rho; h.lambda = o->lambda_; h.tol = o->tol; h.normD = 0.0;
+    h.k = 0; h.stop = 0; h.status = 0; h.maxIter = o->maxIter;
+    iter_state_derive(h);
+    *p->st_host = h;
+    CU_TRY(cudaMemcpyAsync(p->st, p->st_host, sizeof(IterState), cudaMemcpyHostToDevice, st));
+
+    // history buffers sized by maxIter
+    {
+        double* q = nullptr;
+        ST_TRY(dalloc(p, &q, (size_t)3 * o->maxIter));
+        p->errHist = q; p->errL = q + o->maxIter; p->errO = q + 2 * (size_t)o->maxIter;
+        CU_TRY(cudaMemsetAsync(q, 0, (size_t)3 * o->maxIter * 8, st));
+    }
+
+    // normD = norm(D(:))  (:28), all-reduced over the slabs
+    k_sumsq_part<<<1024, 256, 0, st>>>(p->D, p->Np, p->norm_part);
+    k_sum_pairs<<<1, 256, 0, st>>>(p->norm_part, 1024, p->norms, nullptr);
+    CU_TRY(cudaGetLastError());
+    ST_TRY(allreduce_sum(c, p->norms, 2));
+    k_set_normD<<<1, 32, 0, st>>>(p->st, p->norms);
+    c->launches += 3;
+
+    // small Grams of the initial factors: SB = B2'B2, SC (partial over local rows) = C3'C3
+    ST_TRY(launch_small_gram(p, p->B2, p->n2, p->SB));
+    ST_TRY(launch_small_gram(p, p->C3, p->n3, p->bufA + (size_t)p->n1 * p->RS));
+    CU_TRY(cudaStreamSynchronize(st));
+    p->initialized = true;
+    p->printed_k = 0;
+    return TRITD_OK;
+}
+
+// One ADMM iteration, enqueued on the context's stream (triple_decomp_ADMM.m:31-66).
+static int enqueue_iteration(tritd_problem* p) {
+    tritd_ctx* c = p->ctx;
+    cudaStream_t st = c->stream;
+    double* rhsA = p->bufA;
+    double* SC = p->bufA + (size_t)p->n1 * p->RS;
+    const int* stop = &p->st->stop;
+
+    // update_A (:73-81): RHS = X1*F', Gram = (B2'B2) o (C3'C3) + lambda2*I
+    ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, rhsA));
+    ST_TRY(allreduce_sum(c, p->bufA, (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS));
+    ST_TRY(launch_solve(p, rhsA, p->SB, SC, p->opts.lambda2, p->A1, p->A1T, p->n1));
+    ST_TRY(launch_small_gram(p, p->A1, p->n1, p->SA));
+
+    // update_B (:83-88) with the new A: RHS = X2*G', Gram = (A1'A1) o (C3'C3) + lambda2*I
+    ST_TRY(launch_ppass(p, p->mapT));
+    k_rhsB<<<(unsigned)(((long)p->n2 * p->RS + 255) / 256), 256, 0, st>>>(p->P, p->C3, p->rhsB, p->n2, p->n3, p->RS, stop);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    ST_TRY(allreduce_sum(c, p->rhsB, (size_t)p->n2 * p->RS));
+    ST_TRY(launch_solve(p, p->rhsB, p->SA, SC, p->opts.lambda2, p->B2, nullptr, p->n2));
+    ST_TRY(launch_small_gram(p, p->B2, p->n2, p->SB));
+
+    // update_C (:90-95) with the new A, B: slice-local; ridge fixed at 1e-9
+    k_rhsC<<<p->n3, 256, 0, st>>>(p->P, p->B2, p->rhsC, p->n2, p->n3, p->RS, stop);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    ST_TRY(launch_solve(p, p->rhsC, p->SA, p->SB, 1e-9, p->C3, nullptr, p->n3));
+    ST_TRY(launch_small_gram(p, p->C3, p->n3, SC));   // partial over local slices, summed by the next all-reduce
+
+    // L, O, E, duals, next T, residual norms (:38-59, :33)
+    ST_TRY(launch_fused(p, 0, nullptr));
+    k_sum_pairs<<<1, 256, 0, st>>>(p->norm_part, p->gridF, p->norms, stop);
+    CU_TRY(cudaGetLastError());
+    ST_TRY(allreduce_sum(c, p->norms, 2));
+    k_finalize<<<1, 32, 0, st>>>(p->st, p->norms, p->errHist, p->errL, p->errO);
+    CU_TRY(cudaGetLastError());
+    c->launches += 2;
+    return TRITD_OK;
+}
+
+static int fetch_state(tritd_problem* p) {
+    CU_TRY(cudaMemcpyAsync(p->st_host, p->st, sizeof(IterState), cudaMemcpyDeviceToHost, p->ctx->stream));
+    CU_TRY(cudaStreamSynchronize(p->ctx->stream));
+    if (p->st_host->status == kStatusCholesky)
+        return fail(TRITD_ERR_NUMERIC, "ridge system not positive definite at iteration %d (Cholesky pivot <= 0 or non-finite)",
+                    p->st_host->k + 1);
+    return TRITD_OK;
+}
+
+extern "C" int tritd_problem_enqueue(tritd_problem* p, int32_t n) {
+    if (!p || !p->initialized) return fail(TRITD_ERR_INVALID, "problem not initialised");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    for (int i = 0; i < n; ++i) ST_TRY(enqueue_iteration(p));
+    return TRITD_OK;
+}
+
+extern "C" int tritd_problem_sync(tritd_problem* p) {
+    if (!p) return fail(TRITD_ERR_INVALID, "NULL problem");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    return fetch_state(p);
+}
+
+static int print_progress(tritd_problem* p) {
+    // "Iter %d, errL=%.2e, errO=%.2e" every 10th iteration (:60-62)
+    const int k = p->st_host->k;
+    if (!p->opts.disp || k / 10 == p->printed_k / 10) { p->printed_k = k; return TRITD_OK; }
+    std::vector<double> eL(k), eO(k);
+    CU_TRY(cudaMemcpy(eL.data(), p->errL, (size_t)k * 8, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(eO.data(), p->errO, (size_t)k * 8, cudaMemcpyDeviceToHost));
+    for (int q = p->printed_k / 10 * 10 + 10; q <= k; q += 10) printf("Iter %d, errL=%.2e, errO=%.2e\n", q, eL[q - 1], eO[q - 1]);
+    fflush(stdout);
+    p->printed_k = k;
+    return TRITD_OK;
+}
+
+extern "C" int tritd_problem_iterate(tritd_problem* p, int32_t max_more, int32_t* iters_total) {
+    if (!p || !p->initialized) return fail(TRITD_ERR_INVALID, "problem not initialised");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    ST_TRY(fetch_state(p));
+    int remaining = std::min<int>(max_more, p->opts.maxIter - p->st_host->k);
+    // the stopping rule lives on the device; the host only looks at it every 10 iterations
+    // (the cadence of the reference's progress line), later launches of a stopped solve are no-ops
+    while (remaining > 0 && !p->st_host->stop) {
+        const int batch = std::min(remaining, 10 - p->st_host->k % 10);
+        for (int i = 0; i < batch; ++i) ST_TRY(enqueue_iteration(p));
+        ST_TRY(fetch_state(p));
+        ST_TRY(print_progress(p));
+        remaining -= batch;
+    }
+    if (iters_total) *iters_total = p->st_host->k;
+    return TRITD_OK;
+}
+
+static int reconstruct_L(tritd_problem* p, double** Lbuf) {
+    double* q = nullptr;
+    cudaError_t e = cudaMalloc((void**)&q, p->Np * sizeof(double));
+    if (e != cudaSuccess) return fail(TRITD_ERR_CUDA, "cudaMalloc(L): %s", cudaGetErrorString(e));
+    cudaMemsetAsync(q, 0, p->Np * sizeof(double), p->ctx->stream);
+    int s = launch_fused(p, 1, q);
+    if (s != TRITD_OK) { cudaFree(q); return s; }
+    *Lbuf = q;
+    return TRITD_OK;
+}
+
+extern "C" int tritd_problem_get(tritd_problem* p, double* A, double* B, double* C, double* O, double* L,
+                                 double* errHist, double* errL, double* errO, int32_t* iters) {
+    if (!p || !p->initialized) return fail(TRITD_ERR_INVALID, "problem not initialised");
+    tritd_ctx* c = p->ctx;
+    CU_TRY(cudaSetDevice(c->device));
+    ST_TRY(fetch_state(p));
+    const int k = p->st_host->k;
+    std::vector<double> h;
+    if (A) { h.resize((size_t)p->n1 * p->RS); CU_TRY(cudaMemcpy(h.data(), p->A1, h.size() * 8, cudaMemcpyDeviceToHost)); unpack_A(h, p->n1, p->R, p->RS, A); }
+    if (B) { h.resize((size_t)p->n2 * p->RS); CU_TRY(cudaMemcpy(h.data(), p->B2, h.size() * 8, cudaMemcpyDeviceToHost)); unpack_B(h, p->n2, p->r, p->RS, B); }
+    if (C) { h.resize((size_t)p->n3 * p->RS); CU_TRY(cudaMemcpy(h.data(), p->C3, h.size() * 8, cudaMemcpyDeviceToHost)); unpack_C(h, p->n3, p->R, p->RS, C); }
+    if (O) { ST_TRY(copy_out(p, O, p->O)); }
+    if (L) {
+        double* Lbuf = nullptr;
+        ST_TRY(reconstruct_L(p, &Lbuf));
+        int s = copy_out(p, L, Lbuf);
+        cudaStreamSynchronize(c->stream);
+        cudaFree(Lbuf);
+        ST_TRY(s);
+    }
+    if (errHist && k) CU_TRY(cudaMemcpyAsync(errHist, p->errHist, (size_t)k * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (errL && k) CU_TRY(cudaMemcpyAsync(errL, p->errL, (size_t)k * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (errO && k) CU_TRY(cudaMemcpyAsync(errO, p->errO, (size_t)k * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (iters) *iters = k;
+    return TRITD_OK;
+}
+
+extern "C" int tritd_problem_get_O_dev(tritd_problem* p, double* O_dev) {
+    if (!p || !O_dev) return fail(TRITD_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    return copy_out(p, O_dev, p->O);
+}
+extern "C" int tritd_problem_get_L_dev(tritd_problem* p, double* L_dev) {
+    if (!p || !L_dev || !p->initialized) return fail(TRITD_ERR_INVALID, "NULL argument / not initialised");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    double* Lbuf = nullptr;
+    ST_TRY(reconstruct_L(p, &Lbuf));
+    int s = copy_out(p, L_dev, Lbuf);
+    cudaStreamSynchronize(p->ctx->stream);
+    cudaFree(Lbuf);
+    return s;
+}
+
+// ---------------------------------------------------------------------------
+// one-call solver
+// ---------------------------------------------------------------------------
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" int tritd_admm_f64(tritd_ctx* c, const double* D_host, int64_t n1, int64_t n2, int64_t n3, int r,
+                              const tritd_opts* o, const double* A0, const double* B0, const double* C0, double* A,
+                              double* B, double* C, double* O, double* L, double* errHist, int32_t* iters_out,
+                              tritd_timing* tm) {
+    if (!c || !D_host || !o || !A0 || !B0 || !C0 || !errHist) return fail(TRITD_ERR_INVALID, "NULL argument");
+    const double t_begin = now_ms();
+    const int64_t launches0 = c->launches;
+    tritd_problem* p = nullptr;
+    ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
+    int s;
+    double t0 = now_ms();
+    if ((s = tritd_problem_set_D_host(p, D_host)) != TRITD_OK) { tritd_problem_destroy(p); return s; }
+    if ((s = tritd_problem_init(p, o, A0, B0, C0)) != TRITD_OK) { tritd_problem_destroy(p); return s; }
+    const double t_h2d = now_ms() - t0;
+
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, c->stream);
+    int32_t k = 0;
+    s = tritd_problem_iterate(p, o->maxIter, &k);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    float it_ms = 0.f;
+    cudaEventElapsedTime(&it_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (s != TRITD_OK) { tritd_problem_destroy(p); return s; }
+
+    t0 = now_ms();
+    s = tritd_problem_get(p, A, B, C, O, L, errHist, nullptr, nullptr, &k);
+    const double t_d2h = now_ms() - t0;
+    tritd_problem_destroy(p);
+    if (s != TRITD_OK) return s;
+    if (iters_out) *iters_out = k;
+    if (tm) {
+        tm->h2d_ms = t_h2d; tm->iterate_ms = it_ms; tm->d2h_ms = t_d2h; tm->total_ms = now_ms() - t_begin;
+        tm->iters = k; tm->launches = (int32_t)(c->launches - launches0);
+    }
+    return TRITD_OK;
+}
+
+// ---------------------------------------------------------------------------
+// standalone helpers
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    double* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) {
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(double));
+        return e == cudaSuccess ? TRITD_OK : fail(TRITD_ERR_CUDA, "cudaMalloc(%zu doubles): %s", n, cudaGetErrorString(e));
+    }
+};
+
+static int check_r(int r) {
+    if (r < 1) return fail(TRITD_ERR_INVALID, "triple rank r=%d", r);
+    if (r > TRITD_MAX_R) return fail(TRITD_ERR_UNSUPPORTED, "r=%d unsupported (1..%d)", r, TRITD_MAX_R);
+    return TRITD_OK;
+}
+
+extern "C" int tritd_triple_product_f64(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1,
+                                        int64_t n2, int64_t n3, int r, double* Xhat) {
+    if (!c || !A || !B || !C || !Xhat) return fail(TRITD_ERR_INVALID, "NULL argument");
+    ST_TRY(check_r(r));
+    tritd_problem* p = nullptr;
+    ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
+    int s = upload_factors(p, A, B, C);
+    double* Lbuf = nullptr;
+    if (s == TRITD_OK) s = reconstruct_L(p, &Lbuf);
+    if (s == TRITD_OK) s = copy_out(p, Xhat, Lbuf);
+    cudaStreamSynchronize(c->stream);
+    if (Lbuf) cudaFree(Lbuf);
+    if (s == TRITD_OK && cudaGetLastError() != cudaSuccess) s = fail(TRITD_ERR_CUDA, "triple_product kernel failed");
+    tritd_problem_destroy(p);
+    return s;
+}
+
+extern "C" int tritd_unfold_f64(tritd_ctx* c, const double* X, int64_t n1, int64_t n2, int64_t n3, int mode, double* Xn) {
+    if (!c || !X || !Xn) return fail(TRITD_ERR_INVALID, "NULL argument");
+    if (n1 < 1 || n2 < 1 || n3 < 1) return fail(TRITD_ERR_INVALID, "bad size");
+    if (mode < 1 || mode > 3) return fail(TRITD_ERR_INVALID, "Mode must be 1, 2, or 3.");
+    CU_TRY(cudaSetDevice(c->device));
+    const size_t N = (size_t)n1 * n2 * n3;
+    if (mode == 1) { if (Xn != X) memcpy(Xn, X, N * 8); return TRITD_OK; }   // reshape only (unfold.m:6)
+    DevBuf in, out;
+    ST_TRY(in.alloc(N)); ST_TRY(out.alloc(N));
+    CU_TRY(cudaMemcpyAsync(in.p, X, N * 8, cudaMemcpyHostToDevice, c->stream));
+    long rows, cols, batch;
+    if (mode == 2) { rows = n1; cols = n2; batch = n3; } else { rows = n1 * n2; cols = n3; batch = 1; }
+    if (batch > 65535 || (cols + 31) / 32 > 65535) return fail(TRITD_ERR_INVALID, "unfold: dimension too large");
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32), (unsigned)batch);
+    k_transpose<<<grid, 256, 0, c->stream>>>(in.p, out.p, rows, cols);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    CU_TRY(cudaMemcpyAsync(Xn, out.p, N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return TRITD_OK;
+}
+
+static int khatri_rao_host(tritd_ctx* c, const std::vector<double>& Xa, const std::vector<double>& Xb, long na, long nb,
+                           int R, int RS, double* out_host) {
+    CU_TRY(cudaSetDevice(c->device));
+    DevBuf a, b, o;
+    const size_t total = (size_t)R * na * nb;
+    ST_TRY(a.alloc(Xa.size())); ST_TRY(b.alloc(Xb.size())); ST_TRY(o.alloc(total));
+    CU_TRY(cudaMemcpyAsync(a.p, Xa.data(), Xa.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(b.p, Xb.data(), Xb.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16);
+    k_khatri_rao_t<<<grid, 256, 0, c->stream>>>(a.p, b.p, o.p, na, nb, R, RS);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    CU_TRY(cudaMemcpyAsync(out_host, o.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return TRITD_OK;
+}
+
+extern "C" int tritd_buildF_f64(tritd_ctx* c, const double* B, const double* C, int64_t n2, int64_t n3, int r, double* F) {
+    if (!c || !B || !C || !F || n2 < 1 || n3 < 1) return fail(TRITD_ERR_INVALID, "bad argument");
+    ST_TRY(check_r(r));
+    const int R = r * r, RS = (R + 7) / 8 * 8;
+    std::vector<double> b2, c3;
+    pack_B(B, (int)n2, r, RS, b2); pack_C(C, (int)n3, R, RS, c3);
+    return khatri_rao_host(c, b2, c3, n2, n3, R, RS, F);
+}
+extern "C" int tritd_buildG_f64(tritd_ctx* c, const double* A, const double* C, int64_t n1, int64_t n3, int r, double* G) {
+    if (!c || !A || !C || !G || n1 < 1 || n3 < 1) return fail(TRITD_ERR_INVALID, "bad argument");
+    ST_TRY(check_r(r));
+    const int R = r * r, RS = (R + 7) / 8 * 8;
+    std::vector<double> a1, c3;
+    pack_A(A, (int)n1, R, RS, a1); pack_C(C, (int)n3, R, RS, c3);
+    return khatri_rao_host(c, a1, c3, n1, n3, R, RS, G);
+}
+extern "C" int tritd_buildH_f64(tritd_ctx* c, const double* A, const double* B, int64_t n1, int64_t n2, int r, double* H) {
+    if (!c || !A || !B || !H || n1 < 1 || n2 < 1) return fail(TRITD_ERR_INVALID, "bad argument");
+    ST_TRY(check_r(r));
+    const int R = r * r, RS = (R + 7) / 8 * 8;
+    std::vector<double> a1, b2;
+    pack_A(A, (int)n1, R, RS, a1); pack_B(B, (int)n2, r, RS, b2);
+    return khatri_rao_host(c, a1, b2, n1, n2, R, RS, H);
+}
+
+extern "C" int tritd_soft_threshold_f64(tritd_ctx* c, const double* X, int64_t n, double lam, double* out) {
+    if (!c || !X || !out || n < 0) return fail(TRITD_ERR_INVALID, "bad argument");
+    if (n == 0) return TRITD_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    DevBuf in, o;
+    ST_TRY(in.alloc((size_t)n)); ST_TRY(o.alloc((size_t)n));
+    CU_TRY(cudaMemcpyAsync(in.p, X, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    const unsigned grid = (unsigned)std::min<size_t>(((size_t)n + 255) / 256, (size_t)c->num_sms * 16);
+    k_soft_threshold<<<grid, 256, 0, c->stream>>>(in.p, o.p, (size_t)n, lam);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    CU_TRY(cudaMemcpyAsync(out, o.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return TRITD_OK;
+}
+
+extern "C" int tritd_mttkrp_f64(tritd_ctx* c, const double* X, const double* A, const double* B, const double* C,
+                                int64_t n1, int64_t n2, int64_t n3, int r, int mode, double* rhs) {
+    if (!c || !X || !A || !B || !C || !rhs) return fail(TRITD_ERR_INVALID, "NULL argument");
+    if (mode < 1 || mode > 3) return fail(TRITD_ERR_INVALID, "Mode must be 1, 2, or 3.");
+    ST_TRY(check_r(r));
+    tritd_problem* p = nullptr;
+    ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
+    cudaStream_t st = c->stream;
+    auto body = [&]() -> int {
+        ST_TRY(copy_in(p, p->T, X));
+        ST_TRY(upload_factors(p, A, B, C));
+        const int n = mode == 1 ? p->n1 : (mode == 2 ? p->n2 : p->n3);
+        std::vector<double> h((size_t)n * p->RS);
+        if (mode == 1) {
+            ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, p->bufA));
+            CU_TRY(cudaMemcpyAsync(h.data(), p->bufA, h.size() * 8, cudaMemcpyDeviceToHost, st));
+        } else {
+            // transposed copy of A1 for the TMA-fed pass
+            std::vector<double> a1, a1t((size_t)p->RS * p->ldt, 0.0);
+            pack_A(A, p->n1, p->R, p->RS, a1);
+            for (int i = 0; i < p->n1; ++i) for (int k = 0; k < p->R; ++k) a1t[(size_t)k * p->ldt + i] = a1[(size_t)i * p->RS + k];
+            CU_TRY(cudaMemcpyAsync(p->A1T, a1t.data(), a1t.size() * 8, cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            ST_TRY(launch_ppass(p, p->mapT));
+            if (mode == 2) {
+                k_rhsB<<<(unsigned)(((long)p->n2 * p->RS + 255) / 256), 256, 0, st>>>(p->P, p->C3, p->rhsB, p->n2, p->n3, p->RS, &p->st->stop);
+                CU_TRY(cudaMemcpyAsync(h.data(), p->rhsB, h.size() * 8, cudaMemcpyDeviceToHost, st));
+            } else {
+                k_rhsC<<<p->n3, 256, 0, st>>>(p->P, p->B2, p->rhsC, p->n2, p->n3, p->RS, &p->st->stop);
+                CU_TRY(cudaMemcpyAsync(h.data(), p->rhsC, h.size() * 8, cudaMemcpyDeviceToHost, st));
+            }
+            CU_TRY(cudaGetLastError());
+            c->launches += 1;
+        }
+        CU_TRY(cudaStreamSynchronize(st));
+        for (int k = 0; k < p->R; ++k) for (int i = 0; i < n; ++i) rhs[(size_t)k * n + i] = h[(size_t)i * p->RS + k];
+        return TRITD_OK;
+    };
+    int s = body();
+    tritd_problem_destroy(p);
+    return s;
+}

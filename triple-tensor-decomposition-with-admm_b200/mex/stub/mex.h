@@ -1,0 +1,40 @@
+/* Minimal stand-in for MathWorks' mex.h / matrix.h, declaring only what the gateways in this
+ * directory use, so they can be syntax-checked in an image without MATLAB or Octave.
+ * NOT a MEX implementation: nothing here is ever linked. */
+#ifndef TRITD_STUB_MEX_H
+#define TRITD_STUB_MEX_H
+#include <stddef.h>
+typedef struct mxArray_tag mxArray;
+typedef size_t mwSize;
+typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
+typedef enum { mxDOUBLE_CLASS = 6 } mxClassID;
+#ifdef __cplusplus
+extern "C" {
+#endif
+int mxIsDouble(const mxArray*);
+int mxIsComplex(const mxArray*);
+int mxIsSparse(const mxArray*);
+int mxIsStruct(const mxArray*);
+int mxIsEmpty(const mxArray*);
+mwSize mxGetNumberOfDimensions(const mxArray*);
+const mwSize* mxGetDimensions(const mxArray*);
+size_t mxGetNumberOfElements(const mxArray*);
+double* mxGetPr(const mxArray*);
+double mxGetScalar(const mxArray*);
+mxArray* mxGetField(const mxArray*, size_t, const char*);
+mxArray* mxCreateNumericArray(mwSize, const mwSize*, mxClassID, mxComplexity);
+mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
+mxArray* mxCreateDoubleScalar(double);
+void mxDestroyArray(mxArray*);
+void* mxMalloc(size_t);
+void mxFree(void*);
+int mexCallMATLAB(int, mxArray**, int, mxArray**, const char*);
+void mexErrMsgIdAndTxt(const char*, const char*, ...);
+int mexPrintf(const char*, ...);
+void mexLock(void);
+int mexAtExit(void (*)(void));
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,129 @@
+/* MEX gateway: [A,B,C,O,errHist] = triple_decomp_ADMM(D, r, opts)
+ *
+ * Drop-in for fast_robust_triple_tensor/triple_decomp_ADMM.m:1 -- same name, same three
+ * inputs, same five outputs; a triple_decomp_ADMM.mex* earlier on the MATLAB path shadows
+ * the .m file.  All numerical work happens in libtritd (CUDA, sm_100a); this file only
+ * validates arguments, draws the initial factors with MATLAB's own randn in the reference's
+ * order (:23 -- A, B, C -- so rng(0) in the caller gives the reference's factors) and moves
+ * mxArrays in and out.  Optional extension fields of opts: A0, B0, C0 (injected
+ * initial factors), device (CUDA ordinal).  A sixth output, when requested, is
+ * L = triple_product(A,B,C).
+ *
+ * Build (on a machine with MATLAB + CUDA):
+ *   mex -I../../include triple_decomp_ADMM.c -L../tritd -ltritd
+ * This image has neither MATLAB nor Octave: the file is syntax-checked against stub/mex.h.
+ */
+#include <string.h>
+
+#include "mex.h"
+#include "tritd.h"
+
+static tritd_ctx* g_ctx = NULL;
+
+static void at_exit(void) {
+    if (g_ctx) { tritd_destroy(g_ctx); g_ctx = NULL; }
+}
+
+static double req_field(const mxArray* opts, const char* name) {
+    const mxArray* f = mxGetField(opts, 0, name);
+    if (!f) mexErrMsgIdAndTxt("MATLAB:nonExistentField", "Unrecognized field name \"%s\".", name);
+    if (!mxIsDouble(f) && mxGetNumberOfElements(f) != 1)
+        mexErrMsgIdAndTxt("tritd:opts", "opts.%s must be a real scalar.", name);
+    return mxGetScalar(f);
+}
+
+static const double* opt_factor(const mxArray* opts, const char* name, size_t numel) {
+    const mxArray* f = mxGetField(opts, 0, name);
+    if (!f || mxIsEmpty(f)) return NULL;
+    if (!mxIsDouble(f) || mxIsComplex(f) || mxGetNumberOfElements(f) != numel)
+        mexErrMsgIdAndTxt("tritd:opts", "opts.%s has the wrong size or class.", name);
+    return mxGetPr(f);
+}
+
+static mxArray* randn3(mwSize a, mwSize b, mwSize c) {
+    mxArray* dims = mxCreateDoubleMatrix(1, 3, mxREAL);
+    mxArray* out = NULL;
+    double* d = mxGetPr(dims);
+    d[0] = (double)a; d[1] = (double)b; d[2] = (double)c;
+    if (mexCallMATLAB(1, &out, 1, &dims, "randn") != 0) mexErrMsgIdAndTxt("tritd:randn", "randn failed.");
+    mxDestroyArray(dims);
+    return out;
+}
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs != 3) mexErrMsgIdAndTxt("tritd:nargin", "Usage: [A,B,C,O,errHist] = triple_decomp_ADMM(D, r, opts)");
+    if (nlhs > 6) mexErrMsgIdAndTxt("MATLAB:TooManyOutputs", "Too many output arguments.");
+    const mxArray* Dm = prhs[0];
+    if (!mxIsDouble(Dm) || mxIsComplex(Dm) || mxIsSparse(Dm)) mexErrMsgIdAndTxt("tritd:D", "D must be a full real double array.");
+    const mwSize nd = mxGetNumberOfDimensions(Dm);
+    const mwSize* dd = mxGetDimensions(Dm);
+    if (nd < 2 || nd > 3) mexErrMsgIdAndTxt("tritd:D", "D must be n1 x n2 x n3.");
+    const mwSize n1 = dd[0], n2 = dd[1], n3 = nd == 3 ? dd[2] : 1;   /* n3 = 1 arrives as 2-D */
+    if (n1 == 0 || n2 == 0 || n3 == 0) mexErrMsgIdAndTxt("tritd:D", "D must not be empty.");
+    if (mxGetNumberOfElements(prhs[1]) != 1) mexErrMsgIdAndTxt("tritd:r", "r must be a scalar.");
+    const int r = (int)mxGetScalar(prhs[1]);
+    if (r < 1 || (double)r != mxGetScalar(prhs[1])) mexErrMsgIdAndTxt("tritd:r", "r must be a positive integer.");
+    if (!mxIsStruct(prhs[2])) mexErrMsgIdAndTxt("tritd:opts", "opts must be a struct.");
+    const mxArray* om = prhs[2];
+
+    tritd_opts o;   /* the seven fields the reference reads at :16-20; anything else is ignored */
+    o.mu = req_field(om, "mu");
+    o.rho = req_field(om, "rho");
+    o.lambda_ = req_field(om, "lambda");
+    o.lambda2 = req_field(om, "lambda2");
+    o.maxIter = (int32_t)req_field(om, "maxIter");
+    o.tol = req_field(om, "tol");
+    o.disp = req_field(om, "disp") != 0.0;
+
+    /* initial factors: randn(n1,r,r), randn(r,n2,r), randn(r,r,n3) in this order (:23) */
+    const size_t R = (size_t)r * r;
+    mxArray *A0m = NULL, *B0m = NULL, *C0m = NULL;
+    const double* A0 = opt_factor(om, "A0", n1 * R);
+    const double* B0 = opt_factor(om, "B0", n2 * R);
+    const double* C0 = opt_factor(om, "C0", n3 * R);
+    if (!A0) { A0m = randn3(n1, r, r); A0 = mxGetPr(A0m); }
+    if (!B0) { B0m = randn3(r, n2, r); B0 = mxGetPr(B0m); }
+    if (!C0) { C0m = randn3(r, r, n3); C0 = mxGetPr(C0m); }
+
+    if (!g_ctx) {
+        const mxArray* dv = mxGetField(om, 0, "device");
+        if (tritd_create(dv ? (int)mxGetScalar(dv) : 0, &g_ctx) != TRITD_OK)
+            mexErrMsgIdAndTxt("tritd:cuda", "%s", tritd_last_error());
+        mexLock();
+        mexAtExit(at_exit);
+    }
+
+    const mwSize dA[3] = {n1, (mwSize)r, (mwSize)r}, dB[3] = {(mwSize)r, n2, (mwSize)r}, dC[3] = {(mwSize)r, (mwSize)r, n3};
+    const mwSize dO[3] = {n1, n2, n3};
+    mxArray* Am = mxCreateNumericArray(3, dA, mxDOUBLE_CLASS, mxREAL);
+    mxArray* Bm = mxCreateNumericArray(3, dB, mxDOUBLE_CLASS, mxREAL);
+    mxArray* Cm = mxCreateNumericArray(3, dC, mxDOUBLE_CLASS, mxREAL);
+    mxArray* Om = nlhs >= 4 ? mxCreateNumericArray(3, dO, mxDOUBLE_CLASS, mxREAL) : NULL;
+    mxArray* Lm = nlhs >= 6 ? mxCreateNumericArray(3, dO, mxDOUBLE_CLASS, mxREAL) : NULL;
+    double* eh = (double*)mxMalloc(sizeof(double) * (size_t)(o.maxIter > 0 ? o.maxIter : 1));
+    int32_t iters = 0;
+
+    /* inputs are MATLAB-owned and only read; the library prints the reference's progress line
+     * ("Iter %d, errL=%.2e, errO=%.2e", :60-62) itself when opts.disp is set */
+    const int st = tritd_admm_f64(g_ctx, mxGetPr(Dm), (int64_t)n1, (int64_t)n2, (int64_t)n3, r, &o, A0, B0, C0,
+                                  mxGetPr(Am), mxGetPr(Bm), mxGetPr(Cm), Om ? mxGetPr(Om) : NULL,
+                                  Lm ? mxGetPr(Lm) : NULL, eh, &iters, NULL);
+    if (A0m) mxDestroyArray(A0m);
+    if (B0m) mxDestroyArray(B0m);
+    if (C0m) mxDestroyArray(C0m);
+    if (st != TRITD_OK) {
+        mxFree(eh);
+        mexErrMsgIdAndTxt("tritd:solve", "%s", tritd_last_error());   /* long-jumps; mxArrays are reclaimed by MATLAB */
+    }
+
+    plhs[0] = Am;                                   /* nlhs == 0 still returns ans = A */
+    if (nlhs >= 2) plhs[1] = Bm; else mxDestroyArray(Bm);
+    if (nlhs >= 3) plhs[2] = Cm; else mxDestroyArray(Cm);
+    if (nlhs >= 4) plhs[3] = Om;
+    if (nlhs >= 5) {                                /* errHist = errHist(1:k)  (:68) */
+        plhs[4] = mxCreateDoubleMatrix((mwSize)iters, 1, mxREAL);
+        memcpy(mxGetPr(plhs[4]), eh, sizeof(double) * (size_t)iters);
+    }
+    if (nlhs >= 6) plhs[5] = Lm;
+    mxFree(eh);
+}
