@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the TriTD-ADMM hot path (BASELINE.json metric: ADMM iterations/s, fp64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfgX] [--impl reference]
+
+One "step" = one ADMM iteration (triple_decomp_ADMM.m:31-66) on the synthetic tensor of the
+named BASELINE config.  N=1 default workload: cfg3 (240x320x300, r=5), the shape the metric is
+quoted on.  N>1 (launched by torch.distributed.run, one rank per GPU): the SAME tensor sharded
+along mode 3 over the ranks ("strong" scaling), [RHS ; Gram] partials all-reduced with NCCL.
+
+Prints ONE JSON line (rank 0):
+  value     iterations/s with all inputs resident in HBM, timed with CUDA events on the launching
+            stream over exactly K iterations after W warm-up iterations, max over ranks;
+  e2e       iterations/s of one reference-facing call (tritd_admm_f64 through ctypes) with HOST
+            buffers: pinned D in, A/B/C/O/errHist out, H2D and D2H inside the timed region;
+  roofline  the fused element-wise kernel: 72*N algorithmic bytes per launch / its CUDA-event time;
+  cpu_baseline  the numpy/OpenBLAS oracle port timed on this box's host cores (rank 0, N=1).
+--impl reference times the oracle port alone (the MATLAB reference cannot run here).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "triple-tensor-decomposition-with-admm_b200"),):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "admm_iterations_per_second"
+UNIT = "iter/s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_arrays(name, t0=None, t1=None):
+    """Host arrays of the named config; [t0,t1) selects a mode-3 slab."""
+    from tritd import synth
+    n1, n2, n3, r, kind, frac, seed, opts = synth.CONFIGS[name]
+    if kind == "lowrank_sparse":
+        D = synth.make_lowrank_sparse(n1, n2, n3, r, frac, seed, t0=t0 or 0, t1=t1)
+    else:
+        D = synth.make_config(name)["D"]
+        if t0 is not None:
+            D = np.asfortranarray(D[:, :, t0:t1])
+    A0, B0, C0 = synth.init_factors(n1, n2, n3, r, 100 + seed)
+    if t0 is not None:
+        C0 = np.asfortranarray(C0[:, :, t0:t1])
+    return D, r, dict(opts), A0, B0, C0, (n1, n2, n3)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+             0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in self.NAMES.items():
+                    if r & bit and nm != "gpu_idle":
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_oracle_rate(name, steps, warmup, budget_s):
+    """ADMM iterations/s of the oracle port on the host cores: `warmup` untimed + `steps` timed
+    iterations (time stamps taken inside the loop).  To bound the run the tensor is cut to its
+    first `t_slices` mode-3 slices -- every pass of the iteration is linear in n3 -- and the rate
+    is scaled by t_slices/n3 to the full workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tritd_oracle as orc
+    D, r, opts, A0, B0, C0, (n1, n2, n3) = workload_arrays(name)
+    cal = min(4, n3)
+    t = time.perf_counter()
+    orc.triple_decomp_ADMM(np.asfortranarray(D[:, :, :cal]), r, dict(opts, maxIter=2, tol=0.0, disp=0), A0, B0,
+                           np.asfortranarray(C0[:, :, :cal]))
+    per_slice_iter = (time.perf_counter() - t) / (2 * cal)
+    t_slices = int(max(min(4, n3), min(n3, budget_s / max(per_slice_iter * (steps + warmup), 1e-9))))
+    Ds = np.asfortranarray(D[:, :, :t_slices]); Cs = np.asfortranarray(C0[:, :, :t_slices])
+    stamps = [time.perf_counter()]
+    orc.triple_decomp_ADMM(Ds, r, dict(opts, maxIter=steps + warmup, tol=0.0, disp=0), A0, B0, Cs,
+                           on_iter=lambda *a: stamps.append(time.perf_counter()))
+    dt = stamps[-1] - stamps[warmup]
+    rate_full = steps / dt * (t_slices / n3)
+    sample = (f"{warmup}+{steps} iterations of the numpy/OpenBLAS oracle on the first {t_slices} of {n3} mode-3 slices of {name} "
+              f"({n1}x{n2}x{t_slices}); rate scaled by {t_slices}/{n3} (every pass is linear in n3); BLAS threads = all "
+              f"{os.cpu_count()} cores, numpy element-wise passes single-threaded")
+    return rate_full, sample, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    steps, warm = args.steps, args.warmup
+    rate, sample, dt = cpu_oracle_rate(name, steps, warm, budget_s=120.0)
+    from tritd import synth
+    n1, n2, n3, r = synth.CONFIGS[name][:4]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"{name}: {synth.DESCRIPTIONS[name]}", "n1": n1, "n2": n2, "n3": n3, "r": r},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is MATLAB and cannot run here (no MATLAB/Octave); this is the numpy/OpenBLAS oracle port",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--impl", default="tritd", choices=["tritd", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import tritd
+    from tritd import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (tritd has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    name = args.workload
+    n1, n2, n3, r = synth.CONFIGS[name][:4]
+    t0, t1 = tritd.slab_bounds(n3, world, rank) if world > 1 else (0, n3)
+    D, r, opts, A0, B0, C0, _ = workload_arrays(name, t0 if world > 1 else None, t1 if world > 1 else None)
+    n3l = t1 - t0
+    N_global = n1 * n2 * n3
+    K, W = args.steps, args.warmup
+
+    if world > 1:
+        idbuf = [tritd.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(idbuf, src=0)
+        ctx = tritd.Context(local, rank, world, idbuf[0])
+    else:
+        ctx = tritd.Context(local)
+    # the library launches on THIS stream, and so do the timing events below (a dedicated non-default
+    # stream: the C ABI treats a NULL stream handle as "use the context's own stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    ctx.set_stream(stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident throughput ----------------
+    bench_opts = dict(opts, maxIter=W + K + 8, tol=0.0, disp=0)     # tol=0: the stopping rule never fires, every step is real
+    prob = tritd.Problem(ctx, n1, n2, n3l, r)
+    prob.set_D(D)
+    prob.init(bench_opts, A0, B0, C0)
+    prob.enqueue(W)
+    prob.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    prob.set_profiling(True)
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    prob.enqueue(K)
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launches - launches0
+    phase_ms, nprof = prob.phase_ms()
+    prob.set_profiling(False)
+    prob.sync()
+    res = prob.get(want_O=False)
+    assert res["iters"] == W + K, (res["iters"], W + K)
+    assert np.all(np.isfinite(res["errHist"]))
+    prob.close()
+    value = K / (ms_total * 1e-3)
+
+    # ---------------- roofline of the dominant kernel (fused element-wise pass) ----------------
+    peak, peak_src = load_peaks()
+    N_local = n1 * n2 * n3l
+    fused_ms = phase_ms[4] / max(1, nprof)
+    achieved = 72.0 * N_local / (fused_ms * 1e-3) * 1e-9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
+            tj = json.load(f)
+            if tj.get("workload") == name and world == 1:
+                traffic = tj.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    R = r * r
+    flops_iter = 8.0 * N_global * R + 2.0 * R * R * (n2 * n3 + n1 * n3 + n1 * n2)
+    roofline = {"bound": "hbm", "kernel": "k_fused (L reconstruction + O/E/dual/T update + residual norms)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": 72.0 * N_local, "kernel_ms": fused_ms,
+                "iteration_GBps_vs_96N": 96.0 * N_global / world / (ms_total / K * 1e-3) * 1e-9,
+                "iteration_fp64_TFLOPs": flops_iter / world / (ms_total / K * 1e-3) * 1e-12,
+                "dmma_peak_TFLOPs_measured": 37.2,
+                "phase_ms_per_iter": {nm: phase_ms[i] / max(1, nprof) for i, nm in enumerate(tritd.PHASES)}}
+
+    # ---------------- end to end through the reference-facing call, host buffers ----------------
+    e2e = None
+    ttt = None
+    if not args.no_e2e:
+        Dp = torch.empty(D.size, dtype=torch.float64).pin_memory()
+        Dn = Dp.numpy().reshape(D.shape, order="F")
+        Dn[...] = D
+        e2e_opts = dict(opts, maxIter=K, tol=0.0, disp=0)
+        tritd.triple_decomp_ADMM(Dn, r, dict(e2e_opts, maxIter=3), A0, B0, C0, ctx=ctx)       # warm-up call
+        barrier()
+        tw = time.perf_counter()
+        A, B, C, O, eh, info = tritd.triple_decomp_ADMM(Dn, r, e2e_opts, A0, B0, C0, ctx=ctx, return_info=True)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - tw)
+        assert len(eh) == K
+        h2d = (D.nbytes + A0.nbytes + B0.nbytes + C0.nbytes) / K
+        d2h = (O.nbytes + A.nbytes + B.nbytes + C.nbytes + eh.nbytes) / K
+        e2e = {"value": K / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "call": "tritd_admm_f64 (one call, pinned host D; alloc + H2D + K iterations + D2H of A,B,C,O,errHist)",
+               "seconds": dt, "h2d_ms": info["h2d_ms"], "iterate_ms": info["iterate_ms"], "d2h_ms": info["d2h_ms"]}
+        # time-to-tolerance with the reference's own options (tol 1e-5, maxIter 100)
+        barrier()
+        tw = time.perf_counter()
+        out = tritd.triple_decomp_ADMM(Dn, r, dict(opts, disp=0), A0, B0, C0, ctx=ctx, return_info=True)
+        torch.cuda.synchronize()
+        dt2 = max_over_ranks(time.perf_counter() - tw)
+        ttt = {"seconds_host_buffers": dt2, "seconds_device_loop": out[5]["iterate_ms"] * 1e-3, "iterations": len(out[4]),
+               "tol": opts["tol"], "maxIter": opts["maxIter"], "final_errHist": float(out[4][-1])}
+
+    # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, sample, _ = cpu_oracle_rate(name, steps=3, warmup=1, budget_s=20.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{name}: {synth.DESCRIPTIONS[name]}", "n1": n1, "n2": n2, "n3": n3, "r": r,
+                       "sharding": f"mode-3 slabs over {world} rank(s)", "opts": {k: opts[k] for k in ("mu", "rho", "lambda", "lambda2")},
+                       "l2": "inputs larger than L2 (6 state arrays x %.0f MB per rank vs 126 MB L2), no flush" % (N_local * 8e-6)},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "time_to_tol": ttt,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

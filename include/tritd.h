@@ -153,6 +153,16 @@ int tritd_problem_get(tritd_problem* p, double* A, double* B, double* C, double*
 /* Device-side views (dense column-major copies written to caller-owned device memory). */
 int tritd_problem_get_O_dev(tritd_problem* p, double* O_dev);
 int tritd_problem_get_L_dev(tritd_problem* p, double* L_dev);
+/* Per-phase device timing: when enabled, every enqueued iteration is bracketed by CUDA events on
+ * the context's stream at its phase boundaries.  tritd_problem_phase_ms() synchronises, adds up
+ * the elapsed milliseconds of each phase over all iterations recorded since the last call into
+ * ms_out[TRITD_NPHASE] and reports how many iterations that was.  Phases:
+ *   0 mode-1 MTTKRP (+partial reduce)   1 all-reduce + solve A + Gram(A)   2 shared pass P = T x_1 A
+ *   3 RHS_B/all-reduce/solve B/Gram(B)/RHS_C/solve C/Gram(C)   4 fused L/O/E/dual/T/norm kernel
+ *   5 norm reduce + all-reduce + errHist/mu/stopping rule */
+#define TRITD_NPHASE 6
+int tritd_problem_set_profiling(tritd_problem* p, int enable);
+int tritd_problem_phase_ms(tritd_problem* p, double* ms_out, int32_t* iters_out);
 /* Number of kernels launched by this library on this context so far. */
 int64_t tritd_launch_count(const tritd_ctx* ctx);
 

@@ -241,6 +241,9 @@ struct tritd_problem {
     tritd_opts opts{};
     bool has_D = false, initialized = false;
     int printed_k = 0;
+    int hist_cap = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;    // TRITD_NPHASE + 1 events per profiled iteration
     std::vector<void*> allocs;
 };
 
@@ -341,6 +344,7 @@ static int launch_solve(tritd_problem* p, const double* rhs, const double* S1, c
     a.n = n; a.R = p->R; a.RS = p->RS; a.ldt = p->ldt;
     const int P = p->R | 1;
     const size_t smem = (size_t)(p->R + 64) * P * sizeof(double);
+    if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_solve<<<(n + 63) / 64, 256, smem, c->stream>>>(a);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
@@ -360,6 +364,7 @@ extern "C" void tritd_problem_destroy(tritd_problem* p) {
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     for (void* q : p->allocs) cudaFree(q);
+    for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
     if (p->st_host) cudaFreeHost(p->st_host);
     delete p;
 }
@@ -541,12 +546,14 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
     CU_TRY(cudaMemcpyAsync(p->st, p->st_host, sizeof(IterState), cudaMemcpyHostToDevice, st));
 
     // history buffers sized by maxIter
-    {
+    if (o->maxIter > p->hist_cap) {
         double* q = nullptr;
         ST_TRY(dalloc(p, &q, (size_t)3 * o->maxIter));
-        p->errHist = q; p->errL = q + o->maxIter; p->errO = q + 2 * (size_t)o->maxIter;
-        CU_TRY(cudaMemsetAsync(q, 0, (size_t)3 * o->maxIter * 8, st));
+        p->errHist = q;
+        p->hist_cap = o->maxIter;
     }
+    p->errL = p->errHist + p->hist_cap; p->errO = p->errHist + 2 * (size_t)p->hist_cap;
+    CU_TRY(cudaMemsetAsync(p->errHist, 0, (size_t)3 * p->hist_cap * 8, st));
 
     // normD = norm(D(:))  (:28), all-reduced over the slabs
     k_sumsq_part<<<1024, 256, 0, st>>>(p->D, p->Np, p->norm_part);
@@ -572,15 +579,27 @@ static int enqueue_iteration(tritd_problem* p) {
     double* rhsA = p->bufA;
     double* SC = p->bufA + (size_t)p->n1 * p->RS;
     const int* stop = &p->st->stop;
+    auto mark = [&]() -> int {           // phase boundary (only when profiling)
+        if (!p->profiling) return TRITD_OK;
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreate(&e));
+        CU_TRY(cudaEventRecord(e, st));
+        p->prof_ev.push_back(e);
+        return TRITD_OK;
+    };
+    ST_TRY(mark());
 
     // update_A (:73-81): RHS = X1*F', Gram = (B2'B2) o (C3'C3) + lambda2*I
     ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, rhsA));
+    ST_TRY(mark());
     ST_TRY(allreduce_sum(c, p->bufA, (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS));
     ST_TRY(launch_solve(p, rhsA, p->SB, SC, p->opts.lambda2, p->A1, p->A1T, p->n1));
     ST_TRY(launch_small_gram(p, p->A1, p->n1, p->SA));
+    ST_TRY(mark());
 
     // update_B (:83-88) with the new A: RHS = X2*G', Gram = (A1'A1) o (C3'C3) + lambda2*I
     ST_TRY(launch_ppass(p, p->mapT));
+    ST_TRY(mark());
     k_rhsB<<<(unsigned)(((long)p->n2 * p->RS + 255) / 256), 256, 0, st>>>(p->P, p->C3, p->rhsB, p->n2, p->n3, p->RS, stop);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
@@ -595,14 +614,41 @@ static int enqueue_iteration(tritd_problem* p) {
     ST_TRY(launch_solve(p, p->rhsC, p->SA, p->SB, 1e-9, p->C3, nullptr, p->n3));
     ST_TRY(launch_small_gram(p, p->C3, p->n3, SC));   // partial over local slices, summed by the next all-reduce
 
+    ST_TRY(mark());
     // L, O, E, duals, next T, residual norms (:38-59, :33)
     ST_TRY(launch_fused(p, 0, nullptr));
+    ST_TRY(mark());
     k_sum_pairs<<<1, 256, 0, st>>>(p->norm_part, p->gridF, p->norms, stop);
     CU_TRY(cudaGetLastError());
     ST_TRY(allreduce_sum(c, p->norms, 2));
     k_finalize<<<1, 32, 0, st>>>(p->st, p->norms, p->errHist, p->errL, p->errO);
     CU_TRY(cudaGetLastError());
     c->launches += 2;
+    ST_TRY(mark());
+    return TRITD_OK;
+}
+
+extern "C" int tritd_problem_set_profiling(tritd_problem* p, int enable) {
+    if (!p) return fail(TRITD_ERR_INVALID, "NULL problem");
+    p->profiling = enable != 0;
+    return TRITD_OK;
+}
+
+extern "C" int tritd_problem_phase_ms(tritd_problem* p, double* ms_out, int32_t* iters_out) {
+    if (!p || !ms_out) return fail(TRITD_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    CU_TRY(cudaStreamSynchronize(p->ctx->stream));
+    const size_t per = TRITD_NPHASE + 1, n = p->prof_ev.size() / per;
+    for (int q = 0; q < TRITD_NPHASE; ++q) ms_out[q] = 0.0;
+    for (size_t it = 0; it < n; ++it)
+        for (int q = 0; q < TRITD_NPHASE; ++q) {
+            float ms = 0.f;
+            CU_TRY(cudaEventElapsedTime(&ms, p->prof_ev[it * per + q], p->prof_ev[it * per + q + 1]));
+            ms_out[q] += ms;
+        }
+    for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
+    p->prof_ev.clear();
+    if (iters_out) *iters_out = (int32_t)n;
     return TRITD_OK;
 }
 

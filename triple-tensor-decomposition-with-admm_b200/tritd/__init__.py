@@ -30,6 +30,8 @@ LIB_PATH = os.path.join(_HERE, "libtritd.so")
 REQUIRED_OPTS = ("mu", "rho", "lambda", "lambda2", "maxIter", "tol", "disp")
 MAX_R = 8
 NCCL_ID_BYTES = 128
+NPHASE = 6
+PHASES = ("mttkrp1", "solveA", "ppass", "solveBC", "fused", "finalize")
 
 
 class TritdError(RuntimeError):
@@ -76,6 +78,8 @@ SYMBOLS = {
     "tritd_problem_get_O_dev": (C.c_int, [_vp, _vp]),
     "tritd_problem_get_L_dev": (C.c_int, [_vp, _vp]),
     "tritd_launch_count": (C.c_int64, [_vp]),
+    "tritd_problem_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "tritd_problem_phase_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_int32)]),
     "tritd_triple_product_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, C.c_int, _vp]),
     "tritd_unfold_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int, _vp]),
     "tritd_buildF_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_int, _vp]),
@@ -240,6 +244,16 @@ class Problem:
                                                 _ptr(eL), _ptr(eO), C.byref(k)))
         k = k.value
         return dict(A=A, B=B, C=Cc, O=O, L=L, errHist=eh[:k].copy(), errL=eL[:k].copy(), errO=eO[:k].copy(), iters=k)
+
+    def set_profiling(self, enable=True):
+        _check(load_library().tritd_problem_set_profiling(self._h, int(bool(enable))))
+
+    def phase_ms(self):
+        """(ms per phase summed over the recorded iterations, iterations recorded); see TRITD_NPHASE in tritd.h."""
+        out = (C.c_double * NPHASE)()
+        n = C.c_int32()
+        _check(load_library().tritd_problem_phase_ms(self._h, out, C.byref(n)))
+        return list(out), n.value
 
     def get_O_dev(self, dev_ptr):
         _check(load_library().tritd_problem_get_O_dev(self._h, _vp(dev_ptr)))
