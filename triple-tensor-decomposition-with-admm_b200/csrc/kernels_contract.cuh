@@ -161,27 +161,31 @@ k_mttkrp1(const __grid_constant__ CUtensorMap mapT, const Mttkrp1Args a) {
     if (cur_it >= 0) flush(slot);
 }
 
-// Sum the per-CTA partials of k_mttkrp1 in CTA order (deterministic).  One thread per
-// (i, k); CTA c contributes to row i's tile `it` through slot 0 if its range starts in
-// `it`, through slot 1 if it started in the previous tile and crossed into `it`.
-__global__ void k_mttkrp1_reduce(const double* part, double* rhs, int n1, int RS, int n_it, int n_jc, int n3,
-                                 int grid_m, const int* stop) {
+// Sum the per-CTA partials of k_mttkrp1 in a fixed order (deterministic).  256 threads = 8 CTA-lanes x
+// 32 consecutive outputs (i,k); lane l adds the contributing CTAs c = l, l+8, ... and the 8 lanes are
+// combined by a fixed tree.  tile0[c]/tile1[c] (host-computed) are the first/last i-tile CTA c touched:
+// it contributes to tile `it` through slot it - tile0[c] of its `cta_stride`-sized partial block.
+__global__ void __launch_bounds__(256) k_mttkrp1_reduce(const double* part, size_t cta_stride, double* rhs, int n1, int RS,
+                                                       const int* tile0, const int* tile1, int grid_m,
+                                                       const int* stop) {
     if (*stop) return;
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long)n1 * RS) return;
-    const int i = (int)(idx / RS), k = (int)(idx - (long)i * RS);
-    const int it = i >> 7, il = i & 127;
-    const long per_it = (long)n_jc * n3, units = per_it * n_it;
+    __shared__ double red[8][33];
+    const int ol = threadIdx.x & 31, cl = threadIdx.x >> 5;
+    const long idx = (long)blockIdx.x * 32 + ol;
+    const bool ok = idx < (long)n1 * RS;
     double sum = 0.0;
-    for (int c = 0; c < grid_m; ++c) {
-        const long u0 = units * c / grid_m, u1 = units * (c + 1) / grid_m;
-        if (u1 <= u0) continue;
-        const int it0 = (int)(u0 / per_it), it1 = (int)((u1 - 1) / per_it);
-        if (it < it0 || it > it1) continue;
-        const int sl = it - it0;   // 0 or 1 (a range never spans three tiles: see host-side grid choice)
-        sum += part[((size_t)c * 2 + sl) * 128 * RS + (size_t)il * RS + k];
+    if (ok) {
+        const int i = (int)(idx / RS), k = (int)(idx - (long)i * RS);
+        const int it = i >> 7, il = i & 127;
+        for (int c = cl; c < grid_m; c += 8) {
+            const int t0 = tile0[c];
+            if (it >= t0 && it <= tile1[c]) sum += part[(size_t)c * cta_stride + ((size_t)(it - t0) * 128 + il) * RS + k];
+        }
     }
-    rhs[idx] = sum;
+    red[cl][ol] = sum;
+    __syncthreads();
+    if (cl == 0 && ok)
+        rhs[idx] = ((red[0][ol] + red[1][ol]) + (red[2][ol] + red[3][ol])) + ((red[4][ol] + red[5][ol]) + (red[6][ol] + red[7][ol]));
 }
 
 // ---------------------------------------------------------------------------
@@ -304,23 +308,27 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
     }
 }
 
-// rhsB[j][k] = sum_t C3[t][k] * P[t][j][k]: one thread per (j,k), t in order.
-__global__ void k_rhsB(const double* P, const double* C3, double* rhsB, int n2, int n3, int RS, const int* stop) {
+// rhsB[j][k] = sum_t C3[t][k] * P[t][j][k]: one CTA per row j, 256 threads = 8 t-lanes x 32 k,
+// each lane sums t = l, l+8, ... in order, fixed tree over the lanes.
+__global__ void __launch_bounds__(256) k_rhsB(const double* P, const double* C3, double* rhsB, int n2, int n3, int RS,
+                                               const int* stop) {
     if (*stop) return;
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long nrk = (long)n2 * RS;
-    if (idx >= nrk) return;
-    const int k = (int)(idx % RS);
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int t = 0;
-    for (; t + 3 < n3; t += 4) {
-        s0 += C3[(size_t)t * RS + k] * P[(size_t)t * nrk + idx];
-        s1 += C3[(size_t)(t + 1) * RS + k] * P[(size_t)(t + 1) * nrk + idx];
-        s2 += C3[(size_t)(t + 2) * RS + k] * P[(size_t)(t + 2) * nrk + idx];
-        s3 += C3[(size_t)(t + 3) * RS + k] * P[(size_t)(t + 3) * nrk + idx];
+    __shared__ double red[8][33];
+    const int j = blockIdx.x;
+    const int kl = threadIdx.x & 31, tl = threadIdx.x >> 5;
+    const size_t nrk = (size_t)n2 * RS;
+    for (int k0 = 0; k0 < RS; k0 += 32) {
+        const int k = k0 + kl;
+        double s = 0.0;
+        if (k < RS)
+            for (int t = tl; t < n3; t += 8) s = fma(C3[(size_t)t * RS + k], P[(size_t)t * nrk + (size_t)j * RS + k], s);
+        red[tl][kl] = s;
+        __syncthreads();
+        if (tl == 0 && k < RS)
+            rhsB[(size_t)j * RS + k] = ((red[0][kl] + red[1][kl]) + (red[2][kl] + red[3][kl])) +
+                                       ((red[4][kl] + red[5][kl]) + (red[6][kl] + red[7][kl]));
+        __syncthreads();
     }
-    for (; t < n3; ++t) s0 += C3[(size_t)t * RS + k] * P[(size_t)t * nrk + idx];
-    rhsB[idx] = (s0 + s1) + (s2 + s3);
 }
 
 // rhsC[t][k] = sum_j B2[j][k] * P[t][j][k]: one CTA per slice t, 256 threads = 8 j-lanes x 32 k

@@ -33,84 +33,122 @@ __global__ void __launch_bounds__(256) k_small_gram(const double* X, int n, int 
     S[idx] = (s0 + s1) + (s2 + s3);
 }
 
-// X[row][:] = RHS[row][:] * inv(S1 o S2 + alpha*I) for 64 rows per CTA.
-// Every CTA factors the R x R system itself (R <= 64: a few microseconds, no extra launch
-// on the critical path), then each of 64 threads runs forward/back substitution on its row.
-// Optionally also writes the transposed factor XT[k][row] (leading dimension ldt) that
-// k_ppass streams with TMA.
+// X[row][:] = RHS[row][:] * inv(S1 o S2 + alpha*I), 32 rows per CTA, 256 threads.
+// Every CTA inverts the R x R ridge system itself by Gauss-Jordan elimination on [G | I] in shared
+// memory (SPD, so no pivoting; pivots are the Cholesky pivots d_k = L_kk^2 and a non-positive or
+// non-finite one is reported through IterState::status) -- R <= 64, a few microseconds, and no
+// extra launch on the critical path -- and then applies it to its rows like the reference applies
+// pinv(G) (:78).  The CTA also forms the partial small Gram X'X of its rows; the last CTA to finish
+// (ticket counter) sums the partials in CTA order, so S_out = X'X is deterministic and needs no
+// separate kernel.  Optionally writes the transposed factor XT[k][row] that k_ppass streams with TMA.
 struct SolveArgs {
     const double* rhs;     // [n][RS]
     const double *S1, *S2; // [RS][RS]
     double alpha;
     double* X;             // [n][RS]
     double* XT;            // [RS][ldt] or nullptr
+    double* gram_part;     // [grid][R*R]
+    double* gram_out;      // [RS][RS]  (= X'X over the rows of this rank)
+    unsigned* ticket;
     IterState* st;
     int n, R, RS, ldt;
 };
 
+constexpr int kSolveRows = 32;
+
 __global__ void __launch_bounds__(256) k_solve(const SolveArgs a) {
     if (a.st->stop) return;
     extern __shared__ double sm[];
-    const int R = a.R, P = R | 1;   // odd pitch: 64-bit row accesses of a half-warp hit 16 distinct bank pairs
-    double* Lm = sm;              // [R][P]  lower Cholesky factor
-    double* rows = sm + R * P;    // [64][P]
+    const int R = a.R, W2 = 2 * R, PW = W2 | 1, P = R | 1;
+    double* Wm = sm;                       // [R][PW]   [G | I] -> [I | inv(G)]
+    double* rowk = Wm + R * PW;            // [2R]
+    double* colk = rowk + W2;              // [R]
+    double* rows = colk + R;               // [32][P]   RHS rows
+    double* xr = rows + kSolveRows * P;    // [32][P]   solved rows
+    __shared__ int s_last;
     const int tid = threadIdx.x;
+    const int row0 = blockIdx.x * kSolveRows;
 
-    for (int e = tid; e < R * R; e += 256) {
-        const int i = e / R, j = e - i * R;
-        double v = a.S1[i * a.RS + j] * a.S2[i * a.RS + j];
-        if (i == j) v += a.alpha;
-        Lm[i * P + j] = v;
+    for (int e = tid; e < R * W2; e += 256) {
+        const int i = e / W2, j = e - i * W2;
+        double v;
+        if (j < R) {
+            v = a.S1[i * a.RS + j] * a.S2[i * a.RS + j];
+            if (i == j) v += a.alpha;
+        } else {
+            v = (j - R == i) ? 1.0 : 0.0;
+        }
+        Wm[i * PW + j] = v;
     }
-    const int row0 = blockIdx.x * 64;
-    for (int e = tid; e < 64 * R; e += 256) {
+    for (int e = tid; e < kSolveRows * R; e += 256) {
         const int rr = e / R, k = e - rr * R;
         rows[rr * P + k] = (row0 + rr < a.n) ? a.rhs[(size_t)(row0 + rr) * a.RS + k] : 0.0;
     }
     __syncthreads();
 
-    // right-looking Cholesky on the lower triangle
     for (int k = 0; k < R; ++k) {
-        const double d = Lm[k * P + k];
-        if (!(d > 0.0) || !isfinite(d)) {          // uniform across the CTA
+        const double piv = Wm[k * PW + k];
+        if (!(piv > 0.0) || !isfinite(piv)) {          // uniform across the CTA
             if (tid == 0) atomicExch(&a.st->status, kStatusCholesky);
             return;
         }
-        const double sd = sqrt(d);
+        const double inv = 1.0 / piv;
+        if (tid < W2) rowk[tid] = Wm[k * PW + tid] * inv;
+        else if (tid - W2 < R) colk[tid - W2] = Wm[(tid - W2) * PW + k];
+        if (W2 + R > 256)                               // R = 64: 192 threads' worth of work, fits; kept general
+            for (int q = 256 + tid; q < W2 + R; q += 256) colk[q - W2] = Wm[(q - W2) * PW + k];
         __syncthreads();
-        for (int i = k + tid; i < R; i += 256) Lm[i * P + k] = (i == k) ? sd : Lm[i * P + k] / sd;
-        __syncthreads();
-        const int m = R - k - 1;
-        for (int e = tid; e < m * m; e += 256) {
-            const int i = k + 1 + e / m, j = k + 1 + e % m;
-            if (j <= i) Lm[i * P + j] -= Lm[i * P + k] * Lm[j * P + k];
+        for (int e = tid; e < R * W2; e += 256) {
+            const int i = e / W2, j = e - i * W2;
+            Wm[i * PW + j] = (i == k) ? rowk[j] : Wm[i * PW + j] - colk[i] * rowk[j];
         }
         __syncthreads();
     }
 
-    if (tid < 64) {
-        double* b = rows + tid * P;
-        for (int k = 0; k < R; ++k) {              // L y = b
-            double s = b[k];
-            for (int m = 0; m < k; ++m) s -= Lm[k * P + m] * b[m];
-            b[k] = s / Lm[k * P + k];
+    // apply: xr[rr][k] = sum_m rows[rr][m] * inv(G)[m][k]
+    for (int e = tid; e < kSolveRows * R; e += 256) {
+        const int rr = e / R, k = e - rr * R;
+        double s0 = 0.0, s1 = 0.0;
+        int m = 0;
+        for (; m + 1 < R; m += 2) {
+            s0 = fma(rows[rr * P + m], Wm[m * PW + R + k], s0);
+            s1 = fma(rows[rr * P + m + 1], Wm[(m + 1) * PW + R + k], s1);
         }
-        for (int k = R - 1; k >= 0; --k) {         // L' x = y
-            double s = b[k];
-            for (int m = k + 1; m < R; ++m) s -= Lm[m * P + k] * b[m];
-            b[k] = s / Lm[k * P + k];
-        }
+        if (m < R) s0 = fma(rows[rr * P + m], Wm[m * PW + R + k], s0);
+        xr[rr * P + k] = s0 + s1;
     }
     __syncthreads();
-    for (int e = tid; e < 64 * a.RS; e += 256) {
+    for (int e = tid; e < kSolveRows * a.RS; e += 256) {
         const int rr = e / a.RS, k = e - rr * a.RS;
-        if (row0 + rr < a.n) a.X[(size_t)(row0 + rr) * a.RS + k] = (k < R) ? rows[rr * P + k] : 0.0;
+        if (row0 + rr < a.n) a.X[(size_t)(row0 + rr) * a.RS + k] = (k < R) ? xr[rr * P + k] : 0.0;
     }
     if (a.XT) {
-        for (int e = tid; e < 64 * a.RS; e += 256) {
-            const int k = e / 64, rr = e - k * 64;
-            if (row0 + rr < a.n) a.XT[(size_t)k * a.ldt + row0 + rr] = (k < R) ? rows[rr * P + k] : 0.0;
+        for (int e = tid; e < kSolveRows * a.RS; e += 256) {
+            const int k = e / kSolveRows, rr = e - k * kSolveRows;
+            if (row0 + rr < a.n) a.XT[(size_t)k * a.ldt + row0 + rr] = (k < R) ? xr[rr * P + k] : 0.0;
         }
+    }
+    // partial small Gram of this CTA's rows (rows beyond n are zero)
+    for (int e = tid; e < R * R; e += 256) {
+        const int aa = e / R, bb = e - aa * R;
+        double s = 0.0;
+#pragma unroll 4
+        for (int rr = 0; rr < kSolveRows; ++rr) s = fma(xr[rr * P + aa], xr[rr * P + bb], s);
+        a.gram_part[(size_t)blockIdx.x * R * R + e] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int e = tid; e < R * R; e += 256) {
+            double s = 0.0;
+            for (unsigned c = 0; c < gridDim.x; ++c) s += a.gram_part[(size_t)c * R * R + e];
+            const int aa = e / R, bb = e - aa * R;
+            a.gram_out[aa * a.RS + bb] = s;
+        }
+        if (tid == 0) *a.ticket = 0u;
     }
 }
 

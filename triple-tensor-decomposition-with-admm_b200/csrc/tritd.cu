@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "kernels_admm.cuh"
 #include "kernels_aux.cuh"
 #include "kernels_contract.cuh"
 #include "kernels_fused.cuh"
@@ -231,10 +232,18 @@ struct tritd_problem {
     double *bufA = nullptr;              // [rhsA (n1*RS) ; SC (RS*RS)] -- one all-reduce
     double *rhsB = nullptr, *rhsC = nullptr, *P = nullptr, *partM = nullptr;
     double *norm_part = nullptr, *norms = nullptr;
+    double* gram_part = nullptr;         // per-CTA partial small Grams of k_solve
+    unsigned* ticket = nullptr;
+    int *tile0 = nullptr, *tile1 = nullptr;   // first / last i-tile of each k_mttkrp1 CTA
     IterState* st = nullptr;
     double *errHist = nullptr, *errL = nullptr, *errO = nullptr;
     IterState* st_host = nullptr;        // pinned mirror
     CUtensorMap mapT, mapA1T;
+    alignas(64) AdmmMaps maps;           // [8 j][16 i] boxes of D, Y_L, E, Y_O, T, O for k_admm
+    double* partF = nullptr;             // [gridA][128][RS] fused mode-1 partials (next iteration's X1*F')
+    int *tileF = nullptr;                // i-tile of each k_admm CTA
+    int gridA = 0, giA = 0;
+    bool rhsA_ready = false;             // partF holds X1*F' of the current T
     int n_it = 0, n_jc = 0, gridM = 0, gridP = 0, gridF = 0, gi = 0;
     long unitsM = 0, unitsP = 0;
     size_t smemM = 0, smemP = 0;
@@ -289,15 +298,14 @@ static int launch_mttkrp1(tritd_problem* p, const CUtensorMap& map, const double
     Mttkrp1Args a;
     a.B2 = B2; a.C3 = C3; a.part = p->partM; a.stop = &p->st->stop;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_it = p->n_it; a.n_jc = p->n_jc; a.units = p->unitsM;
-#define CALL(NT_, KS_)                                                                                         \
-    CU_TRY(cudaFuncSetAttribute(k_mttkrp1<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemM)); \
+#define CALL(NT_, KS_) \
     k_mttkrp1<NT_><<<p->gridM, (kCW + 1) * 32, p->smemM, c->stream>>>(map, a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
     CU_TRY(cudaGetLastError());
     const long tot = (long)p->n1 * p->RS;
-    k_mttkrp1_reduce<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(p->partM, rhs_out, p->n1, p->RS, p->n_it,
-                                                                         p->n_jc, p->n3, p->gridM, &p->st->stop);
+    k_mttkrp1_reduce<<<(unsigned)((tot + 31) / 32), 256, 0, c->stream>>>(p->partM, (size_t)2 * 128 * p->RS, rhs_out, p->n1,
+                                                                       p->RS, p->tile0, p->tile1, p->gridM, &p->st->stop);
     CU_TRY(cudaGetLastError());
     c->launches += 2;
     return TRITD_OK;
@@ -309,8 +317,7 @@ static int launch_ppass(tritd_problem* p, const CUtensorMap& mapT) {
     a.P = p->P; a.stop = &p->st->stop;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS;
     a.n_jb = p->n_jc; a.n_rb = (long)p->n3 * p->n_jc; a.units = p->unitsP;
-#define CALL(NT_, KS_)                                                                                       \
-    CU_TRY(cudaFuncSetAttribute(k_ppass<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemP)); \
+#define CALL(NT_, KS_) \
     k_ppass<NT_><<<p->gridP, (kCW + 1) * 32, p->smemP, c->stream>>>(mapT, p->mapA1T, a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
@@ -336,16 +343,45 @@ static int launch_fused(tritd_problem* p, int mode, double* Lout) {
     return TRITD_OK;
 }
 
+// The fused iteration kernel (TMA in / DMMA / TMA out); also leaves the next X1*F' partials in partF.
+static int launch_admm(tritd_problem* p) {
+    tritd_ctx* c = p->ctx;
+    AdmmArgs a;
+    a.A1 = p->A1; a.B2 = p->B2; a.C3 = p->C3; a.st = p->st; a.norm_part = p->norm_part; a.partM = p->partF;
+    a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_it = p->n_it; a.n_jc = p->n_jc; a.gi = p->giA;
+#define CALL(NT_, KS_) \
+    k_admm<KS_, NT_, true><<<p->gridA, 256, AdmmCfg<KS_, NT_, true>::kSmem, c->stream>>>(p->maps, a);
+    TRITD_DISPATCH_R(p->r, CALL)
+#undef CALL
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+static int launch_reduce_fused_rhsA(tritd_problem* p, double* rhs_out) {
+    tritd_ctx* c = p->ctx;
+    const long tot = (long)p->n1 * p->RS;
+    k_mttkrp1_reduce<<<(unsigned)((tot + 31) / 32), 256, 0, c->stream>>>(p->partF, (size_t)128 * p->RS, rhs_out, p->n1, p->RS,
+                                                                       p->tileF, p->tileF, p->gridA, &p->st->stop);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+static size_t smem_solve(int R) {
+    const int PW = (2 * R) | 1, P = R | 1;
+    return (size_t)(R * PW + 3 * R + 2 * kSolveRows * P) * sizeof(double);
+}
+
+// X = rhs * inv(S1 o S2 + alpha I); also S_out = X'X (rows of this rank) and optionally X transposed.
 static int launch_solve(tritd_problem* p, const double* rhs, const double* S1, const double* S2, double alpha, double* X,
-                        double* XT, int n) {
+                        double* XT, int n, double* S_out) {
     tritd_ctx* c = p->ctx;
     SolveArgs a;
     a.rhs = rhs; a.S1 = S1; a.S2 = S2; a.alpha = alpha; a.X = X; a.XT = XT; a.st = p->st;
+    a.gram_part = p->gram_part; a.gram_out = S_out; a.ticket = p->ticket;
     a.n = n; a.R = p->R; a.RS = p->RS; a.ldt = p->ldt;
-    const int P = p->R | 1;
-    const size_t smem = (size_t)(p->R + 64) * P * sizeof(double);
-    if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_solve<<<(n + 63) / 64, 256, smem, c->stream>>>(a);
+    k_solve<<<(n + kSolveRows - 1) / kSolveRows, 256, smem_solve(p->R), c->stream>>>(a);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     return TRITD_OK;
@@ -419,11 +455,50 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     p->gridF = p->gi * p->n_it;
 
     PALLOC(partM, (size_t)p->gridM * 2 * 128 * p->RS);
-    PALLOC(norm_part, (size_t)2 * std::max(p->gridF, 1024));
+    {
+        const int nmax = std::max(p->n1, std::max(p->n2, p->n3));
+        PALLOC(gram_part, (size_t)((nmax + kSolveRows - 1) / kSolveRows) * p->R * p->R);
+        PALLOC(ticket, 4);
+        PALLOC(tile0, p->gridM); PALLOC(tile1, p->gridM);
+        std::vector<int> t0(p->gridM), t1(p->gridM);
+        const long per_it = (long)p->n_jc * p->n3;
+        for (int q = 0; q < p->gridM; ++q) {
+            const long u0 = p->unitsM * q / p->gridM, u1 = p->unitsM * (q + 1) / p->gridM;
+            t0[q] = (int)(u0 / per_it);
+            t1[q] = u1 > u0 ? (int)((u1 - 1) / per_it) : t0[q] - 1;
+        }
+        cudaMemcpy(p->tile0, t0.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
+        cudaMemcpy(p->tile1, t1.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
+        cudaMemset(p->ticket, 0, 16);
+        p->giA = std::max(1, c->num_sms / p->n_it);
+        p->gridA = p->giA * p->n_it;
+        PALLOC(partF, (size_t)p->gridA * 128 * p->RS);
+        PALLOC(tileF, p->gridA);
+        std::vector<int> tf(p->gridA);
+        for (int q = 0; q < p->gridA; ++q) tf[q] = q % p->n_it;
+        cudaMemcpy(p->tileF, tf.data(), sizeof(int) * p->gridA, cudaMemcpyHostToDevice);
+    }
+    PALLOC(norm_part, (size_t)2 * std::max(std::max(p->gridF, c->num_sms), 1024));
     PALLOC(norms, 8);
     PALLOC(st, 1);
 #undef PALLOC
     if (cudaMallocHost((void**)&p->st_host, sizeof(IterState)) != cudaSuccess) return bail(fail(TRITD_ERR_CUDA, "cudaMallocHost failed"));
+
+    // opt in to the large dynamic shared-memory carve-outs once
+    {
+        auto q = [&]() -> int {
+#define CALL(NT_, KS_)                                                                                            \
+    CU_TRY(cudaFuncSetAttribute(k_mttkrp1<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemM));    \
+    CU_TRY(cudaFuncSetAttribute(k_ppass<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemP));      \
+    CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
+                                (int)AdmmCfg<KS_, NT_, true>::kSmem));
+            TRITD_DISPATCH_R(r, CALL)
+#undef CALL
+            CU_TRY(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(TRITD_MAX_R * TRITD_MAX_R)));
+            return TRITD_OK;
+        };
+        if ((s = q()) != TRITD_OK) return bail(s);
+    }
 
     // zero everything once: pad rows / pad columns must be exact zeros forever
     cudaStream_t st = c->stream;
@@ -438,6 +513,11 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         cuuint64_t str[2] = {(cuuint64_t)p->ld1 * 8, (cuuint64_t)p->ld1 * p->n2 * 8};
         cuuint32_t box[3] = {16, (cuuint32_t)kBoxRows, 1};
         if ((s = make_map(c, &p->mapT, p->T, 3, dims, str, box)) != TRITD_OK) return bail(s);
+        cuuint32_t box8[3] = {16, 8, 1};
+        struct { CUtensorMap* m; double* base; } mm[6] = {{&p->maps.D, p->D}, {&p->maps.YL, p->YL}, {&p->maps.E, p->E},
+                                                         {&p->maps.YO, p->YO}, {&p->maps.T, p->T}, {&p->maps.O, p->O}};
+        for (auto& q : mm)
+            if ((s = make_map(c, q.m, q.base, 3, dims, str, box8)) != TRITD_OK) return bail(s);
         cuuint64_t dims2[2] = {(cuuint64_t)p->n1, (cuuint64_t)p->RS};
         cuuint64_t str2[1] = {(cuuint64_t)p->ldt * 8};
         cuuint32_t box2[2] = {16, (cuuint32_t)p->RS};
@@ -568,6 +648,7 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
     ST_TRY(launch_small_gram(p, p->C3, p->n3, p->bufA + (size_t)p->n1 * p->RS));
     CU_TRY(cudaStreamSynchronize(st));
     p->initialized = true;
+    p->rhsA_ready = false;
     p->printed_k = 0;
     return TRITD_OK;
 }
@@ -590,35 +671,36 @@ static int enqueue_iteration(tritd_problem* p) {
     ST_TRY(mark());
 
     // update_A (:73-81): RHS = X1*F', Gram = (B2'B2) o (C3'C3) + lambda2*I
-    ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, rhsA));
+    // (from the second iteration on the previous k_admm already accumulated it from registers)
+    if (p->rhsA_ready) ST_TRY(launch_reduce_fused_rhsA(p, rhsA));
+    else ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, rhsA));
     ST_TRY(mark());
     ST_TRY(allreduce_sum(c, p->bufA, (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS));
-    ST_TRY(launch_solve(p, rhsA, p->SB, SC, p->opts.lambda2, p->A1, p->A1T, p->n1));
-    ST_TRY(launch_small_gram(p, p->A1, p->n1, p->SA));
+    ST_TRY(launch_solve(p, rhsA, p->SB, SC, p->opts.lambda2, p->A1, p->A1T, p->n1, p->SA));
     ST_TRY(mark());
 
     // update_B (:83-88) with the new A: RHS = X2*G', Gram = (A1'A1) o (C3'C3) + lambda2*I
     ST_TRY(launch_ppass(p, p->mapT));
     ST_TRY(mark());
-    k_rhsB<<<(unsigned)(((long)p->n2 * p->RS + 255) / 256), 256, 0, st>>>(p->P, p->C3, p->rhsB, p->n2, p->n3, p->RS, stop);
+    k_rhsB<<<p->n2, 256, 0, st>>>(p->P, p->C3, p->rhsB, p->n2, p->n3, p->RS, stop);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     ST_TRY(allreduce_sum(c, p->rhsB, (size_t)p->n2 * p->RS));
-    ST_TRY(launch_solve(p, p->rhsB, p->SA, SC, p->opts.lambda2, p->B2, nullptr, p->n2));
-    ST_TRY(launch_small_gram(p, p->B2, p->n2, p->SB));
+    ST_TRY(launch_solve(p, p->rhsB, p->SA, SC, p->opts.lambda2, p->B2, nullptr, p->n2, p->SB));
 
     // update_C (:90-95) with the new A, B: slice-local; ridge fixed at 1e-9
     k_rhsC<<<p->n3, 256, 0, st>>>(p->P, p->B2, p->rhsC, p->n2, p->n3, p->RS, stop);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
-    ST_TRY(launch_solve(p, p->rhsC, p->SA, p->SB, 1e-9, p->C3, nullptr, p->n3));
-    ST_TRY(launch_small_gram(p, p->C3, p->n3, SC));   // partial over local slices, summed by the next all-reduce
+    // also leaves SC = C3'C3 over the local slices in bufA, where the next all-reduce sums it over ranks
+    ST_TRY(launch_solve(p, p->rhsC, p->SA, p->SB, 1e-9, p->C3, nullptr, p->n3, SC));
 
     ST_TRY(mark());
     // L, O, E, duals, next T, residual norms (:38-59, :33)
-    ST_TRY(launch_fused(p, 0, nullptr));
+    ST_TRY(launch_admm(p));
+    p->rhsA_ready = true;
     ST_TRY(mark());
-    k_sum_pairs<<<1, 256, 0, st>>>(p->norm_part, p->gridF, p->norms, stop);
+    k_sum_pairs<<<1, 256, 0, st>>>(p->norm_part, p->gridA, p->norms, stop);
     CU_TRY(cudaGetLastError());
     ST_TRY(allreduce_sum(c, p->norms, 2));
     k_finalize<<<1, 32, 0, st>>>(p->st, p->norms, p->errHist, p->errL, p->errO);
@@ -947,7 +1029,7 @@ extern "C" int tritd_mttkrp_f64(tritd_ctx* c, const double* X, const double* A, 
             CU_TRY(cudaStreamSynchronize(st));
             ST_TRY(launch_ppass(p, p->mapT));
             if (mode == 2) {
-                k_rhsB<<<(unsigned)(((long)p->n2 * p->RS + 255) / 256), 256, 0, st>>>(p->P, p->C3, p->rhsB, p->n2, p->n3, p->RS, &p->st->stop);
+                k_rhsB<<<p->n2, 256, 0, st>>>(p->P, p->C3, p->rhsB, p->n2, p->n3, p->RS, &p->st->stop);
                 CU_TRY(cudaMemcpyAsync(h.data(), p->rhsB, h.size() * 8, cudaMemcpyDeviceToHost, st));
             } else {
                 k_rhsC<<<p->n3, 256, 0, st>>>(p->P, p->B2, p->rhsC, p->n2, p->n3, p->RS, &p->st->stop);
