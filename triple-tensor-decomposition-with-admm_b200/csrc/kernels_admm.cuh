@@ -8,11 +8,15 @@
 //   :74-78   X1*F' of the NEXT iteration's update_A (mode-1 MTTKRP of the new T), accumulated
 //            from registers so T is read from HBM only once per iteration (by k_ppass).
 //
-// Data movement: every warp owns 16 rows i and runs a private S-stage ring of 1 KB TMA boxes
-// [8 j][16 i] (128B-swizzled) for D, Y_L, E, Y_O; results are written back in place in shared memory
-// (T over D) plus one extra box for O and leave through TMA stores.  No thread touches HBM with a
-// load/store instruction; out-of-range rows/columns are zero-filled on load and clipped on store by
-// the tensor maps.  Algorithmic traffic: 4 reads + 5 writes = 72 bytes per element.
+// Structure: CTA = 8 consumer warps x 16 rows i (an i-tile of 128 rows) + 1 warp that drives TMA.
+// A stage is one "j-group": 8 columns j of slice t for the whole i-tile, i.e. four 8 KB boxes
+// (D, Y_L, E, Y_O) fetched by ONE TMA op each through a 4-D view (i_lo=16, j, i_hi, t) of the
+// column-major arrays, which lands as [warp][8 j][16 i] with the 128B swizzle pattern the DMMA
+// accumulator layout reads conflict-free.  Consumers update the boxes in place (T over D) plus a fifth
+// box for O; the TMA warp then streams the five boxes back with one TMA store each and refills the
+// slot.  No thread touches HBM with a load/store instruction; rows/columns outside the tensor are
+// zero-filled on load and clipped on store by the tensor maps (ld1 is a multiple of 16 so the padded
+// rows exist and stay zero).  Algorithmic traffic: 4 reads + 5 writes = 72 bytes per element.
 #pragma once
 #include "common.cuh"
 #include "kernels_contract.cuh"
@@ -27,182 +31,290 @@ struct AdmmArgs {
     const IterState* st;
     double* norm_part;                 // [grid][2]
     double* partM;                     // [grid][128][RS]: this CTA's partial of the next X1*F'
+    const int* cta_tab;                // [grid][3]: i-tile, index within the tile's CTAs, CTAs of that tile
     int n1, n2, n3, RS;
-    int n_it, n_jc, gi;                // i-tiles (128), j-chunks (32), CTAs per i-tile
+    int n_jc;                          // j-chunks (32 columns)
 };
+
+constexpr int kBoxD = 8 * 128;         // doubles per array per stage: [8 warps][8 j][16 i]
 
 template <int KS, int NT, bool WRITE_O> struct AdmmCfg {
     static constexpr int PL = FusedCfg<KS>::PL;
-    static constexpr int NB = WRITE_O ? 5 : 4;                       // boxes per stage
+    static constexpr int NB = WRITE_O ? 5 : 4;                                  // boxes per stage
+    static constexpr int kStageBytes = NB * kBoxD * 8 + 1024;                   // + the C3 row of the slice; keeps boxes 1 KB aligned
     static constexpr int kFixed = (32 * PL + NT * 8 * kPJ + 64) * 8 + 1024;
     static constexpr int kAvail = 227 * 1024 - kFixed;
-    static constexpr int S = (kAvail / (8 * NB * 1024)) > 6 ? 6 : (kAvail / (8 * NB * 1024));
-    static constexpr size_t kSmem = (size_t)8 * S * NB * 1024 + kFixed;
+    static constexpr int S = (kAvail / kStageBytes) > 6 ? 6 : (kAvail / kStageBytes);
+    static constexpr size_t kSmem = (size_t)S * kStageBytes + kFixed;
     static_assert(S >= 3, "ring too shallow");
 };
 
+// 1-D bulk copy global -> shared with mbarrier completion (the C3 row of a slice).  SASS: UBLKCP.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+// Correctly rounded a/b for normal-range operands from y = RN(1/b): q0 = RN(a*y), r = a - q0*b (exact in
+// one FMA), q = RN(q0 + r*y) (Markstein).  Replaces the ~35-instruction IEEE division sequence in the O update.
+__device__ __forceinline__ double div_by(double a, double b, double y) {
+    const double q0 = __dmul_rn(a, y);
+    const double r = __fma_rn(-q0, b, a);
+    return __fma_rn(r, y, q0);
+}
+
+// One element of triple_decomp_ADMM.m:41-53 and the next T (:33); same association as the MATLAB
+// expressions, every operation an explicit round-to-nearest intrinsic (no FMA contraction).
+struct AdmmPrm { double muL, muO, rmuL, rmuO, thr, musum, rmusum, rmuL_next; };
+
+__device__ __forceinline__ void admm_point2(const AdmmPrm& p, double d, double l, double& yl, double& e, double& yo,
+                                            double& o, double& tn, double& sL, double& sO) {
+    const double dl = __dsub_rn(d, l);                                   // D - L
+    const double r1 = __dadd_rn(dl, __dmul_rn(p.rmuL, yl));              // R1 = D - L + (1/muL)*Y_L
+    const double my = __dmul_rn(p.rmuO, yo);                             // (1/muO)*Y_O
+    const double r2 = __dsub_rn(e, my);                                  // R2 = E - (1/muO)*Y_O
+    o = div_by(__dadd_rn(__dmul_rn(p.muL, r1), __dmul_rn(p.muO, r2)), p.musum, p.rmusum);
+    const double r3 = __dadd_rn(o, my);                                  // R3 = O + (1/muO)*Y_O
+    const double mx = fmax(__dsub_rn(fabs(r3), p.thr), 0.0);
+    const double en = r3 > 0.0 ? mx : (r3 < 0.0 ? -mx : 0.0);            // sign(R3).*max(|R3|-lambda/muO,0)
+    const double resL = __dsub_rn(dl, o);                                // D - L - O
+    const double resO = __dsub_rn(o, en);                                // O - E
+    yl = __dadd_rn(yl, __dmul_rn(p.muL, resL));
+    yo = __dadd_rn(yo, __dmul_rn(p.muO, resO));
+    e = en;
+    tn = __dadd_rn(__dsub_rn(d, o), __dmul_rn(p.rmuL_next, yl));         // next T = D - O + (1/muL')*Y_L
+    sL = fma(resL, resL, sL);
+    sO = fma(resO, resO, sO);
+}
+
+// Block = 3 warpgroups: two of consumers (8 warps), one whose first lane drives TMA.  The kernel is
+// compiled for 168 registers/thread (65536 / 384); the TMA warpgroup gives most of its share back and
+// the consumers grow to 224 with setmaxnreg, so the DMMA accumulators and fragments never spill.
+constexpr int kAdmmThreads = 384;
+
 template <int KS, int NT, bool WRITE_O>
-__global__ void __launch_bounds__(256, 1) k_admm(const __grid_constant__ AdmmMaps maps, const AdmmArgs a) {
+__global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant__ AdmmMaps maps, const AdmmArgs a) {
     using Cfg = AdmmCfg<KS, NT, WRITE_O>;
-    constexpr int PL = Cfg::PL, NB = Cfg::NB, S = Cfg::S, PD = S - 2;
+    constexpr int PL = Cfg::PL, NB = Cfg::NB, S = Cfg::S;
+    constexpr int kStageD = Cfg::kStageBytes / 8;
+    constexpr bool kFoldA = KS <= 8;      // fold C3[t,:] into the A fragments once per slice (else into B per use)
     if (a.st->stop) return;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    double* ring = reinterpret_cast<double*>(smem_raw);              // [8 warps][S][NB][128]
-    double* B2s = ring + 8 * S * NB * 128;                           // [32 j][PL]      B-operand of L
+    double* ring = reinterpret_cast<double*>(smem_raw);              // [S][NB boxes + C3 row]
+    double* B2s = ring + (size_t)S * kStageD;                        // [32 j][PL]      B-operand of L
     double* B2T = B2s + 32 * PL;                                     // [NT*8 k][kPJ]   B-operand of the MTTKRP
     double* red = B2T + NT * 8 * kPJ;                                // [64]
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + 64);          // [8][S]
-    __shared__ IterState prm_s;
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + 64);          // [S] TMA landed
+    uint64_t* done = full + S;                                       // [S] consumers finished writing back
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, tig = lane & 3;
-    const int it = blockIdx.x % a.n_it, x = blockIdx.x / a.n_it;
+    const int it = a.cta_tab[3 * blockIdx.x], x = a.cta_tab[3 * blockIdx.x + 1], gi = a.cta_tab[3 * blockIdx.x + 2];
     const long V = (long)a.n_jc * a.n3;
-    const long v0 = V * x / a.gi, v1 = V * (x + 1) / a.gi;
+    const long v0 = V * x / gi, v1 = V * (x + 1) / gi;
     const long nq = (v1 - v0) * 4;
-    const int iw = it * 128 + warp * 16;
-    const bool active = iw < a.n1;
-    double* wring = ring + (size_t)warp * S * NB * 128;
-    uint64_t* wfull = full + warp * S;
+    const int nact = min(8, (a.n1 - it * 128 + 15) >> 4);            // consumer warps with rows inside the tensor
+    const int jc0 = (int)(v0 / a.n3), t0 = (int)(v0 - (long)jc0 * a.n3);
 
-    if (threadIdx.x == 0) prm_s = *a.st;
-    if (lane == 0) {
-        for (int s = 0; s < S; ++s) mbar_init(&wfull[s], 1);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], nact); }
         mbar_fence_init();
     }
     __syncthreads();
 
-    auto issue_loads = [&](long q) {          // lane 0 of an active warp
-        const long v = v0 + (q >> 2);
-        const int jc = (int)(v / a.n3), t = (int)(v - (long)jc * a.n3), j0 = jc * 32 + (int)(q & 3) * 8;
-        const int s = (int)(q % S);
-        double* st = wring + s * NB * 128;
-        mbar_expect_tx(&wfull[s], 4 * 1024);
-        tma_load_3d(st, &maps.D, &wfull[s], iw, j0, t);
-        tma_load_3d(st + 128, &maps.YL, &wfull[s], iw, j0, t);
-        tma_load_3d(st + 256, &maps.E, &wfull[s], iw, j0, t);
-        tma_load_3d(st + 384, &maps.YO, &wfull[s], iw, j0, t);
-    };
-    if (active && lane == 0) {
-        tma_prefetch_desc(&maps.D); tma_prefetch_desc(&maps.YL); tma_prefetch_desc(&maps.E);
-        tma_prefetch_desc(&maps.YO); tma_prefetch_desc(&maps.T);
-        if (WRITE_O) tma_prefetch_desc(&maps.O);
-        for (long q = 0; q < PD && q < nq; ++q) issue_loads(q);
-    }
-
-    const int i0 = iw + 2 * g;
-    const double* a1r0 = a.A1 + (size_t)min(i0, a.n1 - 1) * a.RS + tig;
-    const double* a1r1 = a.A1 + (size_t)min(i0 + 1, a.n1 - 1) * a.RS + tig;
-    const double z0 = (i0 < a.n1) ? 1.0 : 0.0, z1 = (i0 + 1 < a.n1) ? 1.0 : 0.0;
-
-    double acc[2][NT][2];
+    if (warp >= 8) {
+        // ---------------- TMA warpgroup: loads, stores, slot recycling ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 8 && lane == 0 && nq > 0) {
+            tma_prefetch_desc(&maps.D); tma_prefetch_desc(&maps.YL); tma_prefetch_desc(&maps.E);
+            tma_prefetch_desc(&maps.YO); tma_prefetch_desc(&maps.T);
+            if (WRITE_O) tma_prefetch_desc(&maps.O);
+            int ljc = jc0, lt = t0, ljg = 0, ls = 0;                 // load cursor
+            auto issue_load = [&]() {
+                double* st = ring + (size_t)ls * kStageD;
+                const int j0 = ljc * 32 + ljg * 8;
+                mbar_expect_tx(&full[ls], 4 * kBoxD * 8 + NT * 8 * 8);
+                tma_load_4d(st, &maps.D, &full[ls], 0, j0, it * 8, lt);
+                tma_load_4d(st + kBoxD, &maps.YL, &full[ls], 0, j0, it * 8, lt);
+                tma_load_4d(st + 2 * kBoxD, &maps.E, &full[ls], 0, j0, it * 8, lt);
+                tma_load_4d(st + 3 * kBoxD, &maps.YO, &full[ls], 0, j0, it * 8, lt);
+                bulk_load_1d(st + NB * kBoxD, a.C3 + (size_t)lt * a.RS, NT * 8 * 8, &full[ls]);   // C3 row of slice t
+                if (++ljg == 4) { ljg = 0; if (++lt == a.n3) { lt = 0; ++ljc; } }
+                if (++ls == S) ls = 0;
+            };
+            long loaded = 0;
+            for (; loaded < S && loaded < nq; ++loaded) issue_load();
+            int sjc = jc0, stt = t0, sjg = 0, ss = 0; uint32_t sph = 0;   // store cursor
+            for (long q = 0; q < nq; ++q) {
+                mbar_wait(&done[ss], sph);
+                double* st = ring + (size_t)ss * kStageD;
+                const int j0 = sjc * 32 + sjg * 8;
+                tma_store_4d(&maps.T, st, 0, j0, it * 8, stt);
+                tma_store_4d(&maps.YL, st + kBoxD, 0, j0, it * 8, stt);
+                tma_store_4d(&maps.E, st + 2 * kBoxD, 0, j0, it * 8, stt);
+                tma_store_4d(&maps.YO, st + 3 * kBoxD, 0, j0, it * 8, stt);
+                if (WRITE_O) tma_store_4d(&maps.O, st + 4 * kBoxD, 0, j0, it * 8, stt);
+                tma_store_commit();
+                if (++sjg == 4) { sjg = 0; if (++stt == a.n3) { stt = 0; ++sjc; } }
+                if (++ss == S) { ss = 0; sph ^= 1; }
+                if (q >= 1 && loaded < nq) {          // stage q-1 has left shared memory: refill its slot
+                    tma_store_wait_read<1>();
+                    issue_load();
+                    ++loaded;
+                }
+            }
+            tma_store_wait_all<0>();
+        }
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+      if (warp < nact) {
+        // ---------------- consumers ----------------
+        const int g = lane >> 2, tig = lane & 3;
+        const int i0 = it * 128 + warp * 16 + 2 * g;
+        AdmmPrm prm;
+        {
+            const IterState& S0 = *a.st;
+            prm.muL = S0.muL; prm.muO = S0.muO; prm.rmuL = S0.rmuL; prm.rmuO = S0.rmuO; prm.thr = S0.thr;
+            prm.musum = S0.musum; prm.rmusum = 1.0 / S0.musum; prm.rmuL_next = S0.rmuL_next;
+        }
+        double aF[2][KS];
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+        for (int s = 0; s < KS; ++s) {
+            aF[0][s] = (i0 < a.n1) ? __ldg(a.A1 + (size_t)i0 * a.RS + 4 * s + tig) : 0.0;
+            aF[1][s] = (i0 + 1 < a.n1) ? __ldg(a.A1 + (size_t)(i0 + 1) * a.RS + 4 * s + tig) : 0.0;
+        }
+        double acc[2][NT][2];
 #pragma unroll
-        for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
-    double aS[2][KS];
-    double c3s[NT];
-    double sL = 0.0, sO = 0.0;
-    int cur_jc = -1;
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+        double aS[2][kFoldA ? KS : 1];
+        double sL = 0.0, sO = 0.0;
+        // swizzled offsets (in double2 units) of this lane's two columns c = 0, 1 inside its warp's [8 j][16 i] block
+        const int off0 = warp * 64 + (2 * tig) * 8 + (g ^ (2 * tig));
+        const int off1 = warp * 64 + (2 * tig + 1) * 8 + (g ^ (2 * tig + 1));
+        int slot = 0; uint32_t ph = 0;
+        int jc = jc0, t = t0, cur_jc = -1;
+        const int nthr = nact * 32;
 
-    for (long q = 0; q < nq; ++q) {
-        const long v = v0 + (q >> 2);
-        const int jc = (int)(v / a.n3), t = (int)(v - (long)jc * a.n3);
-        const int jg = (int)(q & 3), j0 = jc * 32 + jg * 8;
-        if (jg == 0) {
-            if (jc != cur_jc) {               // uniform over the CTA: all warps walk the same q sequence
-                __syncthreads();
-                for (int e = threadIdx.x; e < 32 * 4 * KS; e += 256) {
+        for (long u = v0; u < v1; ++u) {
+            if (jc != cur_jc) {                    // uniform over the consumers: all walk the same sequence
+                asm volatile("bar.sync 1, %0;" ::"r"(nthr));
+                for (int e = threadIdx.x; e < 32 * 4 * KS; e += nthr) {
                     const int j = e / (4 * KS), k = e - j * (4 * KS);
                     const int jj = jc * 32 + j;
                     B2s[j * PL + k] = (jj < a.n2) ? a.B2[(size_t)jj * a.RS + k] : 0.0;
                 }
-                for (int e = threadIdx.x; e < NT * 8 * 32; e += 256) {
+                for (int e = threadIdx.x; e < NT * 8 * 32; e += nthr) {
                     const int j = e / (NT * 8), k = e - j * (NT * 8);
                     const int jj = jc * 32 + j;
                     B2T[k * kPJ + j] = (jj < a.n2) ? a.B2[(size_t)jj * a.RS + k] : 0.0;
                 }
-                __syncthreads();
+                asm volatile("bar.sync 1, %0;" ::"r"(nthr));
                 cur_jc = jc;
             }
-            // A fragments of L with C3[t,:] folded in; column scales of the MTTKRP B fragments
 #pragma unroll
-            for (int s = 0; s < KS; ++s) {
-                const double c3 = __ldg(a.C3 + (size_t)t * a.RS + 4 * s + tig);
-                aS[0][s] = __ldg(a1r0 + 4 * s) * c3 * z0;
-                aS[1][s] = __ldg(a1r1 + 4 * s) * c3 * z1;
+            for (int jg = 0; jg < 4; ++jg) {
+                double* st = ring + (size_t)slot * kStageD;
+                mbar_wait(&full[slot], ph);
+                const double* c3row = st + NB * kBoxD;       // C3(t, :), landed with this stage
+                if (kFoldA && jg == 0) {
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) {
+                        const double c3 = c3row[4 * s + tig];
+                        aS[0][s] = aF[0][s] * c3;
+                        aS[1][s] = aF[1][s] * c3;
+                    }
+                }
+                // L patch: l[m][c] = L(i0 + m, j0 + 2*tig + c, t)
+                double l[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    double b = B2s[(jg * 8 + g) * PL + 4 * ks + tig];
+                    if (kFoldA) {
+                        dmma884(l[0][0], l[0][1], aS[0][ks], b);
+                        dmma884(l[1][0], l[1][1], aS[1][ks], b);
+                    } else {
+                        b *= c3row[4 * ks + tig];
+                        dmma884(l[0][0], l[0][1], aF[0][ks], b);
+                        dmma884(l[1][0], l[1][1], aF[1][ks], b);
+                    }
+                }
+                double c3s[NT];                              // column scales of the MTTKRP B fragments
+#pragma unroll
+                for (int n = 0; n < NT; ++n) c3s[n] = c3row[8 * n + g];
+                double2* s2 = reinterpret_cast<double2*>(st);
+                double2 tn[2];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int off = c ? off1 : off0;
+                    const double2 d = s2[off];
+                    double2 yl = s2[kBoxD / 2 + off];
+                    double2 e = s2[2 * (kBoxD / 2) + off];
+                    double2 yo = s2[3 * (kBoxD / 2) + off];
+                    double2 o;
+                    admm_point2(prm, d.x, l[0][c], yl.x, e.x, yo.x, o.x, tn[c].x, sL, sO);
+                    admm_point2(prm, d.y, l[1][c], yl.y, e.y, yo.y, o.y, tn[c].y, sL, sO);
+                    s2[off] = tn[c];
+                    s2[kBoxD / 2 + off] = yl;
+                    s2[2 * (kBoxD / 2) + off] = e;
+                    s2[3 * (kBoxD / 2) + off] = yo;
+                    if (WRITE_O) s2[4 * (kBoxD / 2) + off] = o;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&done[slot]);
+                if (++slot == S) { slot = 0; ph ^= 1; }
+                // next iteration's X1*F': acc[m][n] += T'(i,j) B2(j,k) C3(t,k); k-step c covers j = j0 + 2*tig + c
+#pragma unroll
+                for (int n = 0; n < NT; ++n) {
+                    const double2 b = *reinterpret_cast<const double2*>(B2T + (8 * n + g) * kPJ + jg * 8 + 2 * tig);
+                    const double b0 = b.x * c3s[n], b1 = b.y * c3s[n];
+                    dmma884(acc[0][n][0], acc[0][n][1], tn[0].x, b0);
+                    dmma884(acc[1][n][0], acc[1][n][1], tn[0].y, b0);
+                    dmma884(acc[0][n][0], acc[0][n][1], tn[1].x, b1);
+                    dmma884(acc[1][n][0], acc[1][n][1], tn[1].y, b1);
+                }
             }
+            if (++t == a.n3) { t = 0; ++jc; }
+        }
+        double* p = a.partM + (size_t)blockIdx.x * 128 * a.RS;
 #pragma unroll
-            for (int n = 0; n < NT; ++n) c3s[n] = __ldg(a.C3 + (size_t)t * a.RS + 8 * n + g);
-        }
-        if (!active) continue;
-
-        if (lane == 0 && q + PD < nq) {
-            tma_store_wait_read<1>();         // the slot's previous stores (group q-2) have left shared memory
-            issue_loads(q + PD);
-        }
-        const int s = (int)(q % S);
-        double* st = wring + s * NB * 128;
-        mbar_wait(&wfull[s], (uint32_t)((q / S) & 1));
-
-        // L patch: l[m][c] = L(i0 + m, j0 + 2*tig + c, t)
-        double l[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const double b = B2s[(jg * 8 + g) * PL + 4 * ks + tig];
-            dmma884(l[0][0], l[0][1], aS[0][ks], b);
-            dmma884(l[1][0], l[1][1], aS[1][ks], b);
-        }
-        double2 tn[2];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int row = 2 * tig + c;
-            const double2 d = lds_swz128(st, row, g);
-            double2 yl = lds_swz128(st + 128, row, g);
-            double2 e = lds_swz128(st + 256, row, g);
-            double2 yo = lds_swz128(st + 384, row, g);
-            double2 o;
-            admm_point(prm_s, d.x, l[0][c], yl.x, e.x, yo.x, o.x, tn[c].x, sL, sO);
-            admm_point(prm_s, d.y, l[1][c], yl.y, e.y, yo.y, o.y, tn[c].y, sL, sO);
-            sts_swz128(st, row, g, tn[c]);
-            sts_swz128(st + 128, row, g, yl);
-            sts_swz128(st + 256, row, g, e);
-            sts_swz128(st + 384, row, g, yo);
-            if (WRITE_O) sts_swz128(st + 512, row, g, o);
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            tma_store_3d(&maps.T, st, iw, j0, t);
-            tma_store_3d(&maps.YL, st + 128, iw, j0, t);
-            tma_store_3d(&maps.E, st + 256, iw, j0, t);
-            tma_store_3d(&maps.YO, st + 384, iw, j0, t);
-            if (WRITE_O) tma_store_3d(&maps.O, st + 512, iw, j0, t);
-            tma_store_commit();
-        }
-        // next iteration's X1*F' : acc[m][n] += T'(i, j) * B2(j, k) * C3(t, k); k-step c covers j = j0 + 2*tig + c
-#pragma unroll
-        for (int n = 0; n < NT; ++n) {
-            const double2 b = *reinterpret_cast<const double2*>(B2T + (8 * n + g) * kPJ + jg * 8 + 2 * tig);
-            const double b0 = b.x * c3s[n], b1 = b.y * c3s[n];
-            dmma884(acc[0][n][0], acc[0][n][1], tn[0].x, b0);
-            dmma884(acc[1][n][0], acc[1][n][1], tn[0].y, b0);
-            dmma884(acc[0][n][0], acc[0][n][1], tn[1].x, b1);
-            dmma884(acc[1][n][0], acc[1][n][1], tn[1].y, b1);
-        }
+            for (int n = 0; n < NT; ++n)
+                *reinterpret_cast<double2*>(p + (size_t)(warp * 16 + 2 * g + m) * a.RS + 8 * n + 2 * tig) =
+                    make_double2(acc[m][n][0], acc[m][n][1]);
+        sL = warp_sum(sL);
+        sO = warp_sum(sO);
+        if (lane == 0) { red[warp] = sL; red[8 + warp] = sO; }
+      } else {
+        // consumer warp whose 16 rows lie entirely outside the tensor: contributes zeros
+        double* p = a.partM + (size_t)blockIdx.x * 128 * a.RS;
+        for (int e = lane; e < 16 * a.RS; e += 32) p[(size_t)warp * 16 * a.RS + e] = 0.0;
+        if (lane == 0) { red[warp] = 0.0; red[8 + warp] = 0.0; }
+      }
     }
-    if (active && lane == 0) tma_store_wait_all<0>();
-
-    double* p = a.partM + (size_t)blockIdx.x * 128 * a.RS;
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-        for (int n = 0; n < NT; ++n)
-            *reinterpret_cast<double2*>(p + (size_t)(warp * 16 + 2 * g + m) * a.RS + 8 * n + 2 * tig) =
-                make_double2(acc[m][n][0], acc[m][n][1]);
-
-    block_sum2(sL, sO, red);
-    if (threadIdx.x == 0) { a.norm_part[2 * blockIdx.x] = sL; a.norm_part[2 * blockIdx.x + 1] = sO; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sl = 0.0, so = 0.0;
+        for (int w = 0; w < 8; ++w) { sl += red[w]; so += red[8 + w]; }
+        a.norm_part[2 * blockIdx.x] = sl; a.norm_part[2 * blockIdx.x + 1] = so;
+    }
 }
 
 }  // namespace tritd

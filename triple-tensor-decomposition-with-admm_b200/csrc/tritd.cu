@@ -241,8 +241,8 @@ struct tritd_problem {
     CUtensorMap mapT, mapA1T;
     alignas(64) AdmmMaps maps;           // [8 j][16 i] boxes of D, Y_L, E, Y_O, T, O for k_admm
     double* partF = nullptr;             // [gridA][128][RS] fused mode-1 partials (next iteration's X1*F')
-    int *tileF = nullptr;                // i-tile of each k_admm CTA
-    int gridA = 0, giA = 0;
+    int *tileF = nullptr, *ctaTab = nullptr;   // i-tile of each k_admm CTA; (tile, index in tile, CTAs of tile)
+    int gridA = 0;
     bool rhsA_ready = false;             // partF holds X1*F' of the current T
     int n_it = 0, n_jc = 0, gridM = 0, gridP = 0, gridF = 0, gi = 0;
     long unitsM = 0, unitsP = 0;
@@ -268,7 +268,7 @@ static int dalloc(tritd_problem* p, Tp** ptr, size_t count) {
 
 static int make_map(tritd_ctx* c, CUtensorMap* map, void* base, int rank, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
-    cuuint32_t estr[3] = {1, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -348,9 +348,10 @@ static int launch_admm(tritd_problem* p) {
     tritd_ctx* c = p->ctx;
     AdmmArgs a;
     a.A1 = p->A1; a.B2 = p->B2; a.C3 = p->C3; a.st = p->st; a.norm_part = p->norm_part; a.partM = p->partF;
-    a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_it = p->n_it; a.n_jc = p->n_jc; a.gi = p->giA;
+    a.cta_tab = p->ctaTab;
+    a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc;
 #define CALL(NT_, KS_) \
-    k_admm<KS_, NT_, true><<<p->gridA, 256, AdmmCfg<KS_, NT_, true>::kSmem, c->stream>>>(p->maps, a);
+    k_admm<KS_, NT_, true><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, true>::kSmem, c->stream>>>(p->maps, a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
     CU_TRY(cudaGetLastError());
@@ -419,7 +420,7 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     p->RS = (p->R + 7) / 8 * 8;
     const RankCfg rc = rank_cfg(r);
     p->NT = rc.NT; p->KS = rc.KS;
-    p->ld1 = (p->n1 + 1) & ~1;
+    p->ld1 = (p->n1 + 15) & ~15;      // padded rows exist (and stay zero): TMA views the rows as (16, n1p/16)
     p->ldt = p->ld1;
     p->Np = (size_t)p->ld1 * p->n2 * p->n3;
     p->n_it = (p->n1 + 127) / 128;
@@ -470,13 +471,31 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         cudaMemcpy(p->tile0, t0.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
         cudaMemcpy(p->tile1, t1.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
         cudaMemset(p->ticket, 0, 16);
-        p->giA = std::max(1, c->num_sms / p->n_it);
-        p->gridA = p->giA * p->n_it;
+        // k_admm: one CTA per SM; CTAs are dealt to the i-tiles in proportion to the rows each tile holds
+        p->gridA = std::max(c->num_sms, p->n_it);
+        std::vector<int> per(p->n_it, 1);
+        {
+            int left = p->gridA - p->n_it;
+            std::vector<double> want(p->n_it);
+            for (int q = 0; q < p->n_it; ++q) want[q] = (double)std::min(128, p->n1 - q * 128) / p->n1 * p->gridA;
+            for (int q = 0; q < p->n_it && left > 0; ++q) { int add = std::min(left, std::max(0, (int)want[q] - 1)); per[q] += add; left -= add; }
+            for (int q = 0; left > 0; q = (q + 1) % p->n_it) { ++per[q]; --left; }
+        }
         PALLOC(partF, (size_t)p->gridA * 128 * p->RS);
         PALLOC(tileF, p->gridA);
-        std::vector<int> tf(p->gridA);
-        for (int q = 0; q < p->gridA; ++q) tf[q] = q % p->n_it;
+        PALLOC(ctaTab, 3 * p->gridA);
+        std::vector<int> tf(p->gridA), tab(3 * p->gridA);
+        {
+            // interleave the tiles so neighbouring CTAs (launched together) work on the same columns
+            std::vector<int> used(p->n_it, 0);
+            int q = 0;
+            for (int cta = 0; cta < p->gridA;) {
+                if (used[q] < per[q]) { tf[cta] = q; tab[3 * cta] = q; tab[3 * cta + 1] = used[q]++; tab[3 * cta + 2] = per[q]; ++cta; }
+                q = (q + 1) % p->n_it;
+            }
+        }
         cudaMemcpy(p->tileF, tf.data(), sizeof(int) * p->gridA, cudaMemcpyHostToDevice);
+        cudaMemcpy(p->ctaTab, tab.data(), sizeof(int) * 3 * p->gridA, cudaMemcpyHostToDevice);
     }
     PALLOC(norm_part, (size_t)2 * std::max(std::max(p->gridF, c->num_sms), 1024));
     PALLOC(norms, 8);
@@ -513,11 +532,14 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         cuuint64_t str[2] = {(cuuint64_t)p->ld1 * 8, (cuuint64_t)p->ld1 * p->n2 * 8};
         cuuint32_t box[3] = {16, (cuuint32_t)kBoxRows, 1};
         if ((s = make_map(c, &p->mapT, p->T, 3, dims, str, box)) != TRITD_OK) return bail(s);
-        cuuint32_t box8[3] = {16, 8, 1};
+        // k_admm views each N-array as (i_lo = 16, j, i_hi = ld1/16, t): one box = [8 i_hi][8 j][16 i_lo]
+        cuuint64_t dims4[4] = {16, (cuuint64_t)p->n2, (cuuint64_t)(p->ld1 / 16), (cuuint64_t)p->n3};
+        cuuint64_t str4[3] = {(cuuint64_t)p->ld1 * 8, 128, (cuuint64_t)p->ld1 * p->n2 * 8};
+        cuuint32_t box4[4] = {16, 8, 8, 1};
         struct { CUtensorMap* m; double* base; } mm[6] = {{&p->maps.D, p->D}, {&p->maps.YL, p->YL}, {&p->maps.E, p->E},
                                                          {&p->maps.YO, p->YO}, {&p->maps.T, p->T}, {&p->maps.O, p->O}};
         for (auto& q : mm)
-            if ((s = make_map(c, q.m, q.base, 3, dims, str, box8)) != TRITD_OK) return bail(s);
+            if ((s = make_map(c, q.m, q.base, 4, dims4, str4, box4)) != TRITD_OK) return bail(s);
         cuuint64_t dims2[2] = {(cuuint64_t)p->n1, (cuuint64_t)p->RS};
         cuuint64_t str2[1] = {(cuuint64_t)p->ldt * 8};
         cuuint32_t box2[2] = {16, (cuuint32_t)p->RS};
