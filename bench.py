@@ -13,7 +13,7 @@ Prints ONE JSON line (rank 0):
             stream over exactly K iterations after W warm-up iterations, max over ranks;
   e2e       iterations/s of one reference-facing call (tritd_admm_f64 through ctypes) with HOST
             buffers: pinned D in, A/B/C/O/errHist out, H2D and D2H inside the timed region;
-  roofline  the fused element-wise kernel: 72*N algorithmic bytes per launch / its CUDA-event time;
+  roofline  the fused element-wise kernel: 64*N algorithmic bytes per launch / its CUDA-event time;
   cpu_baseline  the numpy/OpenBLAS oracle port timed on this box's host cores (rank 0, N=1).
 --impl reference times the oracle port alone (the MATLAB reference cannot run here).
 """
@@ -31,6 +31,9 @@ for _p in (os.path.join(ROOT, "triple-tensor-decomposition-with-admm_b200"),):
 
 import numpy as np  # noqa: E402
 
+# k_admm moves 4 reads (D, Y_L, E, Y_O) + 4 writes (T', Y_L, E, Y_O) = 64 bytes per element; O is not
+# stored inside the loop ("64*N if ..."; here it is O, not T, that is not emitted).
+FUSED_BYTES = 64.0
 METRIC = "admm_iterations_per_second"
 UNIT = "iter/s"
 
@@ -245,7 +248,7 @@ def main():
     peak, peak_src = load_peaks()
     N_local = n1 * n2 * n3l
     fused_ms = phase_ms[4] / max(1, nprof)
-    achieved = 72.0 * N_local / (fused_ms * 1e-3) * 1e-9
+    achieved = FUSED_BYTES * N_local / (fused_ms * 1e-3) * 1e-9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
@@ -258,7 +261,7 @@ def main():
     flops_iter = 8.0 * N_global * R + 2.0 * R * R * (n2 * n3 + n1 * n3 + n1 * n2)
     roofline = {"bound": "hbm", "kernel": "k_fused (L reconstruction + O/E/dual/T update + residual norms)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": 72.0 * N_local, "kernel_ms": fused_ms,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": FUSED_BYTES * N_local, "kernel_ms": fused_ms,
                 "iteration_GBps_vs_96N": 96.0 * N_global / world / (ms_total / K * 1e-3) * 1e-9,
                 "iteration_fp64_TFLOPs": flops_iter / world / (ms_total / K * 1e-3) * 1e-12,
                 "dmma_peak_TFLOPs_measured": 37.2,

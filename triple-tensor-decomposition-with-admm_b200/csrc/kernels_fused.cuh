@@ -213,6 +213,18 @@ __global__ void k_finalize(IterState* st, const double* norms, double* errHist, 
     if (k + 1 >= st->maxIter) st->stop = 1;
 }
 
+// O of the last finished iteration, recovered from the state the iteration keeps:
+// k_admm forms T' = (D - O) + (1/muL')*Y_L' and never stores O (nothing inside the loop reads it,
+// triple_decomp_ADMM.m:41-43), so O = D - (T' - (1/muL')*Y_L') with the same product as the forward pass;
+// exact up to one rounding of the sum, i.e. ~1 ulp of max(|D|,|Y_L/muL|) per entry.
+__global__ void __launch_bounds__(256) k_recover_O(const double* __restrict__ D, const double* __restrict__ T,
+                                                   const double* __restrict__ YL, const IterState* st,
+                                                   double* __restrict__ O, size_t n) {
+    const double rmu = st->rmuL;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        O[i] = __dsub_rn(D[i], __dsub_rn(T[i], __dmul_rn(rmu, YL[i])));
+}
+
 __global__ void k_set_normD(IterState* st, const double* sumsq) {
     if (threadIdx.x == 0 && blockIdx.x == 0) st->normD = sqrt(sumsq[0]);
 }

@@ -351,7 +351,7 @@ static int launch_admm(tritd_problem* p) {
     a.cta_tab = p->ctaTab;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc;
 #define CALL(NT_, KS_) \
-    k_admm<KS_, NT_, true><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, true>::kSmem, c->stream>>>(p->maps, a);
+    k_admm<KS_, NT_, false><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, false>::kSmem, c->stream>>>(p->maps, a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
     CU_TRY(cudaGetLastError());
@@ -509,8 +509,8 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
 #define CALL(NT_, KS_)                                                                                            \
     CU_TRY(cudaFuncSetAttribute(k_mttkrp1<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemM));    \
     CU_TRY(cudaFuncSetAttribute(k_ppass<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemP));      \
-    CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,             \
-                                (int)AdmmCfg<KS_, NT_, true>::kSmem));
+    CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                (int)AdmmCfg<KS_, NT_, false>::kSmem));
             TRITD_DISPATCH_R(r, CALL)
 #undef CALL
             CU_TRY(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(TRITD_MAX_R * TRITD_MAX_R)));
@@ -809,6 +809,16 @@ extern "C" int tritd_problem_iterate(tritd_problem* p, int32_t max_more, int32_t
     return TRITD_OK;
 }
 
+// O is not written inside the loop (see k_recover_O): materialise it into p->O on demand.
+static int recover_O(tritd_problem* p) {
+    tritd_ctx* c = p->ctx;
+    const unsigned grid = (unsigned)std::min<size_t>((p->Np + 255) / 256, (size_t)c->num_sms * 16);
+    k_recover_O<<<grid, 256, 0, c->stream>>>(p->D, p->T, p->YL, p->st, p->O, p->Np);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
 static int reconstruct_L(tritd_problem* p, double** Lbuf) {
     double* q = nullptr;
     cudaError_t e = cudaMalloc((void**)&q, p->Np * sizeof(double));
@@ -831,7 +841,7 @@ extern "C" int tritd_problem_get(tritd_problem* p, double* A, double* B, double*
     if (A) { h.resize((size_t)p->n1 * p->RS); CU_TRY(cudaMemcpy(h.data(), p->A1, h.size() * 8, cudaMemcpyDeviceToHost)); unpack_A(h, p->n1, p->R, p->RS, A); }
     if (B) { h.resize((size_t)p->n2 * p->RS); CU_TRY(cudaMemcpy(h.data(), p->B2, h.size() * 8, cudaMemcpyDeviceToHost)); unpack_B(h, p->n2, p->r, p->RS, B); }
     if (C) { h.resize((size_t)p->n3 * p->RS); CU_TRY(cudaMemcpy(h.data(), p->C3, h.size() * 8, cudaMemcpyDeviceToHost)); unpack_C(h, p->n3, p->R, p->RS, C); }
-    if (O) { ST_TRY(copy_out(p, O, p->O)); }
+    if (O) { ST_TRY(recover_O(p)); ST_TRY(copy_out(p, O, p->O)); }
     if (L) {
         double* Lbuf = nullptr;
         ST_TRY(reconstruct_L(p, &Lbuf));
@@ -851,6 +861,7 @@ extern "C" int tritd_problem_get(tritd_problem* p, double* A, double* B, double*
 extern "C" int tritd_problem_get_O_dev(tritd_problem* p, double* O_dev) {
     if (!p || !O_dev) return fail(TRITD_ERR_INVALID, "NULL argument");
     CU_TRY(cudaSetDevice(p->ctx->device));
+    ST_TRY(recover_O(p));
     return copy_out(p, O_dev, p->O);
 }
 extern "C" int tritd_problem_get_L_dev(tritd_problem* p, double* L_dev) {
