@@ -13,8 +13,9 @@ namespace tritd {
 //   C (8x8)       c0 = C[g][2*tig], c1 = C[g][2*tig+1]
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    // not volatile: a pure function of its operands, so the scheduler may interleave independent chains
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 // The permutation used wherever 8 MMA rows (or columns) are mapped onto 8 rows of a

@@ -34,6 +34,7 @@ struct AdmmArgs {
     const int* cta_tab;                // [grid][3]: i-tile, index within the tile's CTAs, CTAs of that tile
     int n1, n2, n3, RS;
     int n_jc;                          // j-chunks (32 columns)
+    int tile_h;                        // rows per i-tile: 16 * (consumer warps used), <= 128
 };
 
 constexpr int kBoxD = 8 * 128;         // doubles per array per stage: [8 warps][8 j][16 i]
@@ -127,7 +128,8 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
     const long V = (long)a.n_jc * a.n3;
     const long v0 = V * x / gi, v1 = V * (x + 1) / gi;
     const long nq = (v1 - v0) * 4;
-    const int nact = min(8, (a.n1 - it * 128 + 15) >> 4);            // consumer warps with rows inside the tensor
+    const int nw = a.tile_h >> 4;                                    // consumer warps per tile (= TMA box depth in i_hi)
+    const int nact = min(nw, (a.n1 - it * a.tile_h + 15) >> 4);      // ... of which have rows inside the tensor
     const int jc0 = (int)(v0 / a.n3), t0 = (int)(v0 - (long)jc0 * a.n3);
 
     if (threadIdx.x == 0) {
@@ -147,11 +149,11 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
             auto issue_load = [&]() {
                 double* st = ring + (size_t)ls * kStageD;
                 const int j0 = ljc * 32 + ljg * 8;
-                mbar_expect_tx(&full[ls], 4 * kBoxD * 8 + NT * 8 * 8);
-                tma_load_4d(st, &maps.D, &full[ls], 0, j0, it * 8, lt);
-                tma_load_4d(st + kBoxD, &maps.YL, &full[ls], 0, j0, it * 8, lt);
-                tma_load_4d(st + 2 * kBoxD, &maps.E, &full[ls], 0, j0, it * 8, lt);
-                tma_load_4d(st + 3 * kBoxD, &maps.YO, &full[ls], 0, j0, it * 8, lt);
+                mbar_expect_tx(&full[ls], 4 * nw * 1024 + NT * 8 * 8);
+                tma_load_4d(st, &maps.D, &full[ls], 0, j0, it * nw, lt);
+                tma_load_4d(st + kBoxD, &maps.YL, &full[ls], 0, j0, it * nw, lt);
+                tma_load_4d(st + 2 * kBoxD, &maps.E, &full[ls], 0, j0, it * nw, lt);
+                tma_load_4d(st + 3 * kBoxD, &maps.YO, &full[ls], 0, j0, it * nw, lt);
                 bulk_load_1d(st + NB * kBoxD, a.C3 + (size_t)lt * a.RS, NT * 8 * 8, &full[ls]);   // C3 row of slice t
                 if (++ljg == 4) { ljg = 0; if (++lt == a.n3) { lt = 0; ++ljc; } }
                 if (++ls == S) ls = 0;
@@ -163,11 +165,11 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
                 mbar_wait(&done[ss], sph);
                 double* st = ring + (size_t)ss * kStageD;
                 const int j0 = sjc * 32 + sjg * 8;
-                tma_store_4d(&maps.T, st, 0, j0, it * 8, stt);
-                tma_store_4d(&maps.YL, st + kBoxD, 0, j0, it * 8, stt);
-                tma_store_4d(&maps.E, st + 2 * kBoxD, 0, j0, it * 8, stt);
-                tma_store_4d(&maps.YO, st + 3 * kBoxD, 0, j0, it * 8, stt);
-                if (WRITE_O) tma_store_4d(&maps.O, st + 4 * kBoxD, 0, j0, it * 8, stt);
+                tma_store_4d(&maps.T, st, 0, j0, it * nw, stt);
+                tma_store_4d(&maps.YL, st + kBoxD, 0, j0, it * nw, stt);
+                tma_store_4d(&maps.E, st + 2 * kBoxD, 0, j0, it * nw, stt);
+                tma_store_4d(&maps.YO, st + 3 * kBoxD, 0, j0, it * nw, stt);
+                if (WRITE_O) tma_store_4d(&maps.O, st + 4 * kBoxD, 0, j0, it * nw, stt);
                 tma_store_commit();
                 if (++sjg == 4) { sjg = 0; if (++stt == a.n3) { stt = 0; ++sjc; } }
                 if (++ss == S) { ss = 0; sph ^= 1; }
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
       if (warp < nact) {
         // ---------------- consumers ----------------
         const int g = lane >> 2, tig = lane & 3;
-        const int i0 = it * 128 + warp * 16 + 2 * g;
+        const int i0 = it * a.tile_h + warp * 16 + 2 * g;
         AdmmPrm prm;
         {
             const IterState& S0 = *a.st;
@@ -227,33 +229,43 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
                 asm volatile("bar.sync 1, %0;" ::"r"(nthr));
                 cur_jc = jc;
             }
+            double l[2][2];
 #pragma unroll
             for (int jg = 0; jg < 4; ++jg) {
                 double* st = ring + (size_t)slot * kStageD;
                 mbar_wait(&full[slot], ph);
                 const double* c3row = st + NB * kBoxD;       // C3(t, :), landed with this stage
-                if (kFoldA && jg == 0) {
+                // L patch of column group jg_: l[m][c] = L(i0 + m, j0 + 2*tig + c, t)
+                auto l_patch = [&](int jg_, double (&l)[2][2]) {
+                    l[0][0] = l[0][1] = l[1][0] = l[1][1] = 0.0;
 #pragma unroll
-                    for (int s = 0; s < KS; ++s) {
-                        const double c3 = c3row[4 * s + tig];
-                        aS[0][s] = aF[0][s] * c3;
-                        aS[1][s] = aF[1][s] * c3;
+                    for (int ks = 0; ks < KS; ++ks) {
+                        double b = B2s[(jg_ * 8 + g) * PL + 4 * ks + tig];
+                        if (kFoldA) {
+                            dmma884(l[0][0], l[0][1], aS[0][ks], b);
+                            dmma884(l[1][0], l[1][1], aS[1][ks], b);
+                        } else {
+                            b *= c3row[4 * ks + tig];
+                            dmma884(l[0][0], l[0][1], aF[0][ks], b);
+                            dmma884(l[1][0], l[1][1], aF[1][ks], b);
+                        }
                     }
-                }
-                // L patch: l[m][c] = L(i0 + m, j0 + 2*tig + c, t)
-                double l[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
-                    double b = B2s[(jg * 8 + g) * PL + 4 * ks + tig];
+                };
+                if (jg == 0) {
                     if (kFoldA) {
-                        dmma884(l[0][0], l[0][1], aS[0][ks], b);
-                        dmma884(l[1][0], l[1][1], aS[1][ks], b);
-                    } else {
-                        b *= c3row[4 * ks + tig];
-                        dmma884(l[0][0], l[0][1], aF[0][ks], b);
-                        dmma884(l[1][0], l[1][1], aF[1][ks], b);
+#pragma unroll
+                        for (int s = 0; s < KS; ++s) {
+                            const double c3 = c3row[4 * s + tig];
+                            aS[0][s] = aF[0][s] * c3;
+                            aS[1][s] = aF[1][s] * c3;
+                        }
                     }
+                    l_patch(0, l);
                 }
+                // the DMMA chain of the NEXT column group does not depend on the data of this stage: issued
+                // here, in the same basic block as the element-wise pass, the scheduler overlaps the two chains
+                double ln[2][2];
+                if (jg < 3) l_patch(jg + 1, ln);
                 double c3s[NT];                              // column scales of the MTTKRP B fragments
 #pragma unroll
                 for (int n = 0; n < NT; ++n) c3s[n] = c3row[8 * n + g];
@@ -289,6 +301,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
                     dmma884(acc[0][n][0], acc[0][n][1], tn[1].x, b1);
                     dmma884(acc[1][n][0], acc[1][n][1], tn[1].y, b1);
                 }
+                if (jg < 3) { l[0][0] = ln[0][0]; l[0][1] = ln[0][1]; l[1][0] = ln[1][0]; l[1][1] = ln[1][1]; }
             }
             if (++t == a.n3) { t = 0; ++jc; }
         }

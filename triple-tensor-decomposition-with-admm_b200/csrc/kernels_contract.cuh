@@ -165,7 +165,7 @@ k_mttkrp1(const __grid_constant__ CUtensorMap mapT, const Mttkrp1Args a) {
 // 32 consecutive outputs (i,k); lane l adds the contributing CTAs c = l, l+8, ... and the 8 lanes are
 // combined by a fixed tree.  tile0[c]/tile1[c] (host-computed) are the first/last i-tile CTA c touched:
 // it contributes to tile `it` through slot it - tile0[c] of its `cta_stride`-sized partial block.
-__global__ void __launch_bounds__(256) k_mttkrp1_reduce(const double* part, size_t cta_stride, double* rhs, int n1, int RS,
+__global__ void __launch_bounds__(256) k_mttkrp1_reduce(const double* part, size_t cta_stride, int tile_h, double* rhs, int n1, int RS,
                                                        const int* tile0, const int* tile1, int grid_m,
                                                        const int* stop) {
     if (*stop) return;
@@ -176,11 +176,21 @@ __global__ void __launch_bounds__(256) k_mttkrp1_reduce(const double* part, size
     double sum = 0.0;
     if (ok) {
         const int i = (int)(idx / RS), k = (int)(idx - (long)i * RS);
-        const int it = i >> 7, il = i & 127;
-        for (int c = cl; c < grid_m; c += 8) {
+        const int it = i / tile_h, il = i - it * tile_h;
+        double s1 = 0.0;
+        int c = cl;
+        for (; c + 8 < grid_m; c += 16) {      // two independent chains: twice the loads in flight
+            const int t0 = tile0[c], u0 = tile0[c + 8];
+            const bool h0 = it >= t0 && it <= tile1[c], h1 = it >= u0 && it <= tile1[c + 8];
+            const double x0 = h0 ? part[(size_t)c * cta_stride + ((size_t)(it - t0) * 128 + il) * RS + k] : 0.0;
+            const double x1 = h1 ? part[(size_t)(c + 8) * cta_stride + ((size_t)(it - u0) * 128 + il) * RS + k] : 0.0;
+            sum += x0; s1 += x1;
+        }
+        for (; c < grid_m; c += 8) {
             const int t0 = tile0[c];
             if (it >= t0 && it <= tile1[c]) sum += part[(size_t)c * cta_stride + ((size_t)(it - t0) * 128 + il) * RS + k];
         }
+        sum += s1;
     }
     red[cl][ol] = sum;
     __syncthreads();
@@ -319,9 +329,18 @@ __global__ void __launch_bounds__(256) k_rhsB(const double* P, const double* C3,
     const size_t nrk = (size_t)n2 * RS;
     for (int k0 = 0; k0 < RS; k0 += 32) {
         const int k = k0 + kl;
-        double s = 0.0;
-        if (k < RS)
-            for (int t = tl; t < n3; t += 8) s = fma(C3[(size_t)t * RS + k], P[(size_t)t * nrk + (size_t)j * RS + k], s);
+        double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (k < RS) {
+            int t = tl;
+            for (; t + 24 < n3; t += 32) {     // four independent chains
+                s = fma(C3[(size_t)t * RS + k], P[(size_t)t * nrk + (size_t)j * RS + k], s);
+                s1 = fma(C3[(size_t)(t + 8) * RS + k], P[(size_t)(t + 8) * nrk + (size_t)j * RS + k], s1);
+                s2 = fma(C3[(size_t)(t + 16) * RS + k], P[(size_t)(t + 16) * nrk + (size_t)j * RS + k], s2);
+                s3 = fma(C3[(size_t)(t + 24) * RS + k], P[(size_t)(t + 24) * nrk + (size_t)j * RS + k], s3);
+            }
+            for (; t < n3; t += 8) s = fma(C3[(size_t)t * RS + k], P[(size_t)t * nrk + (size_t)j * RS + k], s);
+            s = (s + s1) + (s2 + s3);
+        }
         red[tl][kl] = s;
         __syncthreads();
         if (tl == 0 && k < RS)
@@ -341,9 +360,18 @@ __global__ void __launch_bounds__(256) k_rhsC(const double* P, const double* B2,
     const int kl = threadIdx.x & 31, jl = threadIdx.x >> 5;
     for (int k0 = 0; k0 < RS; k0 += 32) {
         const int k = k0 + kl;
-        double s = 0.0;
-        if (k < RS)
-            for (int j = jl; j < n2; j += 8) s += B2[(size_t)j * RS + k] * P[((size_t)t * n2 + j) * RS + k];
+        double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (k < RS) {
+            int j = jl;
+            for (; j + 24 < n2; j += 32) {     // four independent chains
+                s = fma(B2[(size_t)j * RS + k], P[((size_t)t * n2 + j) * RS + k], s);
+                s1 = fma(B2[(size_t)(j + 8) * RS + k], P[((size_t)t * n2 + j + 8) * RS + k], s1);
+                s2 = fma(B2[(size_t)(j + 16) * RS + k], P[((size_t)t * n2 + j + 16) * RS + k], s2);
+                s3 = fma(B2[(size_t)(j + 24) * RS + k], P[((size_t)t * n2 + j + 24) * RS + k], s3);
+            }
+            for (; j < n2; j += 8) s = fma(B2[(size_t)j * RS + k], P[((size_t)t * n2 + j) * RS + k], s);
+            s = (s + s1) + (s2 + s3);
+        }
         red[jl][kl] = s;
         __syncthreads();
         if (jl == 0 && k < RS) {

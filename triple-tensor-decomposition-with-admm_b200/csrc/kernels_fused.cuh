@@ -197,16 +197,25 @@ __global__ void __launch_bounds__(256) k_sumsq_part(const double* x, size_t n, d
     if (threadIdx.x == 0) { part[2 * blockIdx.x] = s; part[2 * blockIdx.x + 1] = 0.0; }
 }
 
-// errHist / mu schedule / stopping rule (triple_decomp_ADMM.m:56-65), one thread.
-// norms[0..1] = global sum(resL^2), sum(resO^2) of the iteration just finished.
-__global__ void k_finalize(IterState* st, const double* norms, double* errHist, double* errL, double* errO) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// errHist / mu schedule / stopping rule (triple_decomp_ADMM.m:56-65).  One CTA: first the fixed-order
+// sum of the per-CTA partials of sum(resL^2), sum(resO^2) (npart pairs; with `reduced` set the pair
+// in norms[] was already summed -- and all-reduced over the ranks), then one thread does the scalars.
+__global__ void __launch_bounds__(256) k_finalize(IterState* st, const double* part, int npart, double* norms, int reduced,
+                                                  double* errHist, double* errL, double* errO) {
     if (st->stop) return;
+    __shared__ double red[64];
+    double a = 0.0, b = 0.0;
+    if (!reduced) {
+        for (int i = threadIdx.x; i < npart; i += 256) { a += part[2 * i]; b += part[2 * i + 1]; }
+        block_sum2(a, b, red);
+    }
+    if (threadIdx.x != 0) return;
+    if (reduced) { a = norms[0]; b = norms[1]; }
     const int k = st->k;
     st->muL = fmin(st->muL * st->rhoL, st->muL_max);
     st->muO = fmin(st->muO * st->rhoO, st->muO_max);
     iter_state_derive(*st);
-    const double eL = sqrt(norms[0]) / st->normD, eO = sqrt(norms[1]) / st->normD;
+    const double eL = sqrt(a) / st->normD, eO = sqrt(b) / st->normD;
     errL[k] = eL; errO[k] = eO; errHist[k] = eL + eO;
     st->k = k + 1;
     if (k >= 1 && fabs(errHist[k] - errHist[k - 1]) < st->tol * errHist[k - 1]) st->stop = 1;

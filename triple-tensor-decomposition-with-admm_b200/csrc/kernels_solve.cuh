@@ -33,14 +33,16 @@ __global__ void __launch_bounds__(256) k_small_gram(const double* X, int n, int 
     S[idx] = (s0 + s1) + (s2 + s3);
 }
 
-// X[row][:] = RHS[row][:] * inv(S1 o S2 + alpha*I), 32 rows per CTA, 256 threads.
-// Every CTA inverts the R x R ridge system itself by Gauss-Jordan elimination on [G | I] in shared
-// memory (SPD, so no pivoting; pivots are the Cholesky pivots d_k = L_kk^2 and a non-positive or
-// non-finite one is reported through IterState::status) -- R <= 64, a few microseconds, and no
-// extra launch on the critical path -- and then applies it to its rows like the reference applies
-// pinv(G) (:78).  The CTA also forms the partial small Gram X'X of its rows; the last CTA to finish
-// (ticket counter) sums the partials in CTA order, so S_out = X'X is deterministic and needs no
-// separate kernel.  Optionally writes the transposed factor XT[k][row] that k_ppass streams with TMA.
+// X[row][:] = RHS[row][:] * inv(S1 o S2 + alpha*I), 32 rows per CTA of 1024 threads.
+// Every CTA inverts the R x R ridge system itself by Gauss-Jordan elimination (SPD, so no pivoting;
+// the pivots are the Cholesky pivots d_k = L_kk^2, and a non-positive or non-finite one is reported
+// through IterState::status).  The matrix lives in registers, a 2 x 2 patch per thread; only the
+// pivot row and column pass through shared memory, one barrier per step -- R <= 64 steps of a few
+// hundred cycles, a few microseconds, no extra launch on the critical path.  The
+// inverse is then applied to the CTA's rows like the reference applies pinv(G) (:78).  The CTA also
+// forms the partial small Gram X'X of its rows; the last CTA to finish (ticket counter) sums the
+// partials in CTA order, so S_out = X'X is deterministic and needs no separate kernel.  Optionally
+// writes the transposed factor XT[k][row] that k_ppass streams with TMA.
 struct SolveArgs {
     const double* rhs;     // [n][RS]
     const double *S1, *S2; // [RS][RS]
@@ -51,105 +53,182 @@ struct SolveArgs {
     double* gram_out;      // [RS][RS]  (= X'X over the rows of this rank)
     unsigned* ticket;
     IterState* st;
+    long long* dbg;        // optional: clock64 stamps of CTA 0 (diagnostics)
     int n, R, RS, ldt;
 };
 
 constexpr int kSolveRows = 32;
+constexpr int kSolveThreads = 1024;
 
-__global__ void __launch_bounds__(256) k_solve(const SolveArgs a) {
+__global__ void __launch_bounds__(kSolveThreads) k_solve(const SolveArgs a) {
     if (a.st->stop) return;
     extern __shared__ double sm[];
-    const int R = a.R, W2 = 2 * R, PW = W2 | 1, P = R | 1;
-    double* Wm = sm;                       // [R][PW]   [G | I] -> [I | inv(G)]
-    double* rowk = Wm + R * PW;            // [2R]
-    double* colk = rowk + W2;              // [R]
-    double* rows = colk + R;               // [32][P]   RHS rows
-    double* xr = rows + kSolveRows * P;    // [32][P]   solved rows
+    const int R = a.R, P = R | 1, RR = R * R;   // odd pitch
+    double* Gb = sm;                       // [R][P]     inv(G) (written once, after the elimination)
+    double* prow = Gb + R * P;             // [2][64]    published pivot row    (double-buffered)
+    double* pcol = prow + 128;             // [2][64]    published pivot column (double-buffered)
+    double* rows = pcol + 128;             // [32][P]    RHS rows
+    double* xr = rows + kSolveRows * P;    // [32][P]    solved rows
     __shared__ int s_last;
     const int tid = threadIdx.x;
     const int row0 = blockIdx.x * kSolveRows;
+#define TRITD_STAMP(q) if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[q] = clock64();
+    TRITD_STAMP(0)
 
-    for (int e = tid; e < R * W2; e += 256) {
-        const int i = e / W2, j = e - i * W2;
-        double v;
-        if (j < R) {
-            v = a.S1[i * a.RS + j] * a.S2[i * a.RS + j];
-            if (i == j) v += a.alpha;
-        } else {
-            v = (j - R == i) ? 1.0 : 0.0;
+    // this thread's entries e = tid + m*1024 of an R x R (or 32 x R) index space
+    int ei[4], ej[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int e = tid + m * kSolveThreads;
+        ei[m] = e / R; ej[m] = e - ei[m] * R;
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+        if (tid + m * kSolveThreads < kSolveRows * R)
+            rows[ei[m] * P + ej[m]] = (row0 + ei[m] < a.n) ? a.rhs[(size_t)(row0 + ei[m]) * a.RS + ej[m]] : 0.0;
+
+    // In-place Gauss-Jordan with the matrix in REGISTERS: thread (ty,tx) of a 32 x 32 grid owns entries
+    // (ty + 32p, tx + 32q), p,q in {0,1}.  Per step only the pivot row and pivot column go through shared
+    // memory (double-buffered, published by their owners as they are produced), so a step is: one barrier,
+    // five shared loads, one reciprocal, four FMAs.  A bad pivot only raises a flag (checked once).
+    auto fast_rcp = [](double x) {
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+        double e = fma(-x, y, 1.0);
+        y = fma(y, e, y);
+        e = fma(-x, y, 1.0);
+        return fma(y, e, y);
+    };
+    const int ty = tid >> 5, tx = tid & 31;
+    double gq[2][2];
+#pragma unroll
+    for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+            const int i = ty + 32 * p2, j = tx + 32 * q2;
+            double v = 0.0;
+            if (i < R && j < R) {
+                v = a.S1[i * a.RS + j] * a.S2[i * a.RS + j];
+                if (i == j) v += a.alpha;
+                if (i == 0) prow[j] = v;
+                if (j == 0) pcol[i] = v;
+            }
+            gq[p2][q2] = v;
         }
-        Wm[i * PW + j] = v;
-    }
-    for (int e = tid; e < kSolveRows * R; e += 256) {
-        const int rr = e / R, k = e - rr * R;
-        rows[rr * P + k] = (row0 + rr < a.n) ? a.rhs[(size_t)(row0 + rr) * a.RS + k] : 0.0;
-    }
     __syncthreads();
-
+    TRITD_STAMP(1)
+    bool bad = false;
     for (int k = 0; k < R; ++k) {
-        const double piv = Wm[k * PW + k];
-        if (!(piv > 0.0) || !isfinite(piv)) {          // uniform across the CTA
-            if (tid == 0) atomicExch(&a.st->status, kStatusCholesky);
-            return;
-        }
-        const double inv = 1.0 / piv;
-        if (tid < W2) rowk[tid] = Wm[k * PW + tid] * inv;
-        else if (tid - W2 < R) colk[tid - W2] = Wm[(tid - W2) * PW + k];
-        if (W2 + R > 256)                               // R = 64: 192 threads' worth of work, fits; kept general
-            for (int q = 256 + tid; q < W2 + R; q += 256) colk[q - W2] = Wm[(q - W2) * PW + k];
-        __syncthreads();
-        for (int e = tid; e < R * W2; e += 256) {
-            const int i = e / W2, j = e - i * W2;
-            Wm[i * PW + j] = (i == k) ? rowk[j] : Wm[i * PW + j] - colk[i] * rowk[j];
-        }
+        const double* pr = prow + (k & 1) * 64;
+        const double* pc = pcol + (k & 1) * 64;
+        double* prn = prow + ((k + 1) & 1) * 64;
+        double* pcn = pcol + ((k + 1) & 1) * 64;
+        const double piv = pr[k];
+        bad = bad || !(piv > 0.0) || !isfinite(piv);
+        const double inv = fast_rcp(piv);
+#pragma unroll
+        for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+            for (int q2 = 0; q2 < 2; ++q2) {
+                const int i = ty + 32 * p2, j = tx + 32 * q2;
+                if (i < R && j < R) {
+                    double v;
+                    if (i == k) v = (j == k) ? inv : pr[j] * inv;
+                    else if (j == k) v = -pc[i] * inv;
+                    else v = fma(-pc[i], pr[j] * inv, gq[p2][q2]);
+                    gq[p2][q2] = v;
+                    if (i == k + 1) prn[j] = v;
+                    if (j == k + 1) pcn[i] = v;
+                }
+            }
         __syncthreads();
     }
+    if (bad) {                                         // uniform: every thread saw the same pivots
+        if (tid == 0) atomicExch(&a.st->status, kStatusCholesky);
+        return;
+    }
+#pragma unroll
+    for (int p2 = 0; p2 < 2; ++p2)
+#pragma unroll
+        for (int q2 = 0; q2 < 2; ++q2) {
+            const int i = ty + 32 * p2, j = tx + 32 * q2;
+            if (i < R && j < R) Gb[i * P + j] = gq[p2][q2];
+        }
+    __syncthreads();
+    const double* Gi = Gb;
+    TRITD_STAMP(2)
 
     // apply: xr[rr][k] = sum_m rows[rr][m] * inv(G)[m][k]
-    for (int e = tid; e < kSolveRows * R; e += 256) {
-        const int rr = e / R, k = e - rr * R;
-        double s0 = 0.0, s1 = 0.0;
-        int m = 0;
-        for (; m + 1 < R; m += 2) {
-            s0 = fma(rows[rr * P + m], Wm[m * PW + R + k], s0);
-            s1 = fma(rows[rr * P + m + 1], Wm[(m + 1) * PW + R + k], s1);
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        if (tid + m * kSolveThreads < kSolveRows * R) {
+            const int rr = ei[m], k = ej[m];
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int q = 0;
+            for (; q + 3 < R; q += 4) {
+                s0 = fma(rows[rr * P + q], Gi[q * P + k], s0);
+                s1 = fma(rows[rr * P + q + 1], Gi[(q + 1) * P + k], s1);
+                s2 = fma(rows[rr * P + q + 2], Gi[(q + 2) * P + k], s2);
+                s3 = fma(rows[rr * P + q + 3], Gi[(q + 3) * P + k], s3);
+            }
+            for (; q < R; ++q) s0 = fma(rows[rr * P + q], Gi[q * P + k], s0);
+            xr[rr * P + k] = (s0 + s1) + (s2 + s3);
         }
-        if (m < R) s0 = fma(rows[rr * P + m], Wm[m * PW + R + k], s0);
-        xr[rr * P + k] = s0 + s1;
     }
     __syncthreads();
-    for (int e = tid; e < kSolveRows * a.RS; e += 256) {
+    TRITD_STAMP(3)
+    for (int e = tid; e < kSolveRows * a.RS; e += kSolveThreads) {
         const int rr = e / a.RS, k = e - rr * a.RS;
         if (row0 + rr < a.n) a.X[(size_t)(row0 + rr) * a.RS + k] = (k < R) ? xr[rr * P + k] : 0.0;
     }
     if (a.XT) {
-        for (int e = tid; e < kSolveRows * a.RS; e += 256) {
+        for (int e = tid; e < kSolveRows * a.RS; e += kSolveThreads) {
             const int k = e / kSolveRows, rr = e - k * kSolveRows;
             if (row0 + rr < a.n) a.XT[(size_t)k * a.ldt + row0 + rr] = (k < R) ? xr[rr * P + k] : 0.0;
         }
     }
+    TRITD_STAMP(4)
     // partial small Gram of this CTA's rows (rows beyond n are zero)
-    for (int e = tid; e < R * R; e += 256) {
-        const int aa = e / R, bb = e - aa * R;
-        double s = 0.0;
-#pragma unroll 4
-        for (int rr = 0; rr < kSolveRows; ++rr) s = fma(xr[rr * P + aa], xr[rr * P + bb], s);
-        a.gram_part[(size_t)blockIdx.x * R * R + e] = s;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        if (tid + m * kSolveThreads < RR) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+            for (int rr = 0; rr < kSolveRows; rr += 4) {
+                s0 = fma(xr[rr * P + ei[m]], xr[rr * P + ej[m]], s0);
+                s1 = fma(xr[(rr + 1) * P + ei[m]], xr[(rr + 1) * P + ej[m]], s1);
+                s2 = fma(xr[(rr + 2) * P + ei[m]], xr[(rr + 2) * P + ej[m]], s2);
+                s3 = fma(xr[(rr + 3) * P + ei[m]], xr[(rr + 3) * P + ej[m]], s3);
+            }
+            a.gram_part[(size_t)blockIdx.x * RR + tid + m * kSolveThreads] = (s0 + s1) + (s2 + s3);
+        }
     }
+    TRITD_STAMP(5)
     __threadfence();
     __syncthreads();
+    TRITD_STAMP(6)
     if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (s_last) {
         __threadfence();
-        for (int e = tid; e < R * R; e += 256) {
-            double s = 0.0;
-            for (unsigned c = 0; c < gridDim.x; ++c) s += a.gram_part[(size_t)c * R * R + e];
-            const int aa = e / R, bb = e - aa * R;
-            a.gram_out[aa * a.RS + bb] = s;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int e = tid + m * kSolveThreads;
+            if (e < RR) {
+                double s0 = 0.0, s1 = 0.0;
+                unsigned c = 0;
+                for (; c + 1 < gridDim.x; c += 2) {
+                    s0 += a.gram_part[(size_t)c * RR + e];
+                    s1 += a.gram_part[(size_t)(c + 1) * RR + e];
+                }
+                if (c < gridDim.x) s0 += a.gram_part[(size_t)c * RR + e];
+                a.gram_out[ei[m] * a.RS + ej[m]] = s0 + s1;
+            }
         }
         if (tid == 0) *a.ticket = 0u;
     }
+    TRITD_STAMP(7)
+#undef TRITD_STAMP
 }
 
 }  // namespace tritd

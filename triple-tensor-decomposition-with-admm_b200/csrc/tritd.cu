@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -234,6 +235,7 @@ struct tritd_problem {
     double *norm_part = nullptr, *norms = nullptr;
     double* gram_part = nullptr;         // per-CTA partial small Grams of k_solve
     unsigned* ticket = nullptr;
+    long long* dbg = nullptr;            // optional clock64 stamps of k_solve (TRITD_DEBUG_STAMPS=1)
     int *tile0 = nullptr, *tile1 = nullptr;   // first / last i-tile of each k_mttkrp1 CTA
     IterState* st = nullptr;
     double *errHist = nullptr, *errL = nullptr, *errO = nullptr;
@@ -242,7 +244,7 @@ struct tritd_problem {
     alignas(64) AdmmMaps maps;           // [8 j][16 i] boxes of D, Y_L, E, Y_O, T, O for k_admm
     double* partF = nullptr;             // [gridA][128][RS] fused mode-1 partials (next iteration's X1*F')
     int *tileF = nullptr, *ctaTab = nullptr;   // i-tile of each k_admm CTA; (tile, index in tile, CTAs of tile)
-    int gridA = 0;
+    int gridA = 0, tileH = 128, nitA = 1;  // k_admm: rows per i-tile (16 x consumer warps used) and number of i-tiles
     bool rhsA_ready = false;             // partF holds X1*F' of the current T
     int n_it = 0, n_jc = 0, gridM = 0, gridP = 0, gridF = 0, gi = 0;
     long unitsM = 0, unitsP = 0;
@@ -304,7 +306,7 @@ static int launch_mttkrp1(tritd_problem* p, const CUtensorMap& map, const double
 #undef CALL
     CU_TRY(cudaGetLastError());
     const long tot = (long)p->n1 * p->RS;
-    k_mttkrp1_reduce<<<(unsigned)((tot + 31) / 32), 256, 0, c->stream>>>(p->partM, (size_t)2 * 128 * p->RS, rhs_out, p->n1,
+    k_mttkrp1_reduce<<<(unsigned)((tot + 31) / 32), 256, 0, c->stream>>>(p->partM, (size_t)2 * 128 * p->RS, 128, rhs_out, p->n1,
                                                                        p->RS, p->tile0, p->tile1, p->gridM, &p->st->stop);
     CU_TRY(cudaGetLastError());
     c->launches += 2;
@@ -349,7 +351,7 @@ static int launch_admm(tritd_problem* p) {
     AdmmArgs a;
     a.A1 = p->A1; a.B2 = p->B2; a.C3 = p->C3; a.st = p->st; a.norm_part = p->norm_part; a.partM = p->partF;
     a.cta_tab = p->ctaTab;
-    a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc;
+    a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc; a.tile_h = p->tileH;
 #define CALL(NT_, KS_) \
     k_admm<KS_, NT_, false><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, false>::kSmem, c->stream>>>(p->maps, a);
     TRITD_DISPATCH_R(p->r, CALL)
@@ -362,7 +364,7 @@ static int launch_admm(tritd_problem* p) {
 static int launch_reduce_fused_rhsA(tritd_problem* p, double* rhs_out) {
     tritd_ctx* c = p->ctx;
     const long tot = (long)p->n1 * p->RS;
-    k_mttkrp1_reduce<<<(unsigned)((tot + 31) / 32), 256, 0, c->stream>>>(p->partF, (size_t)128 * p->RS, rhs_out, p->n1, p->RS,
+    k_mttkrp1_reduce<<<(unsigned)((tot + 31) / 32), 256, 0, c->stream>>>(p->partF, (size_t)128 * p->RS, p->tileH, rhs_out, p->n1, p->RS,
                                                                        p->tileF, p->tileF, p->gridA, &p->st->stop);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
@@ -370,8 +372,8 @@ static int launch_reduce_fused_rhsA(tritd_problem* p, double* rhs_out) {
 }
 
 static size_t smem_solve(int R) {
-    const int PW = (2 * R) | 1, P = R | 1;
-    return (size_t)(R * PW + 3 * R + 2 * kSolveRows * P) * sizeof(double);
+    const int P = R | 1;
+    return (size_t)(R * P + 256 + 2 * kSolveRows * P) * sizeof(double);
 }
 
 // X = rhs * inv(S1 o S2 + alpha I); also S_out = X'X (rows of this rank) and optionally X transposed.
@@ -380,9 +382,9 @@ static int launch_solve(tritd_problem* p, const double* rhs, const double* S1, c
     tritd_ctx* c = p->ctx;
     SolveArgs a;
     a.rhs = rhs; a.S1 = S1; a.S2 = S2; a.alpha = alpha; a.X = X; a.XT = XT; a.st = p->st;
-    a.gram_part = p->gram_part; a.gram_out = S_out; a.ticket = p->ticket;
+    a.gram_part = p->gram_part; a.gram_out = S_out; a.ticket = p->ticket; a.dbg = p->dbg;
     a.n = n; a.R = p->R; a.RS = p->RS; a.ldt = p->ldt;
-    k_solve<<<(n + kSolveRows - 1) / kSolveRows, 256, smem_solve(p->R), c->stream>>>(a);
+    k_solve<<<(n + kSolveRows - 1) / kSolveRows, kSolveThreads, smem_solve(p->R), c->stream>>>(a);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     return TRITD_OK;
@@ -460,6 +462,7 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         const int nmax = std::max(p->n1, std::max(p->n2, p->n3));
         PALLOC(gram_part, (size_t)((nmax + kSolveRows - 1) / kSolveRows) * p->R * p->R);
         PALLOC(ticket, 4);
+        if (getenv("TRITD_DEBUG_STAMPS")) { PALLOC(dbg, 16); cudaMemset(p->dbg, 0, 128); }
         PALLOC(tile0, p->gridM); PALLOC(tile1, p->gridM);
         std::vector<int> t0(p->gridM), t1(p->gridM);
         const long per_it = (long)p->n_jc * p->n3;
@@ -471,27 +474,25 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         cudaMemcpy(p->tile0, t0.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
         cudaMemcpy(p->tile1, t1.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
         cudaMemset(p->ticket, 0, 16);
-        // k_admm: one CTA per SM; CTAs are dealt to the i-tiles in proportion to the rows each tile holds
-        p->gridA = std::max(c->num_sms, p->n_it);
-        std::vector<int> per(p->n_it, 1);
-        {
-            int left = p->gridA - p->n_it;
-            std::vector<double> want(p->n_it);
-            for (int q = 0; q < p->n_it; ++q) want[q] = (double)std::min(128, p->n1 - q * 128) / p->n1 * p->gridA;
-            for (int q = 0; q < p->n_it && left > 0; ++q) { int add = std::min(left, std::max(0, (int)want[q] - 1)); per[q] += add; left -= add; }
-            for (int q = 0; left > 0; q = (q + 1) % p->n_it) { ++per[q]; --left; }
-        }
+        // k_admm: one CTA per SM.  The i-tiles are as even as 16-row warp strips allow (240 rows -> 128 + 112,
+        // 130 rows -> 80 + 50) and every tile gets the same number of CTAs: a stage costs the same whether
+        // 7 or 8 warps work on it, so equal stage counts finish together.
+        const int nwr = (p->n1 + 15) / 16;
+        p->nitA = (nwr + 7) / 8;
+        p->tileH = 16 * ((nwr + p->nitA - 1) / p->nitA);
+        p->gridA = std::max(c->num_sms / p->nitA, 1) * p->nitA;
+        std::vector<int> per(p->nitA, p->gridA / p->nitA);
         PALLOC(partF, (size_t)p->gridA * 128 * p->RS);
         PALLOC(tileF, p->gridA);
         PALLOC(ctaTab, 3 * p->gridA);
         std::vector<int> tf(p->gridA), tab(3 * p->gridA);
         {
             // interleave the tiles so neighbouring CTAs (launched together) work on the same columns
-            std::vector<int> used(p->n_it, 0);
+            std::vector<int> used(p->nitA, 0);
             int q = 0;
             for (int cta = 0; cta < p->gridA;) {
                 if (used[q] < per[q]) { tf[cta] = q; tab[3 * cta] = q; tab[3 * cta + 1] = used[q]++; tab[3 * cta + 2] = per[q]; ++cta; }
-                q = (q + 1) % p->n_it;
+                q = (q + 1) % p->nitA;
             }
         }
         cudaMemcpy(p->tileF, tf.data(), sizeof(int) * p->gridA, cudaMemcpyHostToDevice);
@@ -535,7 +536,7 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         // k_admm views each N-array as (i_lo = 16, j, i_hi = ld1/16, t): one box = [8 i_hi][8 j][16 i_lo]
         cuuint64_t dims4[4] = {16, (cuuint64_t)p->n2, (cuuint64_t)(p->ld1 / 16), (cuuint64_t)p->n3};
         cuuint64_t str4[3] = {(cuuint64_t)p->ld1 * 8, 128, (cuuint64_t)p->ld1 * p->n2 * 8};
-        cuuint32_t box4[4] = {16, 8, 8, 1};
+        cuuint32_t box4[4] = {16, 8, (cuuint32_t)(p->tileH / 16), 1};
         struct { CUtensorMap* m; double* base; } mm[6] = {{&p->maps.D, p->D}, {&p->maps.YL, p->YL}, {&p->maps.E, p->E},
                                                          {&p->maps.YO, p->YO}, {&p->maps.T, p->T}, {&p->maps.O, p->O}};
         for (auto& q : mm)
@@ -722,13 +723,23 @@ static int enqueue_iteration(tritd_problem* p) {
     ST_TRY(launch_admm(p));
     p->rhsA_ready = true;
     ST_TRY(mark());
-    k_sum_pairs<<<1, 256, 0, st>>>(p->norm_part, p->gridA, p->norms, stop);
+    if (c->nranks > 1) {
+        k_sum_pairs<<<1, 256, 0, st>>>(p->norm_part, p->gridA, p->norms, stop);
+        CU_TRY(cudaGetLastError());
+        c->launches += 1;
+        ST_TRY(allreduce_sum(c, p->norms, 2));
+    }
+    k_finalize<<<1, 256, 0, st>>>(p->st, p->norm_part, p->gridA, p->norms, c->nranks > 1 ? 1 : 0, p->errHist, p->errL, p->errO);
     CU_TRY(cudaGetLastError());
-    ST_TRY(allreduce_sum(c, p->norms, 2));
-    k_finalize<<<1, 32, 0, st>>>(p->st, p->norms, p->errHist, p->errL, p->errO);
-    CU_TRY(cudaGetLastError());
-    c->launches += 2;
+    c->launches += 1;
     ST_TRY(mark());
+    return TRITD_OK;
+}
+
+// diagnostics: the clock64 stamps k_solve leaves when TRITD_DEBUG_STAMPS is set (not part of the public header)
+extern "C" int tritd_debug_stamps(tritd_problem* p, long long* out8) {
+    if (!p || !p->dbg) return fail(TRITD_ERR_INVALID, "no debug stamps");
+    CU_TRY(cudaMemcpy(out8, p->dbg, 64, cudaMemcpyDeviceToHost));
     return TRITD_OK;
 }
 
