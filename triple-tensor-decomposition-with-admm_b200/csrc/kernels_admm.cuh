@@ -8,8 +8,8 @@
 //   :74-78   X1*F' of the NEXT iteration's update_A (mode-1 MTTKRP of the new T), accumulated
 //            from registers so T is read from HBM only once per iteration (by k_ppass).
 //
-// Structure: CTA = 8 consumer warps x 16 rows i (an i-tile of 128 rows) + 1 warp that drives TMA.
-// A stage is one "j-group": 8 columns j of slice t for the whole i-tile, i.e. four 8 KB boxes
+// Structure: CTA = 8 consumer warps x 16 rows i (an i-tile of <= 128 rows) + 1 warp that drives TMA.
+// A stage is JG (1 or 2) groups of 8 columns j of slice t for the whole i-tile, i.e. four 8*JG KB boxes
 // (D, Y_L, E, Y_O) fetched by ONE TMA op each through a 4-D view (i_lo=16, j, i_hi, t) of the
 // column-major arrays, which lands as [warp][8 j][16 i] with the 128B swizzle pattern the DMMA
 // accumulator layout reads conflict-free.  Consumers update the boxes in place (T over D) plus a fifth
@@ -37,14 +37,16 @@ struct AdmmArgs {
     int tile_h;                        // rows per i-tile: 16 * (consumer warps used), <= 128
 };
 
-constexpr int kBoxD = 8 * 128;         // doubles per array per stage: [8 warps][8 j][16 i]
-
 template <int KS, int NT, bool WRITE_O> struct AdmmCfg {
     static constexpr int PL = FusedCfg<KS>::PL;
     static constexpr int NB = WRITE_O ? 5 : 4;                                  // boxes per stage
-    static constexpr int kStageBytes = NB * kBoxD * 8 + 1024;                   // + the C3 row of the slice; keeps boxes 1 KB aligned
     static constexpr int kFixed = (32 * PL + NT * 8 * kPJ + 64) * 8 + 1024;
     static constexpr int kAvail = 227 * 1024 - kFixed;
+    // a stage holds JG groups of 8 columns: two when three such stages fit (more independent work per warp
+    // between barriers), else one
+    static constexpr int JG = (kAvail / (NB * 2 * 8 * 128 * 8 + 1024)) >= 3 ? 2 : 1;
+    static constexpr int kBoxD = 8 * JG * 128;                                  // doubles per array per stage: [8 warps][8*JG j][16 i]
+    static constexpr int kStageBytes = NB * kBoxD * 8 + 1024;                   // + the C3 row of the slice; keeps boxes 1 KB aligned
     static constexpr int S = (kAvail / kStageBytes) > 6 ? 6 : (kAvail / kStageBytes);
     static constexpr size_t kSmem = (size_t)S * kStageBytes + kFixed;
     static_assert(S >= 3, "ring too shallow");
@@ -111,8 +113,9 @@ constexpr int kAdmmThreads = 384;
 template <int KS, int NT, bool WRITE_O>
 __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant__ AdmmMaps maps, const AdmmArgs a) {
     using Cfg = AdmmCfg<KS, NT, WRITE_O>;
-    constexpr int PL = Cfg::PL, NB = Cfg::NB, S = Cfg::S;
+    constexpr int PL = Cfg::PL, NB = Cfg::NB, S = Cfg::S, JG = Cfg::JG, kBoxD = Cfg::kBoxD;
     constexpr int kStageD = Cfg::kStageBytes / 8;
+    constexpr int SPU = 4 / JG;           // stages per unit (32 columns of one slice)
     constexpr bool kFoldA = KS <= 8;      // fold C3[t,:] into the A fragments once per slice (else into B per use)
     if (a.st->stop) return;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
     const int it = a.cta_tab[3 * blockIdx.x], x = a.cta_tab[3 * blockIdx.x + 1], gi = a.cta_tab[3 * blockIdx.x + 2];
     const long V = (long)a.n_jc * a.n3;
     const long v0 = V * x / gi, v1 = V * (x + 1) / gi;
-    const long nq = (v1 - v0) * 4;
+    const long nq = (v1 - v0) * SPU;
     const int nw = a.tile_h >> 4;                                    // consumer warps per tile (= TMA box depth in i_hi)
     const int nact = min(nw, (a.n1 - it * a.tile_h + 15) >> 4);      // ... of which have rows inside the tensor
     const int jc0 = (int)(v0 / a.n3), t0 = (int)(v0 - (long)jc0 * a.n3);
@@ -148,14 +151,14 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
             int ljc = jc0, lt = t0, ljg = 0, ls = 0;                 // load cursor
             auto issue_load = [&]() {
                 double* st = ring + (size_t)ls * kStageD;
-                const int j0 = ljc * 32 + ljg * 8;
-                mbar_expect_tx(&full[ls], 4 * nw * 1024 + NT * 8 * 8);
+                const int j0 = ljc * 32 + ljg * (8 * JG);
+                mbar_expect_tx(&full[ls], 4 * nw * JG * 1024 + NT * 8 * 8);
                 tma_load_4d(st, &maps.D, &full[ls], 0, j0, it * nw, lt);
                 tma_load_4d(st + kBoxD, &maps.YL, &full[ls], 0, j0, it * nw, lt);
                 tma_load_4d(st + 2 * kBoxD, &maps.E, &full[ls], 0, j0, it * nw, lt);
                 tma_load_4d(st + 3 * kBoxD, &maps.YO, &full[ls], 0, j0, it * nw, lt);
                 bulk_load_1d(st + NB * kBoxD, a.C3 + (size_t)lt * a.RS, NT * 8 * 8, &full[ls]);   // C3 row of slice t
-                if (++ljg == 4) { ljg = 0; if (++lt == a.n3) { lt = 0; ++ljc; } }
+                if (++ljg == SPU) { ljg = 0; if (++lt == a.n3) { lt = 0; ++ljc; } }
                 if (++ls == S) ls = 0;
             };
             long loaded = 0;
@@ -164,14 +167,14 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
             for (long q = 0; q < nq; ++q) {
                 mbar_wait(&done[ss], sph);
                 double* st = ring + (size_t)ss * kStageD;
-                const int j0 = sjc * 32 + sjg * 8;
+                const int j0 = sjc * 32 + sjg * (8 * JG);
                 tma_store_4d(&maps.T, st, 0, j0, it * nw, stt);
                 tma_store_4d(&maps.YL, st + kBoxD, 0, j0, it * nw, stt);
                 tma_store_4d(&maps.E, st + 2 * kBoxD, 0, j0, it * nw, stt);
                 tma_store_4d(&maps.YO, st + 3 * kBoxD, 0, j0, it * nw, stt);
                 if (WRITE_O) tma_store_4d(&maps.O, st + 4 * kBoxD, 0, j0, it * nw, stt);
                 tma_store_commit();
-                if (++sjg == 4) { sjg = 0; if (++stt == a.n3) { stt = 0; ++sjc; } }
+                if (++sjg == SPU) { sjg = 0; if (++stt == a.n3) { stt = 0; ++sjc; } }
                 if (++ss == S) { ss = 0; sph ^= 1; }
                 if (q >= 1 && loaded < nq) {          // stage q-1 has left shared memory: refill its slot
                     tma_store_wait_read<1>();
@@ -206,9 +209,10 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
             for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
         double aS[2][kFoldA ? KS : 1];
         double sL = 0.0, sO = 0.0;
-        // swizzled offsets (in double2 units) of this lane's two columns c = 0, 1 inside its warp's [8 j][16 i] block
-        const int off0 = warp * 64 + (2 * tig) * 8 + (g ^ (2 * tig));
-        const int off1 = warp * 64 + (2 * tig + 1) * 8 + (g ^ (2 * tig + 1));
+        // swizzled offsets (in double2 units) of this lane's two columns c = 0, 1 of the first column group inside its
+        // warp's [8*JG j][16 i] block; the second group is 64 further (8 rows of 128 B, same swizzle phase)
+        const int off0 = warp * (64 * JG) + (2 * tig) * 8 + (g ^ (2 * tig));
+        const int off1 = warp * (64 * JG) + (2 * tig + 1) * 8 + (g ^ (2 * tig + 1));
         int slot = 0; uint32_t ph = 0;
         int jc = jc0, t = t0, cur_jc = -1;
         const int nthr = nact * 32;
@@ -229,18 +233,33 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
                 asm volatile("bar.sync 1, %0;" ::"r"(nthr));
                 cur_jc = jc;
             }
-            double l[2][2];
 #pragma unroll
-            for (int jg = 0; jg < 4; ++jg) {
+            for (int sg = 0; sg < SPU; ++sg) {
                 double* st = ring + (size_t)slot * kStageD;
                 mbar_wait(&full[slot], ph);
                 const double* c3row = st + NB * kBoxD;       // C3(t, :), landed with this stage
-                // L patch of column group jg_: l[m][c] = L(i0 + m, j0 + 2*tig + c, t)
-                auto l_patch = [&](int jg_, double (&l)[2][2]) {
-                    l[0][0] = l[0][1] = l[1][0] = l[1][1] = 0.0;
+                if (kFoldA && sg == 0) {
+#pragma unroll
+                    for (int s = 0; s < KS; ++s) {
+                        const double c3 = c3row[4 * s + tig];
+                        aS[0][s] = aF[0][s] * c3;
+                        aS[1][s] = aF[1][s] * c3;
+                    }
+                }
+                double c3s[NT];                              // column scales of the MTTKRP B fragments
+#pragma unroll
+                for (int n = 0; n < NT; ++n) c3s[n] = c3row[8 * n + g];
+                double2* s2 = reinterpret_cast<double2*>(st);
+                // the JG column groups of a stage are independent: one basic block, so their DMMA and
+                // element-wise dependency chains interleave
+#pragma unroll
+                for (int h = 0; h < JG; ++h) {
+                    const int jg = sg * JG + h;
+                    // L patch: l[m][c] = L(i0 + m, j0 + 2*tig + c, t)
+                    double l[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
-                        double b = B2s[(jg_ * 8 + g) * PL + 4 * ks + tig];
+                        double b = B2s[(jg * 8 + g) * PL + 4 * ks + tig];
                         if (kFoldA) {
                             dmma884(l[0][0], l[0][1], aS[0][ks], b);
                             dmma884(l[1][0], l[1][1], aS[1][ks], b);
@@ -250,58 +269,38 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
                             dmma884(l[1][0], l[1][1], aF[1][ks], b);
                         }
                     }
-                };
-                if (jg == 0) {
-                    if (kFoldA) {
+                    double2 tn[2];
 #pragma unroll
-                        for (int s = 0; s < KS; ++s) {
-                            const double c3 = c3row[4 * s + tig];
-                            aS[0][s] = aF[0][s] * c3;
-                            aS[1][s] = aF[1][s] * c3;
-                        }
+                    for (int c = 0; c < 2; ++c) {
+                        const int off = (c ? off1 : off0) + 64 * h;
+                        const double2 d = s2[off];
+                        double2 yl = s2[kBoxD / 2 + off];
+                        double2 e = s2[2 * (kBoxD / 2) + off];
+                        double2 yo = s2[3 * (kBoxD / 2) + off];
+                        double2 o;
+                        admm_point2(prm, d.x, l[0][c], yl.x, e.x, yo.x, o.x, tn[c].x, sL, sO);
+                        admm_point2(prm, d.y, l[1][c], yl.y, e.y, yo.y, o.y, tn[c].y, sL, sO);
+                        s2[off] = tn[c];
+                        s2[kBoxD / 2 + off] = yl;
+                        s2[2 * (kBoxD / 2) + off] = e;
+                        s2[3 * (kBoxD / 2) + off] = yo;
+                        if (WRITE_O) s2[4 * (kBoxD / 2) + off] = o;
                     }
-                    l_patch(0, l);
-                }
-                // the DMMA chain of the NEXT column group does not depend on the data of this stage: issued
-                // here, in the same basic block as the element-wise pass, the scheduler overlaps the two chains
-                double ln[2][2];
-                if (jg < 3) l_patch(jg + 1, ln);
-                double c3s[NT];                              // column scales of the MTTKRP B fragments
+                    // next iteration's X1*F': acc[m][n] += T'(i,j) B2(j,k) C3(t,k); k-step c covers j = j0 + 2*tig + c
 #pragma unroll
-                for (int n = 0; n < NT; ++n) c3s[n] = c3row[8 * n + g];
-                double2* s2 = reinterpret_cast<double2*>(st);
-                double2 tn[2];
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const int off = c ? off1 : off0;
-                    const double2 d = s2[off];
-                    double2 yl = s2[kBoxD / 2 + off];
-                    double2 e = s2[2 * (kBoxD / 2) + off];
-                    double2 yo = s2[3 * (kBoxD / 2) + off];
-                    double2 o;
-                    admm_point2(prm, d.x, l[0][c], yl.x, e.x, yo.x, o.x, tn[c].x, sL, sO);
-                    admm_point2(prm, d.y, l[1][c], yl.y, e.y, yo.y, o.y, tn[c].y, sL, sO);
-                    s2[off] = tn[c];
-                    s2[kBoxD / 2 + off] = yl;
-                    s2[2 * (kBoxD / 2) + off] = e;
-                    s2[3 * (kBoxD / 2) + off] = yo;
-                    if (WRITE_O) s2[4 * (kBoxD / 2) + off] = o;
+                    for (int n = 0; n < NT; ++n) {
+                        const double2 b = *reinterpret_cast<const double2*>(B2T + (8 * n + g) * kPJ + jg * 8 + 2 * tig);
+                        const double b0 = b.x * c3s[n], b1 = b.y * c3s[n];
+                        dmma884(acc[0][n][0], acc[0][n][1], tn[0].x, b0);
+                        dmma884(acc[1][n][0], acc[1][n][1], tn[0].y, b0);
+                        dmma884(acc[0][n][0], acc[0][n][1], tn[1].x, b1);
+                        dmma884(acc[1][n][0], acc[1][n][1], tn[1].y, b1);
+                    }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&done[slot]);
                 if (++slot == S) { slot = 0; ph ^= 1; }
-                // next iteration's X1*F': acc[m][n] += T'(i,j) B2(j,k) C3(t,k); k-step c covers j = j0 + 2*tig + c
-#pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    const double2 b = *reinterpret_cast<const double2*>(B2T + (8 * n + g) * kPJ + jg * 8 + 2 * tig);
-                    const double b0 = b.x * c3s[n], b1 = b.y * c3s[n];
-                    dmma884(acc[0][n][0], acc[0][n][1], tn[0].x, b0);
-                    dmma884(acc[1][n][0], acc[1][n][1], tn[0].y, b0);
-                    dmma884(acc[0][n][0], acc[0][n][1], tn[1].x, b1);
-                    dmma884(acc[1][n][0], acc[1][n][1], tn[1].y, b1);
-                }
-                if (jg < 3) { l[0][0] = ln[0][0]; l[0][1] = ln[0][1]; l[1][0] = ln[1][0]; l[1][1] = ln[1][1]; }
             }
             if (++t == a.n3) { t = 0; ++jc; }
         }

@@ -536,7 +536,17 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         // k_admm views each N-array as (i_lo = 16, j, i_hi = ld1/16, t): one box = [8 i_hi][8 j][16 i_lo]
         cuuint64_t dims4[4] = {16, (cuuint64_t)p->n2, (cuuint64_t)(p->ld1 / 16), (cuuint64_t)p->n3};
         cuuint64_t str4[3] = {(cuuint64_t)p->ld1 * 8, 128, (cuuint64_t)p->ld1 * p->n2 * 8};
-        cuuint32_t box4[4] = {16, 8, (cuuint32_t)(p->tileH / 16), 1};
+        int jgroups = 1;
+        {
+            auto q = [&]() -> int {
+#define CALL(NT_, KS_) jgroups = AdmmCfg<KS_, NT_, false>::JG;
+                TRITD_DISPATCH_R(r, CALL)
+#undef CALL
+                return TRITD_OK;
+            };
+            if ((s = q()) != TRITD_OK) return bail(s);
+        }
+        cuuint32_t box4[4] = {16, (cuuint32_t)(8 * jgroups), (cuuint32_t)(p->tileH / 16), 1};
         struct { CUtensorMap* m; double* base; } mm[6] = {{&p->maps.D, p->D}, {&p->maps.YL, p->YL}, {&p->maps.E, p->E},
                                                          {&p->maps.YO, p->YO}, {&p->maps.T, p->T}, {&p->maps.O, p->O}};
         for (auto& q : mm)
