@@ -40,7 +40,10 @@ struct AdmmArgs {
 template <int KS, int NT, bool WRITE_O> struct AdmmCfg {
     static constexpr int PL = FusedCfg<KS>::PL;
     static constexpr int NB = WRITE_O ? 5 : 4;                                  // boxes per stage
-    static constexpr int kFixed = (32 * PL + NT * 8 * kPJ + 64) * 8 + 1024;
+    // large R: the B operand of L is read from the transposed chunk too (2-way bank conflict on a small share of
+    // the shared-memory traffic) so that the second layout's 17 KB buy a two-group stage
+    static constexpr bool kShareB = KS > 8;
+    static constexpr int kFixed = ((kShareB ? 0 : 32 * PL) + NT * 8 * kPJ + 64) * 8 + 1024;
     static constexpr int kAvail = 227 * 1024 - kFixed;
     // a stage holds JG groups of 8 columns: two when three such stages fit (more independent work per warp
     // between barriers), else one
@@ -121,7 +124,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);              // [S][NB boxes + C3 row]
     double* B2s = ring + (size_t)S * kStageD;                        // [32 j][PL]      B-operand of L
-    double* B2T = B2s + 32 * PL;                                     // [NT*8 k][kPJ]   B-operand of the MTTKRP
+    double* B2T = B2s + (Cfg::kShareB ? 0 : 32 * PL);                // [NT*8 k][kPJ]   B-operand of the MTTKRP
     double* red = B2T + NT * 8 * kPJ;                                // [64]
     uint64_t* full = reinterpret_cast<uint64_t*>(red + 64);          // [S] TMA landed
     uint64_t* done = full + S;                                       // [S] consumers finished writing back
@@ -220,11 +223,12 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         for (long u = v0; u < v1; ++u) {
             if (jc != cur_jc) {                    // uniform over the consumers: all walk the same sequence
                 asm volatile("bar.sync 1, %0;" ::"r"(nthr));
-                for (int e = threadIdx.x; e < 32 * 4 * KS; e += nthr) {
-                    const int j = e / (4 * KS), k = e - j * (4 * KS);
-                    const int jj = jc * 32 + j;
-                    B2s[j * PL + k] = (jj < a.n2) ? a.B2[(size_t)jj * a.RS + k] : 0.0;
-                }
+                if (!Cfg::kShareB)
+                    for (int e = threadIdx.x; e < 32 * 4 * KS; e += nthr) {
+                        const int j = e / (4 * KS), k = e - j * (4 * KS);
+                        const int jj = jc * 32 + j;
+                        B2s[j * PL + k] = (jj < a.n2) ? a.B2[(size_t)jj * a.RS + k] : 0.0;
+                    }
                 for (int e = threadIdx.x; e < NT * 8 * 32; e += nthr) {
                     const int j = e / (NT * 8), k = e - j * (NT * 8);
                     const int jj = jc * 32 + j;
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
                     double l[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
-                        double b = B2s[(jg * 8 + g) * PL + 4 * ks + tig];
+                        double b = Cfg::kShareB ? B2T[(4 * ks + tig) * kPJ + jg * 8 + g] : B2s[(jg * 8 + g) * PL + 4 * ks + tig];
                         if (kFoldA) {
                             dmma884(l[0][0], l[0][1], aS[0][ks], b);
                             dmma884(l[1][0], l[1][1], aS[1][ks], b);
