@@ -60,6 +60,7 @@ struct SolveArgs {
 constexpr int kSolveRows = 32;
 constexpr int kSolveThreads = 1024;
 
+template <int PQ>   // PQ x PQ register patch per thread: 1 for R <= 32, 2 for R <= 64
 __global__ void __launch_bounds__(kSolveThreads) k_solve(const SolveArgs a) {
     if (a.st->stop) return;
     extern __shared__ double sm[];
@@ -69,8 +70,9 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(const SolveArgs a) {
     double* pcol = prow + 128;             // [2][64]    published pivot column (double-buffered)
     double* rows = pcol + 128;             // [32][P]    RHS rows
     double* xr = rows + kSolveRows * P;    // [32][P]    solved rows
-    __shared__ int s_last;
+    __shared__ int s_last, s_bad;
     const int tid = threadIdx.x;
+    if (tid == 0) s_bad = 0;
     const int row0 = blockIdx.x * kSolveRows;
 #define TRITD_STAMP(q) if (a.dbg && blockIdx.x == 0 && tid == 0) a.dbg[q] = clock64();
     TRITD_STAMP(0)
@@ -100,11 +102,11 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(const SolveArgs a) {
         return fma(y, e, y);
     };
     const int ty = tid >> 5, tx = tid & 31;
-    double gq[2][2];
+    double gq[PQ][PQ];
 #pragma unroll
-    for (int p2 = 0; p2 < 2; ++p2)
+    for (int p2 = 0; p2 < PQ; ++p2)
 #pragma unroll
-        for (int q2 = 0; q2 < 2; ++q2) {
+        for (int q2 = 0; q2 < PQ; ++q2) {
             const int i = ty + 32 * p2, j = tx + 32 * q2;
             double v = 0.0;
             if (i < R && j < R) {
@@ -118,43 +120,49 @@ __global__ void __launch_bounds__(kSolveThreads) k_solve(const SolveArgs a) {
     __syncthreads();
     TRITD_STAMP(1)
     bool bad = false;
-    for (int k = 0; k < R; ++k) {
-        const double* pr = prow + (k & 1) * 64;
-        const double* pc = pcol + (k & 1) * 64;
-        double* prn = prow + ((k + 1) & 1) * 64;
-        double* pcn = pcol + ((k + 1) & 1) * 64;
-        const double piv = pr[k];
-        bad = bad || !(piv > 0.0) || !isfinite(piv);
-        const double inv = fast_rcp(piv);
+    // only the warps that own rows take part in the elimination (named barrier over those warps)
+    const int nwarp_act = PQ == 1 ? R : 32;
+    if (ty < nwarp_act) {
+        for (int k = 0; k < R; ++k) {
+            const double* pr = prow + (k & 1) * 64;
+            const double* pc = pcol + (k & 1) * 64;
+            double* prn = prow + ((k + 1) & 1) * 64;
+            double* pcn = pcol + ((k + 1) & 1) * 64;
+            const double piv = pr[k];
+            bad = bad || !(piv > 0.0) || !isfinite(piv);
+            const double inv = fast_rcp(piv);
 #pragma unroll
-        for (int p2 = 0; p2 < 2; ++p2)
+            for (int p2 = 0; p2 < PQ; ++p2)
 #pragma unroll
-            for (int q2 = 0; q2 < 2; ++q2) {
-                const int i = ty + 32 * p2, j = tx + 32 * q2;
-                if (i < R && j < R) {
-                    double v;
-                    if (i == k) v = (j == k) ? inv : pr[j] * inv;
-                    else if (j == k) v = -pc[i] * inv;
-                    else v = fma(-pc[i], pr[j] * inv, gq[p2][q2]);
-                    gq[p2][q2] = v;
-                    if (i == k + 1) prn[j] = v;
-                    if (j == k + 1) pcn[i] = v;
+                for (int q2 = 0; q2 < PQ; ++q2) {
+                    const int i = ty + 32 * p2, j = tx + 32 * q2;
+                    if (i < R && j < R) {
+                        double v;
+                        if (i == k) v = (j == k) ? inv : pr[j] * inv;
+                        else if (j == k) v = -pc[i] * inv;
+                        else v = fma(-pc[i], pr[j] * inv, gq[p2][q2]);
+                        gq[p2][q2] = v;
+                        if (i == k + 1) prn[j] = v;
+                        if (j == k + 1) pcn[i] = v;
+                    }
                 }
+            asm volatile("bar.sync 1, %0;" ::"r"(nwarp_act * 32));
+        }
+#pragma unroll
+        for (int p2 = 0; p2 < PQ; ++p2)
+#pragma unroll
+            for (int q2 = 0; q2 < PQ; ++q2) {
+                const int i = ty + 32 * p2, j = tx + 32 * q2;
+                if (i < R && j < R) Gb[i * P + j] = gq[p2][q2];
             }
-        __syncthreads();
+        if (bad && tid == 0) s_bad = 1;
     }
-    if (bad) {                                         // uniform: every thread saw the same pivots
+    __syncthreads();
+    bad = s_bad != 0;
+    if (bad) {                                         // uniform (every thread of the elimination saw the same pivots)
         if (tid == 0) atomicExch(&a.st->status, kStatusCholesky);
         return;
     }
-#pragma unroll
-    for (int p2 = 0; p2 < 2; ++p2)
-#pragma unroll
-        for (int q2 = 0; q2 < 2; ++q2) {
-            const int i = ty + 32 * p2, j = tx + 32 * q2;
-            if (i < R && j < R) Gb[i * P + j] = gq[p2][q2];
-        }
-    __syncthreads();
     const double* Gi = Gb;
     TRITD_STAMP(2)
 

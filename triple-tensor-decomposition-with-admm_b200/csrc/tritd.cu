@@ -384,7 +384,8 @@ static int launch_solve(tritd_problem* p, const double* rhs, const double* S1, c
     a.rhs = rhs; a.S1 = S1; a.S2 = S2; a.alpha = alpha; a.X = X; a.XT = XT; a.st = p->st;
     a.gram_part = p->gram_part; a.gram_out = S_out; a.ticket = p->ticket; a.dbg = p->dbg;
     a.n = n; a.R = p->R; a.RS = p->RS; a.ldt = p->ldt;
-    k_solve<<<(n + kSolveRows - 1) / kSolveRows, kSolveThreads, smem_solve(p->R), c->stream>>>(a);
+    if (p->R <= 32) k_solve<1><<<(n + kSolveRows - 1) / kSolveRows, kSolveThreads, smem_solve(p->R), c->stream>>>(a);
+    else k_solve<2><<<(n + kSolveRows - 1) / kSolveRows, kSolveThreads, smem_solve(p->R), c->stream>>>(a);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     return TRITD_OK;
@@ -514,7 +515,7 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
                                 (int)AdmmCfg<KS_, NT_, false>::kSmem));
             TRITD_DISPATCH_R(r, CALL)
 #undef CALL
-            CU_TRY(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(TRITD_MAX_R * TRITD_MAX_R)));
+            CU_TRY(cudaFuncSetAttribute(k_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(TRITD_MAX_R * TRITD_MAX_R)));
             return TRITD_OK;
         };
         if ((s = q()) != TRITD_OK) return bail(s);
