@@ -224,23 +224,30 @@ def main():
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    prob.set_profiling(True)
     launches0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    prob.enqueue(K)
+    prob.enqueue(K)                       # K iterations back to back on `stream` (CUDA-graph replays), no host sync
     e1.record(stream)
     barrier()
     sampler.stop_flag = True
     sampler.join()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launches - launches0
-    phase_ms, nprof = prob.phase_ms()
-    prob.set_profiling(False)
     prob.sync()
     res = prob.get(want_O=False)
     assert res["iters"] == W + K, (res["iters"], W + K)
     assert np.all(np.isfinite(res["errHist"]))
+    # second pass over the same K steps with the library's per-phase CUDA events (plain launches) for the
+    # per-kernel times the roofline needs; kept out of `value` because the events add gaps
+    prob.init(bench_opts, A0, B0, C0)
+    prob.enqueue(W)
+    prob.sync()
+    barrier()
+    prob.set_profiling(True)
+    prob.enqueue(K)
+    phase_ms, nprof = prob.phase_ms()
+    prob.set_profiling(False)
     prob.close()
     value = K / (ms_total * 1e-3)
 
@@ -259,9 +266,10 @@ def main():
         pass
     R = r * r
     flops_iter = 8.0 * N_global * R + 2.0 * R * R * (n2 * n3 + n1 * n3 + n1 * n2)
-    roofline = {"bound": "hbm", "kernel": "k_fused (L reconstruction + O/E/dual/T update + residual norms)",
+    roofline = {"bound": "hbm", "kernel": "k_admm (TMA in / DMMA L reconstruction + O/E/dual/T update + residual norms + next mode-1 MTTKRP / TMA out)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": FUSED_BYTES * N_local, "kernel_ms": fused_ms,
+                "kernel_ms_source": "CUDA events recorded by the library around k_admm on the launching stream, averaged over a second pass of the same K steps",
                 "iteration_GBps_vs_96N": 96.0 * N_global / world / (ms_total / K * 1e-3) * 1e-9,
                 "iteration_fp64_TFLOPs": flops_iter / world / (ms_total / K * 1e-3) * 1e-12,
                 "dmma_peak_TFLOPs_measured": 37.2,
@@ -274,23 +282,25 @@ def main():
         Dp = torch.empty(D.size, dtype=torch.float64).pin_memory()
         Dn = Dp.numpy().reshape(D.shape, order="F")
         Dn[...] = D
+        Op = torch.empty(D.size, dtype=torch.float64).pin_memory()         # the caller's O buffer, pinned as well
+        On = Op.numpy().reshape(D.shape, order="F")
         e2e_opts = dict(opts, maxIter=K, tol=0.0, disp=0)
         tritd.triple_decomp_ADMM(Dn, r, dict(e2e_opts, maxIter=3), A0, B0, C0, ctx=ctx)       # warm-up call
         barrier()
         tw = time.perf_counter()
-        A, B, C, O, eh, info = tritd.triple_decomp_ADMM(Dn, r, e2e_opts, A0, B0, C0, ctx=ctx, return_info=True)
+        A, B, C, O, eh, info = tritd.triple_decomp_ADMM(Dn, r, e2e_opts, A0, B0, C0, ctx=ctx, return_info=True, out_O=On)
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - tw)
         assert len(eh) == K
         h2d = (D.nbytes + A0.nbytes + B0.nbytes + C0.nbytes) / K
         d2h = (O.nbytes + A.nbytes + B.nbytes + C.nbytes + eh.nbytes) / K
         e2e = {"value": K / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "call": "tritd_admm_f64 (one call, pinned host D; alloc + H2D + K iterations + D2H of A,B,C,O,errHist)",
+               "call": "tritd_admm_f64 (one call, pinned host D and O; alloc + H2D + K iterations + D2H of A,B,C,O,errHist)",
                "seconds": dt, "h2d_ms": info["h2d_ms"], "iterate_ms": info["iterate_ms"], "d2h_ms": info["d2h_ms"]}
         # time-to-tolerance with the reference's own options (tol 1e-5, maxIter 100)
         barrier()
         tw = time.perf_counter()
-        out = tritd.triple_decomp_ADMM(Dn, r, dict(opts, disp=0), A0, B0, C0, ctx=ctx, return_info=True)
+        out = tritd.triple_decomp_ADMM(Dn, r, dict(opts, disp=0), A0, B0, C0, ctx=ctx, return_info=True, out_O=On)
         torch.cuda.synchronize()
         dt2 = max_over_ranks(time.perf_counter() - tw)
         ttt = {"seconds_host_buffers": dt2, "seconds_device_loop": out[5]["iterate_ms"] * 1e-3, "iterations": len(out[4]),

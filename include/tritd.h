@@ -119,6 +119,11 @@ int tritd_admm_f64(tritd_ctx* ctx, const double* D_host, int64_t n1, int64_t n2,
                    double* A, double* B, double* C, double* O, double* L_or_null,
                    double* errHist, int32_t* iters_out, tritd_timing* timing_or_null);
 
+/* tritd_admm_f64 keeps its device state (the N-sized arrays, tensor maps, the captured iteration graph) in the
+ * context and reuses it when the next call has the same shape and rank; tritd_trim() releases it (tritd_destroy()
+ * does so too). */
+int tritd_trim(tritd_ctx* ctx);
+
 /* ---- the solver, staged (device-resident state; used by benchmarks and by
  *      callers that keep L/O on the GPU) ------------------------------------ */
 

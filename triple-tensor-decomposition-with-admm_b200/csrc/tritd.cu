@@ -109,6 +109,7 @@ struct tritd_ctx {
     int num_sms = 0;
     int64_t launches = 0;
     PFN_encodeTiled encode = nullptr;
+    tritd_problem* cached = nullptr;     // device state of the last tritd_admm_f64 call, reused when the shape repeats
 };
 
 struct RankCfg { int NT, KS; };
@@ -187,9 +188,18 @@ extern "C" int tritd_create_rank(int device, int rank, int nranks, const void* n
     return TRITD_OK;
 }
 
+extern "C" void tritd_problem_destroy(tritd_problem* p);
+
+extern "C" int tritd_trim(tritd_ctx* c) {
+    if (!c) return fail(TRITD_ERR_INVALID, "ctx is NULL");
+    if (c->cached) { tritd_problem_destroy(c->cached); c->cached = nullptr; }
+    return TRITD_OK;
+}
+
 extern "C" void tritd_destroy(tritd_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    tritd_trim(c);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -255,6 +265,9 @@ struct tritd_problem {
     int hist_cap = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;    // TRITD_NPHASE + 1 events per profiled iteration
+    cudaGraphExec_t graph = nullptr;     // one steady-state iteration, captured once and replayed
+    int graph_launches = 0;              // kernels inside the graph
+    bool graph_off = false;              // capture failed or TRITD_NO_GRAPH set: plain launches
     std::vector<void*> allocs;
 };
 
@@ -405,6 +418,7 @@ extern "C" void tritd_problem_destroy(tritd_problem* p) {
     cudaStreamSynchronize(p->ctx->stream);
     for (void* q : p->allocs) cudaFree(q);
     for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
+    if (p->graph) cudaGraphExecDestroy(p->graph);
     if (p->st_host) cudaFreeHost(p->st_host);
     delete p;
 }
@@ -683,6 +697,8 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
     CU_TRY(cudaStreamSynchronize(st));
     p->initialized = true;
     p->rhsA_ready = false;
+    p->graph_off = getenv("TRITD_NO_GRAPH") != nullptr;
+    if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }     // opts (lambda2) are baked into the graph
     p->printed_k = 0;
     return TRITD_OK;
 }
@@ -754,6 +770,38 @@ extern "C" int tritd_debug_stamps(tritd_problem* p, long long* out8) {
     return TRITD_OK;
 }
 
+// One iteration: the first one (and profiled ones) as plain launches, every later one as a replay of a CUDA graph
+// captured from the very same enqueue_iteration() -- all iteration state lives in device memory, so the graph
+// needs no parameter updates -- which removes the launch gaps between the ~9 small dependent kernels.
+static int run_iteration(tritd_problem* p) {
+    tritd_ctx* c = p->ctx;
+    if (p->profiling || !p->rhsA_ready || p->graph_off) return enqueue_iteration(p);
+    if (!p->graph) {
+        const int64_t l0 = c->launches;
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            p->graph_off = true;
+            return enqueue_iteration(p);
+        }
+        const int s = enqueue_iteration(p);
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        p->graph_launches = (int)(c->launches - l0);
+        c->launches = l0;
+        if (s != TRITD_OK || e != cudaSuccess || !g || cudaGraphInstantiate(&p->graph, g, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            p->graph = nullptr;
+            p->graph_off = true;
+            return enqueue_iteration(p);
+        }
+        cudaGraphDestroy(g);
+    }
+    CU_TRY(cudaGraphLaunch(p->graph, c->stream));
+    c->launches += p->graph_launches;
+    return TRITD_OK;
+}
+
 extern "C" int tritd_problem_set_profiling(tritd_problem* p, int enable) {
     if (!p) return fail(TRITD_ERR_INVALID, "NULL problem");
     p->profiling = enable != 0;
@@ -790,7 +838,7 @@ static int fetch_state(tritd_problem* p) {
 extern "C" int tritd_problem_enqueue(tritd_problem* p, int32_t n) {
     if (!p || !p->initialized) return fail(TRITD_ERR_INVALID, "problem not initialised");
     CU_TRY(cudaSetDevice(p->ctx->device));
-    for (int i = 0; i < n; ++i) ST_TRY(enqueue_iteration(p));
+    for (int i = 0; i < n; ++i) ST_TRY(run_iteration(p));
     return TRITD_OK;
 }
 
@@ -822,7 +870,7 @@ extern "C" int tritd_problem_iterate(tritd_problem* p, int32_t max_more, int32_t
     // (the cadence of the reference's progress line), later launches of a stopped solve are no-ops
     while (remaining > 0 && !p->st_host->stop) {
         const int batch = std::min(remaining, 10 - p->st_host->k % 10);
-        for (int i = 0; i < batch; ++i) ST_TRY(enqueue_iteration(p));
+        for (int i = 0; i < batch; ++i) ST_TRY(run_iteration(p));
         ST_TRY(fetch_state(p));
         ST_TRY(print_progress(p));
         remaining -= batch;
@@ -911,12 +959,19 @@ extern "C" int tritd_admm_f64(tritd_ctx* c, const double* D_host, int64_t n1, in
     if (!c || !D_host || !o || !A0 || !B0 || !C0 || !errHist) return fail(TRITD_ERR_INVALID, "NULL argument");
     const double t_begin = now_ms();
     const int64_t launches0 = c->launches;
-    tritd_problem* p = nullptr;
-    ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
+    // device state (6 N-sized arrays, tensor maps, the captured iteration graph) is kept in the context and
+    // reused when the next call has the same shape and rank -- a MATLAB session typically calls the solver
+    // repeatedly on equally sized data; tritd_trim() / tritd_destroy() release it
+    tritd_problem* p = c->cached;
+    if (p && !(p->n1 == n1 && p->n2 == n2 && p->n3 == n3 && p->r == r)) { tritd_trim(c); p = nullptr; }
+    if (!p) {
+        ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
+        c->cached = p;
+    }
     int s;
     double t0 = now_ms();
-    if ((s = tritd_problem_set_D_host(p, D_host)) != TRITD_OK) { tritd_problem_destroy(p); return s; }
-    if ((s = tritd_problem_init(p, o, A0, B0, C0)) != TRITD_OK) { tritd_problem_destroy(p); return s; }
+    if ((s = tritd_problem_set_D_host(p, D_host)) != TRITD_OK) { tritd_trim(c); return s; }
+    if ((s = tritd_problem_init(p, o, A0, B0, C0)) != TRITD_OK) { tritd_trim(c); return s; }
     const double t_h2d = now_ms() - t0;
 
     cudaEvent_t e0, e1;
@@ -929,13 +984,12 @@ extern "C" int tritd_admm_f64(tritd_ctx* c, const double* D_host, int64_t n1, in
     float it_ms = 0.f;
     cudaEventElapsedTime(&it_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (s != TRITD_OK) { tritd_problem_destroy(p); return s; }
+    if (s != TRITD_OK) { tritd_trim(c); return s; }
 
     t0 = now_ms();
     s = tritd_problem_get(p, A, B, C, O, L, errHist, nullptr, nullptr, &k);
     const double t_d2h = now_ms() - t0;
-    tritd_problem_destroy(p);
-    if (s != TRITD_OK) return s;
+    if (s != TRITD_OK) { tritd_trim(c); return s; }
     if (iters_out) *iters_out = k;
     if (tm) {
         tm->h2d_ms = t_h2d; tm->iterate_ms = it_ms; tm->d2h_ms = t_d2h; tm->total_ms = now_ms() - t_begin;

@@ -66,6 +66,7 @@ SYMBOLS = {
     "tritd_slab_bounds": (C.c_int, [_i64, C.c_int, C.c_int, C.POINTER(_i64), C.POINTER(_i64)]),
     "tritd_admm_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int, C.POINTER(tritd_opts), _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), C.POINTER(tritd_timing)]),
+    "tritd_trim": (C.c_int, [_vp]),
     "tritd_problem_create": (C.c_int, [_vp, _i64, _i64, _i64, C.c_int, C.POINTER(_vp)]),
     "tritd_problem_destroy": (None, [_vp]),
     "tritd_problem_set_D_host": (C.c_int, [_vp, _vp]),
@@ -164,6 +165,10 @@ class Context:
     @property
     def launches(self) -> int:
         return int(load_library().tritd_launch_count(self._h))
+
+    def trim(self):
+        """Release the device state tritd_admm_f64 caches between equally shaped calls."""
+        _check(load_library().tritd_trim(self._h))
 
     def close(self):
         if self._h:
@@ -276,13 +281,15 @@ class Problem:
 # --------------------------------------------------------------------------
 # the reference's functions
 # --------------------------------------------------------------------------
-def triple_decomp_ADMM(D, r, opts, A0=None, B0=None, C0=None, rng=None, ctx=None, return_info=False, want_L=False):
+def triple_decomp_ADMM(D, r, opts, A0=None, B0=None, C0=None, rng=None, ctx=None, return_info=False, want_L=False,
+                       out_O=None):
     """[A,B,C,O,errHist] = triple_decomp_ADMM(D, r, opts)   (triple_decomp_ADMM.m:1-70).
 
     The reference draws A,B,C with randn at :23 (order A, B, C).  Here the same
     order is drawn from ``rng`` (numpy Generator; default_rng(0) if omitted)
     unless ``A0,B0,C0`` (or ``opts['A0']`` ...) inject them -- the library itself
-    never draws random numbers."""
+    never draws random numbers.  ``out_O`` may be a preallocated Fortran-ordered float64 array (e.g. a view of pinned
+    memory) to receive O."""
     D = np.asarray(D)
     if D.ndim == 2:                       # MATLAB hands an n1 x n2 x 1 tensor over as 2-D
         D = D[:, :, None]
@@ -303,7 +310,12 @@ def triple_decomp_ADMM(D, r, opts, A0=None, B0=None, C0=None, rng=None, ctx=None
     A0 = _f64(A0, (n1, r, r)); B0 = _f64(B0, (r, n2, r)); C0 = _f64(C0, (r, r, n3))
     ctx = ctx or default_context()
     A = np.zeros((n1, r, r), order="F"); B = np.zeros((r, n2, r), order="F"); Cc = np.zeros((r, r, n3), order="F")
-    O = np.zeros((n1, n2, n3), order="F")
+    if out_O is not None:
+        if out_O.shape != (n1, n2, n3) or out_O.dtype != np.float64 or not out_O.flags.f_contiguous:
+            raise ValueError("out_O must be a Fortran-ordered float64 array of D's shape")
+        O = out_O
+    else:
+        O = np.zeros((n1, n2, n3), order="F")
     L = np.zeros((n1, n2, n3), order="F") if want_L else None
     errHist = np.zeros(o.maxIter)
     k = C.c_int32()
