@@ -6,15 +6,15 @@ import numpy as np
 import tritd
 from tritd import synth
 
-def run(n1, n2, n3, r, iters=30):
+def run(n1, n2, n3, r, iters=100):
     rng = np.random.default_rng(0)
     D = np.asfortranarray(rng.standard_normal((n1, n2, n3)))
     A0, B0, C0 = synth.init_factors(n1, n2, n3, r, 1)
     ctx = tritd.default_context()
     with tritd.Problem(ctx, n1, n2, n3, r) as p:
         p.set_D(D)
-        p.init(dict(synth.VIDEO_OPTS, maxIter=iters + 10, tol=0.0), A0, B0, C0)
-        p.enqueue(5); p.sync()
+        p.init(dict(synth.VIDEO_OPTS, maxIter=iters + 2100, tol=0.0), A0, B0, C0)
+        p.enqueue(2000 if n1 * n2 * n3 < 5e7 else 300); p.sync()      # long warm-up: SM clocks ramp up slowly
         p.set_profiling(True)
         p.enqueue(iters)
         ms, n = p.phase_ms()

@@ -28,8 +28,12 @@ struct AdmmMaps { CUtensorMap D, YL, E, YO, T, O; };
 
 struct AdmmArgs {
     const double *A1, *B2, *C3;        // [n][RS]
-    const IterState* st;
+    IterState* st;
     double* norm_part;                 // [grid][2]
+    double* norms;                     // [2]: fixed-order sum of norm_part (left for the all-reduce when !finalize)
+    double *errHist, *errL, *errO;     // history (written by the last CTA when finalize)
+    unsigned* ticket;                  // CTA completion counter (zero between launches)
+    int finalize;                      // 1: the last CTA also runs the errHist / mu / stopping-rule step (:56-65)
     double* partM;                     // [grid][128][RS]: this CTA's partial of the next X1*F'
     const int* cta_tab;                // [grid][3]: i-tile, index within the tile's CTAs, CTAs of that tile
     int n1, n2, n3, RS;
@@ -326,10 +330,27 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
       }
     }
     __syncthreads();
+    __shared__ int s_last;
     if (threadIdx.x == 0) {
         double sl = 0.0, so = 0.0;
         for (int w = 0; w < 8; ++w) { sl += red[w]; so += red[8 + w]; }
         a.norm_part[2 * blockIdx.x] = sl; a.norm_part[2 * blockIdx.x + 1] = so;
+        __threadfence();
+        s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // Last CTA to finish (every CTA has read the iteration scalars long ago): fixed-order sum of the per-CTA
+    // residual sums, then -- single rank -- the scalar step of the iteration; with several ranks the pair is
+    // left in norms[] for the all-reduce and k_finalize does the scalar step.
+    __threadfence();
+    double sa = 0.0, sb = 0.0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += kAdmmThreads) { sa += __ldcg(a.norm_part + 2 * i); sb += __ldcg(a.norm_part + 2 * i + 1); }
+    block_sum2(sa, sb, red);
+    if (threadIdx.x == 0) {
+        *a.ticket = 0u;
+        if (a.finalize) iter_finalize(a.st, sa, sb, a.errHist, a.errL, a.errO);
+        else { a.norms[0] = sa; a.norms[1] = sb; }
     }
 }
 

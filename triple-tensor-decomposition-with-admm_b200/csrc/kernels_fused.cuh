@@ -197,6 +197,21 @@ __global__ void __launch_bounds__(256) k_sumsq_part(const double* x, size_t n, d
     if (threadIdx.x == 0) { part[2 * blockIdx.x] = s; part[2 * blockIdx.x + 1] = 0.0; }
 }
 
+// The scalar step that ends an iteration (triple_decomp_ADMM.m:56-65): mu schedule BEFORE errHist, the
+// relative-change stopping rule, maxIter.  a, b = sum(resL.^2), sum(resO.^2) over the whole tensor.
+__device__ __forceinline__ void iter_finalize(IterState* st, double a, double b, double* errHist, double* errL, double* errO) {
+    const int k = st->k;
+    st->muL = fmin(st->muL * st->rhoL, st->muL_max);
+    st->muO = fmin(st->muO * st->rhoO, st->muO_max);
+    iter_state_derive(*st);
+    const double eL = sqrt(a) / st->normD, eO = sqrt(b) / st->normD;
+    errL[k] = eL; errO[k] = eO; errHist[k] = eL + eO;
+    st->k = k + 1;
+    if (k >= 1 && fabs(errHist[k] - errHist[k - 1]) < st->tol * errHist[k - 1]) st->stop = 1;
+    if (k + 1 >= st->maxIter) st->stop = 1;
+    if (st->status != 0) st->stop = 1;     // a factor update reported a bad pivot: later launches become no-ops
+}
+
 // errHist / mu schedule / stopping rule (triple_decomp_ADMM.m:56-65).  One CTA: first the fixed-order
 // sum of the per-CTA partials of sum(resL^2), sum(resO^2) (npart pairs; with `reduced` set the pair
 // in norms[] was already summed -- and all-reduced over the ranks), then one thread does the scalars.
@@ -211,15 +226,7 @@ __global__ void __launch_bounds__(256) k_finalize(IterState* st, const double* p
     }
     if (threadIdx.x != 0) return;
     if (reduced) { a = norms[0]; b = norms[1]; }
-    const int k = st->k;
-    st->muL = fmin(st->muL * st->rhoL, st->muL_max);
-    st->muO = fmin(st->muO * st->rhoO, st->muO_max);
-    iter_state_derive(*st);
-    const double eL = sqrt(a) / st->normD, eO = sqrt(b) / st->normD;
-    errL[k] = eL; errO[k] = eO; errHist[k] = eL + eO;
-    st->k = k + 1;
-    if (k >= 1 && fabs(errHist[k] - errHist[k - 1]) < st->tol * errHist[k - 1]) st->stop = 1;
-    if (k + 1 >= st->maxIter) st->stop = 1;
+    iter_finalize(st, a, b, errHist, errL, errO);
 }
 
 // O of the last finished iteration, recovered from the state the iteration keeps:

@@ -22,7 +22,7 @@
 #include "kernels_aux.cuh"
 #include "kernels_contract.cuh"
 #include "kernels_fused.cuh"
-#include "kernels_solve.cuh"
+#include "kernels_update.cuh"
 
 using namespace tritd;
 
@@ -243,9 +243,9 @@ struct tritd_problem {
     double *bufA = nullptr;              // [rhsA (n1*RS) ; SC (RS*RS)] -- one all-reduce
     double *rhsB = nullptr, *rhsC = nullptr, *P = nullptr, *partM = nullptr;
     double *norm_part = nullptr, *norms = nullptr;
-    double* gram_part = nullptr;         // per-CTA partial small Grams of k_solve
-    unsigned* ticket = nullptr;
-    long long* dbg = nullptr;            // optional clock64 stamps of k_solve (TRITD_DEBUG_STAMPS=1)
+    double* Minv = nullptr;              // [3][RS][RS] inverses of the three ridge systems (written by k_upd's block 0)
+    long long* dbg = nullptr;            // optional globaltimer stamps of k_upd (TRITD_DEBUG_STAMPS=1)
+    unsigned* flags = nullptr;           // [3][4] k_upd hand-shake words (A, B, C) + [12] the k_admm completion ticket
     int *tile0 = nullptr, *tile1 = nullptr;   // first / last i-tile of each k_mttkrp1 CTA
     IterState* st = nullptr;
     double *errHist = nullptr, *errL = nullptr, *errO = nullptr;
@@ -363,6 +363,8 @@ static int launch_admm(tritd_problem* p) {
     tritd_ctx* c = p->ctx;
     AdmmArgs a;
     a.A1 = p->A1; a.B2 = p->B2; a.C3 = p->C3; a.st = p->st; a.norm_part = p->norm_part; a.partM = p->partF;
+    a.norms = p->norms; a.errHist = p->errHist; a.errL = p->errL; a.errO = p->errO;
+    a.ticket = p->flags + 12; a.finalize = c->nranks == 1 ? 1 : 0;
     a.cta_tab = p->ctaTab;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc; a.tile_h = p->tileH;
 #define CALL(NT_, KS_) \
@@ -374,31 +376,39 @@ static int launch_admm(tritd_problem* p) {
     return TRITD_OK;
 }
 
-static int launch_reduce_fused_rhsA(tritd_problem* p, double* rhs_out) {
-    tritd_ctx* c = p->ctx;
-    const long tot = (long)p->n1 * p->RS;
-    k_mttkrp1_reduce<<<(unsigned)((tot + 31) / 32), 256, 0, c->stream>>>(p->partF, (size_t)128 * p->RS, p->tileH, rhs_out, p->n1, p->RS,
-                                                                       p->tileF, p->tileF, p->gridA, &p->st->stop);
-    CU_TRY(cudaGetLastError());
-    c->launches += 1;
-    return TRITD_OK;
-}
+// One factor update (k_upd): RHS rows from `src`, X = RHS * inv(S1 o S2 + alpha I), S_out = X'X, optionally X
+// transposed.  which = 0/1/2 (A/B/C) selects the scratch inverse and the hand-shake flags.  apply == false: only
+// reduce the RHS rows into rhs_out (the all-reduce comes next).
+constexpr int kGramSlices = 8;     // SA / SB / SC are stacks of up to 8 row-slice partial Grams
+static int gram_slices(int n, bool single_matrix) { return single_matrix ? 1 : std::max(1, std::min(kGramSlices, (n + 63) / 64)); }
 
-static size_t smem_solve(int R) {
-    const int P = R | 1;
-    return (size_t)(R * P + 256 + 2 * kSolveRows * P) * sizeof(double);
-}
-
-// X = rhs * inv(S1 o S2 + alpha I); also S_out = X'X (rows of this rank) and optionally X transposed.
-static int launch_solve(tritd_problem* p, const double* rhs, const double* S1, const double* S2, double alpha, double* X,
-                        double* XT, int n, double* S_out) {
+static int launch_upd(tritd_problem* p, int which, int src, bool apply, const double* rhs_direct, double* rhs_out,
+                      const double* S1, int ns1, const double* S2, int ns2, double alpha, double* X, double* XT, int n,
+                      double* S_out, int gr) {
     tritd_ctx* c = p->ctx;
-    SolveArgs a;
-    a.rhs = rhs; a.S1 = S1; a.S2 = S2; a.alpha = alpha; a.X = X; a.XT = XT; a.st = p->st;
-    a.gram_part = p->gram_part; a.gram_out = S_out; a.ticket = p->ticket; a.dbg = p->dbg;
+    UpdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rhs = rhs_direct;
+    a.part = p->partF; a.part_count = p->gridA / p->nitA; a.nit = p->nitA; a.tile_h = p->tileH;
+    a.P = p->P; a.W = src == kSrcPB ? p->C3 : p->B2; a.n2 = p->n2; a.n3 = p->n3;
+    a.S1 = S1; a.S2 = S2; a.ns1 = ns1; a.ns2 = ns2; a.alpha = alpha; a.gr = gr;
+    a.Minv = p->Minv + (size_t)which * p->RS * p->RS;
+    a.rhs_out = rhs_out; a.X = X; a.XT = XT; a.gram_out = S_out;
+    a.st = p->st; a.flags = p->flags + 4 * which; a.apply = apply ? 1 : 0;
     a.n = n; a.R = p->R; a.RS = p->RS; a.ldt = p->ldt;
-    if (p->R <= 32) k_solve<1><<<(n + kSolveRows - 1) / kSolveRows, kSolveThreads, smem_solve(p->R), c->stream>>>(a);
-    else k_solve<2><<<(n + kSolveRows - 1) / kSolveRows, kSolveThreads, smem_solve(p->R), c->stream>>>(a);
+    a.dbg = p->dbg ? p->dbg + 16 * which : nullptr;
+    const size_t sm = upd_smem_bytes(p->RS);
+#define UPD_LAUNCH(SRC_, WPR_, GRID_)                                                                  \
+    if (p->RS <= 32) k_upd<SRC_, WPR_, 1><<<(GRID_), kUpdThreads, sm, c->stream>>>(a);                  \
+    else k_upd<SRC_, WPR_, 2><<<(GRID_), kUpdThreads, sm, c->stream>>>(a);
+    switch (src) {
+        case kSrcDirect: UPD_LAUNCH(kSrcDirect, 1, (n + 7) / 8 + 1) break;
+        case kSrcPartF: UPD_LAUNCH(kSrcPartF, 1, (n + 7) / 8 + 1) break;
+        case kSrcPB: UPD_LAUNCH(kSrcPB, 4, (n + 1) / 2 + 1) break;
+        case kSrcPC: UPD_LAUNCH(kSrcPC, 4, (n + 1) / 2 + 1) break;
+        default: return fail(TRITD_ERR_INVALID, "bad update source");
+    }
+#undef UPD_LAUNCH
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     return TRITD_OK;
@@ -449,8 +459,8 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     PALLOC(D, p->Np); PALLOC(E, p->Np); PALLOC(YL, p->Np); PALLOC(YO, p->Np); PALLOC(T, p->Np); PALLOC(O, p->Np);
     PALLOC(A1, (size_t)p->n1 * p->RS); PALLOC(B2, (size_t)p->n2 * p->RS); PALLOC(C3, (size_t)p->n3 * p->RS);
     PALLOC(A1T, (size_t)p->RS * p->ldt);
-    PALLOC(SA, (size_t)p->RS * p->RS); PALLOC(SB, (size_t)p->RS * p->RS);
-    PALLOC(bufA, (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS);
+    PALLOC(SA, (size_t)kGramSlices * p->RS * p->RS); PALLOC(SB, (size_t)kGramSlices * p->RS * p->RS);
+    PALLOC(bufA, (size_t)p->n1 * p->RS + (size_t)kGramSlices * p->RS * p->RS);
     PALLOC(rhsB, (size_t)p->n2 * p->RS); PALLOC(rhsC, (size_t)p->n3 * p->RS);
     PALLOC(P, (size_t)p->n3 * p->n2 * p->RS);
 
@@ -475,9 +485,10 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     PALLOC(partM, (size_t)p->gridM * 2 * 128 * p->RS);
     {
         const int nmax = std::max(p->n1, std::max(p->n2, p->n3));
-        PALLOC(gram_part, (size_t)((nmax + kSolveRows - 1) / kSolveRows) * p->R * p->R);
-        PALLOC(ticket, 4);
-        if (getenv("TRITD_DEBUG_STAMPS")) { PALLOC(dbg, 16); cudaMemset(p->dbg, 0, 128); }
+        (void)nmax;
+        PALLOC(Minv, (size_t)3 * p->RS * p->RS);
+        PALLOC(flags, 16);
+        if (getenv("TRITD_DEBUG_STAMPS")) { PALLOC(dbg, 48); cudaMemset(p->dbg, 0, 48 * 8); }
         PALLOC(tile0, p->gridM); PALLOC(tile1, p->gridM);
         std::vector<int> t0(p->gridM), t1(p->gridM);
         const long per_it = (long)p->n_jc * p->n3;
@@ -488,7 +499,7 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         }
         cudaMemcpy(p->tile0, t0.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
         cudaMemcpy(p->tile1, t1.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
-        cudaMemset(p->ticket, 0, 16);
+        cudaMemset(p->flags, 0, 64);
         // k_admm: one CTA per SM.  The i-tiles are as even as 16-row warp strips allow (240 rows -> 128 + 112,
         // 130 rows -> 80 + 50) and every tile gets the same number of CTAs: a stage costs the same whether
         // 7 or 8 warps work on it, so equal stage counts finish together.
@@ -529,7 +540,6 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
                                 (int)AdmmCfg<KS_, NT_, false>::kSmem));
             TRITD_DISPATCH_R(r, CALL)
 #undef CALL
-            CU_TRY(cudaFuncSetAttribute(k_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(TRITD_MAX_R * TRITD_MAX_R)));
             return TRITD_OK;
         };
         if ((s = q()) != TRITD_OK) return bail(s);
@@ -672,6 +682,7 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
     iter_state_derive(h);
     *p->st_host = h;
     CU_TRY(cudaMemcpyAsync(p->st, p->st_host, sizeof(IterState), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(p->flags, 0, 64, st));
 
     // history buffers sized by maxIter
     if (o->maxIter > p->hist_cap) {
@@ -691,7 +702,9 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
     k_set_normD<<<1, 32, 0, st>>>(p->st, p->norms);
     c->launches += 3;
 
-    // small Grams of the initial factors: SB = B2'B2, SC (partial over local rows) = C3'C3
+    // small Grams of the initial factors: SB = B2'B2, SC (partial over local rows) = C3'C3 -- slice 0 of their stacks
+    CU_TRY(cudaMemsetAsync(p->SB, 0, (size_t)kGramSlices * p->RS * p->RS * 8, st));
+    CU_TRY(cudaMemsetAsync(p->bufA + (size_t)p->n1 * p->RS, 0, (size_t)kGramSlices * p->RS * p->RS * 8, st));
     ST_TRY(launch_small_gram(p, p->B2, p->n2, p->SB));
     ST_TRY(launch_small_gram(p, p->C3, p->n3, p->bufA + (size_t)p->n1 * p->RS));
     CU_TRY(cudaStreamSynchronize(st));
@@ -709,7 +722,6 @@ static int enqueue_iteration(tritd_problem* p) {
     cudaStream_t st = c->stream;
     double* rhsA = p->bufA;
     double* SC = p->bufA + (size_t)p->n1 * p->RS;
-    const int* stop = &p->st->stop;
     auto mark = [&]() -> int {           // phase boundary (only when profiling)
         if (!p->profiling) return TRITD_OK;
         cudaEvent_t e;
@@ -720,53 +732,54 @@ static int enqueue_iteration(tritd_problem* p) {
     };
     ST_TRY(mark());
 
-    // update_A (:73-81): RHS = X1*F', Gram = (B2'B2) o (C3'C3) + lambda2*I
-    // (from the second iteration on the previous k_admm already accumulated it from registers)
-    if (p->rhsA_ready) ST_TRY(launch_reduce_fused_rhsA(p, rhsA));
-    else ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, rhsA));
+    const bool multi = c->nranks > 1;
+    // SA, SB, SC are stacks of row-slice partial Grams (one matrix for SC when it has to be all-reduced)
+    const int gA = gram_slices(p->n1, false), gB = gram_slices(p->n2, false), gC = gram_slices(p->n3, multi);
+    // update_A (:73-81): RHS = X1*F', Gram = (B2'B2) o (C3'C3) + lambda2*I.  From the second iteration on the
+    // previous k_admm left per-CTA partials of X1*F' (accumulated from registers); single rank: k_upd sums them,
+    // applies the inverse and forms A1'A1 in one launch.
+    const bool direct_A = !p->rhsA_ready || multi;
+    if (!p->rhsA_ready) ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, rhsA));
+    else if (multi) ST_TRY(launch_upd(p, 0, kSrcPartF, false, nullptr, rhsA, nullptr, 0, nullptr, 0, 0.0, nullptr, nullptr, p->n1, nullptr, 1));
     ST_TRY(mark());
     ST_TRY(allreduce_sum(c, p->bufA, (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS));
-    ST_TRY(launch_solve(p, rhsA, p->SB, SC, p->opts.lambda2, p->A1, p->A1T, p->n1, p->SA));
+    ST_TRY(launch_upd(p, 0, direct_A ? kSrcDirect : kSrcPartF, true, rhsA, nullptr, p->SB, gB, SC, gC, p->opts.lambda2, p->A1, p->A1T,
+                      p->n1, p->SA, gA));
     ST_TRY(mark());
 
-    // update_B (:83-88) with the new A: RHS = X2*G', Gram = (A1'A1) o (C3'C3) + lambda2*I
+    // update_B (:83-88) with the new A: RHS = X2*G' = sum_t C3(t,:) .* P(t,j,:), Gram = (A1'A1) o (C3'C3) + lambda2*I
     ST_TRY(launch_ppass(p, p->mapT));
     ST_TRY(mark());
-    k_rhsB<<<p->n2, 256, 0, st>>>(p->P, p->C3, p->rhsB, p->n2, p->n3, p->RS, stop);
-    CU_TRY(cudaGetLastError());
-    c->launches += 1;
-    ST_TRY(allreduce_sum(c, p->rhsB, (size_t)p->n2 * p->RS));
-    ST_TRY(launch_solve(p, p->rhsB, p->SA, SC, p->opts.lambda2, p->B2, nullptr, p->n2, p->SB));
+    if (multi) {
+        ST_TRY(launch_upd(p, 1, kSrcPB, false, nullptr, p->rhsB, nullptr, 0, nullptr, 0, 0.0, nullptr, nullptr, p->n2, nullptr, 1));
+        ST_TRY(allreduce_sum(c, p->rhsB, (size_t)p->n2 * p->RS));
+    }
+    ST_TRY(launch_upd(p, 1, multi ? kSrcDirect : kSrcPB, true, p->rhsB, nullptr, p->SA, gA, SC, gC, p->opts.lambda2, p->B2, nullptr,
+                      p->n2, p->SB, gB));
 
-    // update_C (:90-95) with the new A, B: slice-local; ridge fixed at 1e-9
-    k_rhsC<<<p->n3, 256, 0, st>>>(p->P, p->B2, p->rhsC, p->n2, p->n3, p->RS, stop);
-    CU_TRY(cudaGetLastError());
-    c->launches += 1;
-    // also leaves SC = C3'C3 over the local slices in bufA, where the next all-reduce sums it over ranks
-    ST_TRY(launch_solve(p, p->rhsC, p->SA, p->SB, 1e-9, p->C3, nullptr, p->n3, SC));
+    // update_C (:90-95) with the new A, B: slice-local; ridge fixed at 1e-9.  Leaves SC = C3'C3 over the local
+    // slices in bufA, where the next all-reduce sums it over the ranks.
+    ST_TRY(launch_upd(p, 2, kSrcPC, true, nullptr, nullptr, p->SA, gA, p->SB, gB, 1e-9, p->C3, nullptr, p->n3, SC, gC));
 
     ST_TRY(mark());
-    // L, O, E, duals, next T, residual norms (:38-59, :33)
+    // L, O, E, duals, next T, residual norms (:38-59, :33); single rank: its last CTA also does :56-65
     ST_TRY(launch_admm(p));
     p->rhsA_ready = true;
     ST_TRY(mark());
-    if (c->nranks > 1) {
-        k_sum_pairs<<<1, 256, 0, st>>>(p->norm_part, p->gridA, p->norms, stop);
+    if (multi) {
+        ST_TRY(allreduce_sum(c, p->norms, 2));
+        k_finalize<<<1, 256, 0, st>>>(p->st, p->norm_part, p->gridA, p->norms, 1, p->errHist, p->errL, p->errO);
         CU_TRY(cudaGetLastError());
         c->launches += 1;
-        ST_TRY(allreduce_sum(c, p->norms, 2));
     }
-    k_finalize<<<1, 256, 0, st>>>(p->st, p->norm_part, p->gridA, p->norms, c->nranks > 1 ? 1 : 0, p->errHist, p->errL, p->errO);
-    CU_TRY(cudaGetLastError());
-    c->launches += 1;
     ST_TRY(mark());
     return TRITD_OK;
 }
 
-// diagnostics: the clock64 stamps k_solve leaves when TRITD_DEBUG_STAMPS is set (not part of the public header)
-extern "C" int tritd_debug_stamps(tritd_problem* p, long long* out8) {
+// diagnostics: the globaltimer stamps k_upd leaves when TRITD_DEBUG_STAMPS is set (not part of the public header)
+extern "C" int tritd_debug_stamps(tritd_problem* p, long long* out48) {
     if (!p || !p->dbg) return fail(TRITD_ERR_INVALID, "no debug stamps");
-    CU_TRY(cudaMemcpy(out8, p->dbg, 64, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(out48, p->dbg, 48 * 8, cudaMemcpyDeviceToHost));
     return TRITD_OK;
 }
 
