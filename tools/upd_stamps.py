@@ -21,5 +21,5 @@ for (n1, n2, n3, r) in shapes:
         for w, nm in enumerate("ABC"):
             s = list(out)[16 * w:16 * w + 16]
             b = s[0]
-            print((n1, n2, n3, r), nm, "ns since block0 start: inv_done=%d gram_wait_done=%d chunk_loaded=%d computed=%d end=%d | block1: start=%d reduced=%d inv_seen=%d Ms_loaded=%d applied=%d XT_written=%d rows_done=%d" % (
-                s[1] - b, s[2] - b, s[11] - b, s[12] - b, s[3] - b, s[4] - b, s[5] - b, s[6] - b, s[8] - b, s[9] - b, s[10] - b, s[7] - b))
+            print((n1, n2, n3, r), nm, "ns since block0 start: inv_init=%d inv_done=%d gram_wait_done=%d chunk_loaded=%d computed=%d end=%d | block1: start=%d reduced=%d inv_seen=%d Ms_loaded=%d applied=%d XT_written=%d rows_done=%d" % (
+                s[13] - b, s[1] - b, s[2] - b, s[11] - b, s[12] - b, s[3] - b, s[4] - b, s[5] - b, s[6] - b, s[8] - b, s[9] - b, s[10] - b, s[7] - b))

@@ -7,7 +7,7 @@
 //   block 0      inverts the R x R ridge system (in-place Gauss-Jordan, SPD => no pivoting, the pivots are the
 //                Cholesky pivots L_kk^2; a non-positive / non-finite pivot is reported through IterState::status)
 //                WHILE the row CTAs reduce their RHS rows, publishes inv(G) and raises flags[0];
-//   blocks 1..   8/WPR rows each: fixed-order reduction of the RHS rows from the source, wait for flags[0],
+//   blocks 1..   8/wpr rows each: fixed-order reduction of the RHS rows from the source, wait for flags[0],
 //                apply the inverse like the reference applies pinv(G), write X (and its transpose for TMA);
 //   blocks 0..G-1 finally form S = X'X straight from the freshly written rows once every row CTA has
 //                signalled flags[1] (one entry per thread, rows summed in a fixed order => deterministic).
@@ -15,11 +15,6 @@
 // partial-Gram buffers exist.  Row CTAs wait only for block 0 (scheduled first, waits for nobody); the Gram
 // phase waits for the row CTAs, which never wait for it: no cyclic dependency, at most G CTAs spin.
 //
-// RHS sources:
-//   kSrcDirect  rhs[row][k] as given (first iteration; N>1 after the all-reduce)
-//   kSrcPartF   sum over the k_admm CTAs of the row's i-tile of their mode-1 partials (update_A)
-//   kSrcPB      sum_t C3[t][k] * P[t][row][k]                          (update_B, :86)
-//   kSrcPC      sum_j B2[j][k] * P[row][j][k]                          (update_C, :93)
 // With apply == 0 the kernel only reduces: rows go to rhs_out (N>1: the all-reduce comes next).
 #pragma once
 #include "common.cuh"
@@ -29,24 +24,31 @@ namespace tritd {
 
 constexpr int kStatusCholesky = 1;
 
-enum UpdSrc { kSrcDirect = 0, kSrcPartF = 1, kSrcPB = 2, kSrcPC = 3 };
-
+// The RHS source is a strided sum: row `row` of the RHS is  sum_{m < count} w[m*wstride + k] * v[row_base + m*stride + k]
+// with row_base = (row / tile_h) * tile_stride + (row % tile_h) * row_stride, so ONE kernel body (one set of
+// instruction addresses, which stays warm in the instruction cache across the three updates of an iteration) serves
+//   direct      count = 1, v = rhs, w = 1                        (first iteration; N>1 after the all-reduce)
+//   mode-1      v = k_admm's per-CTA partials of X1*F', w = 1    (update_A)
+//   P over t    v = P[t][row][k], w = C3[t][k]                   (update_B, :86)
+//   P over j    v = P[row][j][k], w = B2[j][k]                   (update_C, :93)
 struct UpdArgs {
-    const double* rhs;        // kSrcDirect: [n][RS]
-    const double* part;       // kSrcPartF: [gridA][128][RS]; the CTAs of i-tile `it` are c = it + q*nit, q < part_count
-    int part_count, nit, tile_h;
-    const double* P;          // kSrcPB / kSrcPC: [n3][n2][RS]
-    const double* W;          // kSrcPB: C3 [n3][RS]; kSrcPC: B2 [n2][RS]
-    int n2, n3;
-    const double *S1, *S2;    // small Grams of the two other factors, each a stack of ns1 / ns2 partial [RS][RS] matrices
-    int ns1, ns2;
+    const double* v;          // items
+    const double* w;          // weights (a vector of ones with wstride 0 when the source is a plain sum)
+    long stride, wstride;     // item stride of v / w in doubles
+    long tile_stride, row_stride;
+    int tile_h;               // rows per tile of the source (INT_MAX when rows are simply row_stride apart)
+    int count;                // items per row
+    int wpr;                  // warps that share a row: 1 (8 rows per CTA) or 8 (1 row per CTA)
+    const double *S1, *S2;    // [RS][RS] small Grams of the two other factors
     double alpha;
     double* Minv;             // [R][RS] scratch: inv(S1 o S2 + alpha I), written by block 0
     double* rhs_out;          // apply == 0: reduced rows [n][RS]
     double* X;                // [n][RS]
     double* XT;               // [RS][ldt] or nullptr
-    double* gram_out;         // [gr][RS][RS]: X'X over the rows of this rank as gr row-slice partials (consumers sum them)
-    int gr;
+    double* gram_out;         // [RS][RS] = X'X over the rows of this rank
+    double* gram_part;        // [gr][RS][RS] scratch: row-slice partials
+    unsigned* gram_cnt;       // [<= 64] per entry-slice arrival counters (zero between launches)
+    int gr;                   // row slices of the Gram phase
     IterState* st;
     unsigned* flags;          // [0] inverse published, [1] row CTAs done, [2] Gram CTAs done; all zero between launches
     int apply;
@@ -92,37 +94,38 @@ __device__ __forceinline__ double rcp_newton(double x) {
 // column pass through shared memory (double-buffered, published by their owners as they are produced): one
 // barrier, 2*PQ+1 shared loads, one reciprocal, PQ*PQ FMAs.  Returns true when a pivot was bad.
 template <int PQ>
-__device__ bool invert_ridge_system(const double* S1, int ns1, const double* S2, int ns2, double alpha, int R, int RS, double* out,
-                                    double* sm /* >= 256 doubles */) {
+__device__ bool invert_ridge_system(const double* S1, const double* S2, double alpha, int R, int RS, double* out,
+                                    double* sm /* >= 256 doubles */, long long* dbg = nullptr) {
     double* prow = sm;        // [2][64]
     double* pcol = sm + 128;  // [2][64]
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     double gq[PQ][PQ];
+    {
+        // all loads first (2*PQ*PQ in flight per thread), then the Hadamard product and the ridge
+        double t1[PQ][PQ], t2[PQ][PQ];
 #pragma unroll
-    for (int p = 0; p < PQ; ++p)
+        for (int p = 0; p < PQ; ++p)
 #pragma unroll
-        for (int q = 0; q < PQ; ++q) {
-            const int i = ty + 16 * p, j = tx + 16 * q;
-            double v = 0.0;
-            if (i < R && j < R) {
-                // partial stacks (<= 8 slices) are summed in slice order; all loads of an entry are issued together
-                double t1[8], t2[8];
+            for (int q = 0; q < PQ; ++q) {
+                const int i = ty + 16 * p, j = tx + 16 * q;
+                const bool ok = i < R && j < R;
+                t1[p][q] = ok ? S1[i * RS + j] : 0.0;
+                t2[p][q] = ok ? S2[i * RS + j] : 0.0;
+            }
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    t1[s] = s < ns1 ? S1[s * RS * RS + i * RS + j] : 0.0;
-                    t2[s] = s < ns2 ? S2[s * RS * RS + i * RS + j] : 0.0;
-                }
-                double s1 = t1[0], s2 = t2[0];
+        for (int p = 0; p < PQ; ++p)
 #pragma unroll
-                for (int s = 1; s < 8; ++s) { s1 += t1[s]; s2 += t2[s]; }
-                v = s1 * s2;
-                if (i == j) v += alpha;
+            for (int q = 0; q < PQ; ++q) {
+                const int i = ty + 16 * p, j = tx + 16 * q;
+                double v = t1[p][q] * t2[p][q];
+                if (i == j && i < R) v += alpha;
                 if (i == 0) prow[j] = v;
                 if (j == 0) pcol[i] = v;
+                gq[p][q] = v;
             }
-            gq[p][q] = v;
-        }
+    }
     __syncthreads();
+    if (dbg && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[13] = t_; }
     bool bad = false;
     // Steps k = 16*KP + kl with the 16-block KP of the pivot a compile-time constant (unrolled), so the pivot row and
     // column are fixed registers: one generic FMA per entry, then per-step fix-ups of row k / column k.
@@ -212,24 +215,25 @@ __global__ void __launch_bounds__(256) k_small_gram(const double* X, int n, int 
 }
 
 constexpr int kUpdThreads = 256;
+constexpr int kUpdMaxGramCtas = 64;   // CTAs that may spin in the Gram phase (<< 148 SMs x resident CTAs)
 __host__ __device__ inline size_t upd_smem_bytes(int RS) {
     const int ms = RS * RS > 64 * RS ? RS * RS : 64 * RS;      // inv(G) tile / Gram row chunk [64][RS]
     return (size_t)(3 * 8 * 64 + ms) * sizeof(double);
 }
 
-template <int SRC, int WPR, int KPL>   // KPL = columns per lane: 1 (RS <= 32) or 2 (RS <= 64)
+template <int PQ>   // ceil(R / 16): the register patch of the inversion; also fixes the columns per lane (1 for RS <= 32, else 2)
 __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
     if (a.st->stop) return;
-    constexpr int ROWS = 8 / WPR;                 // rows per row CTA; WPR warps share a row
-    constexpr int CH = 8;                         // independent accumulation chains per lane and column
+    constexpr int KPL = PQ <= 2 ? 1 : 2;
+    constexpr int CH = 8;                         // independent accumulation chains (= loads in flight) per lane and column
     extern __shared__ double sm[];
     double* red = sm;                             // [8 warps][64]  (block 0: pivot row/column buffers)
-    double* rhs_s = sm + 512;                     // [ROWS][64]
-    double* xs = sm + 1024;                       // [ROWS][64]
-    double* Ms = sm + 1536;                       // [R][RS] inverse, later the Gram row chunk [32][RS]
+    double* rhs_s = sm + 512;                     // [rows][64]
+    double* Ms = sm + 1536;                       // [R][RS] inverse, later the Gram row chunk [64][RS]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int R = a.R, RS = a.RS;
-    const int nrowcta = (a.n + ROWS - 1) / ROWS;
+    const int wpr = a.wpr, rows = 8 / wpr;        // rows per row CTA; wpr warps share a row
+    const int nrowcta = (a.n + rows - 1) / rows;
 #define TRITD_STAMP(blk, q)                                                         \
     if (a.dbg && blockIdx.x == (blk) && tid == 0) {                                 \
         long long t_;                                                               \
@@ -242,19 +246,15 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
     if (blockIdx.x == 0) {
         if (!a.apply) return;
         // ---------------- the ridge system, inverted while the row CTAs reduce ----------------
-        bool bad;
-        if (R <= 16) bad = invert_ridge_system<1>(a.S1, a.ns1, a.S2, a.ns2, a.alpha, R, RS, a.Minv, red);
-        else if (R <= 32) bad = invert_ridge_system<2>(a.S1, a.ns1, a.S2, a.ns2, a.alpha, R, RS, a.Minv, red);
-        else if (R <= 48) bad = invert_ridge_system<3>(a.S1, a.ns1, a.S2, a.ns2, a.alpha, R, RS, a.Minv, red);
-        else bad = invert_ridge_system<4>(a.S1, a.ns1, a.S2, a.ns2, a.alpha, R, RS, a.Minv, red);
+        const bool bad = invert_ridge_system<PQ>(a.S1, a.S2, a.alpha, R, RS, a.Minv, red, a.dbg);
         if (bad && tid == 0) atomicExch(&a.st->status, kStatusCholesky);
         __syncthreads();
         if (tid == 0) st_release_u32(&a.flags[0], 1u);
         TRITD_STAMP(0, 1)
     } else {
-        // ---------------- RHS rows: fixed-order reduction from the source ----------------
-        const int row0 = (blockIdx.x - 1) * ROWS;
-        const int r = warp / WPR, sub = warp - r * WPR;
+        // ---------------- RHS rows: fixed-order strided sum ----------------
+        const int row0 = (blockIdx.x - 1) * rows;
+        const int r = warp / wpr, sub = warp - r * wpr;
         const int row = row0 + r;
         double acc[KPL][CH];
 #pragma unroll
@@ -265,75 +265,47 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
 #pragma unroll
         for (int q = 0; q < KPL; ++q) kok[q] = lane + 32 * q < RS;
         if (row < a.n) {
-            if (SRC == kSrcDirect) {
-                if (sub == 0)
-#pragma unroll
-                    for (int q = 0; q < KPL; ++q)
-                        if (kok[q]) acc[q][0] = a.rhs[(size_t)row * RS + lane + 32 * q];
-            } else {
-                const int count = SRC == kSrcPartF ? a.part_count : (SRC == kSrcPB ? a.n3 : a.n2);
-                const double* base;           // item m lives at base + m * stride (+ k)
-                size_t stride;
-                const double* wbase = a.W + lane;
-                if (SRC == kSrcPartF) {
-                    const int it = row / a.tile_h, il = row - it * a.tile_h;
-                    base = a.part + ((size_t)it * 128 + il) * RS + lane;
-                    stride = (size_t)a.nit * 128 * RS;
-                } else if (SRC == kSrcPB) {
-                    base = a.P + (size_t)row * RS + lane;
-                    stride = (size_t)a.n2 * RS;
-                } else {
-                    base = a.P + (size_t)row * a.n2 * RS + lane;
-                    stride = (size_t)RS;
-                }
-                // the loads of a round are issued together (CH x KPL per lane in flight), then accumulated
-                int m0 = sub;
-                for (; m0 + (CH - 1) * WPR < count; m0 += WPR * CH) {
-                    double v[KPL][CH], w[KPL][CH];
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        const size_t m = (size_t)(m0 + c * WPR);
-#pragma unroll
-                        for (int q = 0; q < KPL; ++q) {
-                            v[q][c] = kok[q] ? base[m * stride + 32 * q] : 0.0;
-                            if (SRC != kSrcPartF) w[q][c] = kok[q] ? wbase[m * RS + 32 * q] : 0.0;
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < CH; ++c)
-#pragma unroll
-                        for (int q = 0; q < KPL; ++q) {
-                            if (SRC == kSrcPartF) acc[q][c] += v[q][c];
-                            else acc[q][c] = fma(w[q][c], v[q][c], acc[q][c]);
-                        }
-                }
+            const int it = row / a.tile_h, il = row - it * a.tile_h;
+            const double* vb = a.v + it * a.tile_stride + il * a.row_stride + lane;
+            const double* wb = a.w + lane;
+            // items m = sub + wpr * (c + CH * round); the loads of a round are issued together, then accumulated;
+            // out-of-range items of the last round read item 0 with weight 0
+            for (int m0 = sub; m0 < a.count; m0 += wpr * CH) {
+                double v[KPL][CH], w[KPL][CH];
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
-                    const int m = m0 + c * WPR;
-                    if (m < count) {
+                    const int m = m0 + c * wpr;
+                    const bool ok = m < a.count;
+                    const long mv = ok ? m * a.stride : 0, mw = ok ? m * a.wstride : 0;
 #pragma unroll
-                        for (int q = 0; q < KPL; ++q) {
-                            const double v = kok[q] ? base[(size_t)m * stride + 32 * q] : 0.0;
-                            if (SRC == kSrcPartF) acc[q][c] += v;
-                            else acc[q][c] = fma(kok[q] ? wbase[(size_t)m * RS + 32 * q] : 0.0, v, acc[q][c]);
-                        }
+                    for (int q = 0; q < KPL; ++q) {
+                        v[q][c] = kok[q] ? vb[mv + 32 * q] : 0.0;
+                        w[q][c] = (ok && kok[q]) ? wb[mw + 32 * q] : 0.0;
                     }
                 }
+#pragma unroll
+                for (int c = 0; c < CH; ++c)
+#pragma unroll
+                    for (int q = 0; q < KPL; ++q) acc[q][c] = fma(w[q][c], v[q][c], acc[q][c]);
             }
         }
 #pragma unroll
-        for (int q = 0; q < KPL; ++q) {
-            const double s = ((acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3])) + ((acc[q][4] + acc[q][5]) + (acc[q][6] + acc[q][7]));
-            red[warp * 64 + lane + 32 * q] = s;
-        }
+        for (int q = 0; q < KPL; ++q)
+            red[warp * 64 + lane + 32 * q] =
+                ((acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3])) + ((acc[q][4] + acc[q][5]) + (acc[q][6] + acc[q][7]));
         __syncthreads();
-        for (int e = tid; e < ROWS * RS; e += kUpdThreads) {
-            const int rr = e / RS, k = e - rr * RS;
-            double v = red[(rr * WPR) * 64 + k];
+        // combine the wpr warps of a row in warp order: thread (rr = warp, k = lane + 32q) for rr < rows
+        if (warp < rows) {
 #pragma unroll
-            for (int s = 1; s < WPR; ++s) v += red[(rr * WPR + s) * 64 + k];
-            rhs_s[rr * 64 + k] = v;
-            if (!a.apply && row0 + rr < a.n) a.rhs_out[(size_t)(row0 + rr) * RS + k] = v;
+            for (int q = 0; q < KPL; ++q) {
+                const int k = lane + 32 * q;
+                if (k < RS) {
+                    double v = red[(warp * wpr) * 64 + k];
+                    for (int s2 = 1; s2 < wpr; ++s2) v += red[(warp * wpr + s2) * 64 + k];
+                    rhs_s[warp * 64 + k] = v;
+                    if (!a.apply && row0 + warp < a.n) a.rhs_out[(size_t)(row0 + warp) * RS + k] = v;
+                }
+            }
         }
         if (!a.apply) return;
         TRITD_STAMP(1, 5)
@@ -344,32 +316,33 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
         for (int e = tid; e < R * RS; e += kUpdThreads) Ms[e] = __ldcg(a.Minv + e);
         __syncthreads();
         TRITD_STAMP(1, 8)
-        for (int e = tid; e < ROWS * RS; e += kUpdThreads) {
-            const int rr = e / RS, k = e - rr * RS;
-            double v = 0.0;
-            if (k < R) {
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-                int m = 0;
-                for (; m + 3 < R; m += 4) {
-                    s0 = fma(rhs_s[rr * 64 + m], Ms[m * RS + k], s0);
-                    s1 = fma(rhs_s[rr * 64 + m + 1], Ms[(m + 1) * RS + k], s1);
-                    s2 = fma(rhs_s[rr * 64 + m + 2], Ms[(m + 2) * RS + k], s2);
-                    s3 = fma(rhs_s[rr * 64 + m + 3], Ms[(m + 3) * RS + k], s3);
+        if (warp < rows) {
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {
+                const int k = lane + 32 * q;
+                if (k < RS) {
+                    double v = 0.0;
+                    if (k < R) {
+                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                        const double* rr = rhs_s + warp * 64;
+                        int m = 0;
+                        for (; m + 3 < R; m += 4) {
+                            s0 = fma(rr[m], Ms[m * RS + k], s0);
+                            s1 = fma(rr[m + 1], Ms[(m + 1) * RS + k], s1);
+                            s2 = fma(rr[m + 2], Ms[(m + 2) * RS + k], s2);
+                            s3 = fma(rr[m + 3], Ms[(m + 3) * RS + k], s3);
+                        }
+                        for (; m < R; ++m) s0 = fma(rr[m], Ms[m * RS + k], s0);
+                        v = (s0 + s1) + (s2 + s3);
+                    }
+                    if (row0 + warp < a.n) {
+                        a.X[(size_t)(row0 + warp) * RS + k] = v;
+                        if (a.XT) a.XT[(size_t)k * a.ldt + row0 + warp] = v;
+                    }
                 }
-                for (; m < R; ++m) s0 = fma(rhs_s[rr * 64 + m], Ms[m * RS + k], s0);
-                v = (s0 + s1) + (s2 + s3);
             }
-            xs[rr * 64 + k] = v;
-            if (row0 + rr < a.n) a.X[(size_t)(row0 + rr) * RS + k] = v;
         }
         TRITD_STAMP(1, 9)
-        if (a.XT) {
-            __syncthreads();
-            for (int e = tid; e < ROWS * RS; e += kUpdThreads) {
-                const int k = e / ROWS, rr = e - k * ROWS;
-                if (row0 + rr < a.n) a.XT[(size_t)k * a.ldt + row0 + rr] = xs[rr * 64 + k];
-            }
-        }
         __syncthreads();
         TRITD_STAMP(1, 10)
         if (tid == 0) red_release_add_u32(&a.flags[1], 1u);
@@ -377,43 +350,83 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
     }
 
     // ---------------- S = X'X once every row is written ----------------
-    // G entry slices (256 entries, one per thread) x gr row slices, one (entry, row) slice per CTA: every slice is a
-    // couple of 64-row chunks, so the phase is one or two L2 round trips; the gr partial matrices are summed by the
-    // consumer (block 0 of the next updates) in slice order.
+    // Slices of ES entries x one row range, one per CTA: the 256 threads are RG row groups x ES entries (4 x 64 for
+    // R <= 32, so a 64-row chunk costs 16 MACs per thread); the groups are combined in group order through shared memory and the
+    // gr row-range partials by the last slice to arrive, in slice order (deterministic either way).
     const int RR = R * R;
-    const int G = (RR + kUpdThreads - 1) / kUpdThreads;
+    const int ES = RR <= 1024 ? 64 : 256, RG = kUpdThreads / ES;       // entries per slice x row groups = 256 threads
+    const int G = (RR + ES - 1) / ES;
     const int nslice = G * a.gr;
-    if ((int)blockIdx.x >= nslice) return;
+    // Only the first `npart` CTAs take part (and spin): the row CTAs behind them must be able to become resident,
+    // so the number of waiting CTAs stays well below the number of CTA slots of the GPU.
+    const int npart = min(min(nslice, (int)gridDim.x), kUpdMaxGramCtas);
+    if ((int)blockIdx.x >= npart) return;
     cta_wait_eq(&a.flags[1], (unsigned)nrowcta);
     TRITD_STAMP(0, 2)
-    for (int sl = blockIdx.x; sl < nslice; sl += gridDim.x) {
+    const int el = tid % ES, grp = tid / ES, rpg = 64 / RG;
+    __shared__ int s_lastslice;
+    for (int sl = blockIdx.x; sl < nslice; sl += npart) {
         const int es = sl % G, rs = sl / G;
         const int r0 = (int)((long)a.n * rs / a.gr), r1 = (int)((long)a.n * (rs + 1) / a.gr);
-        const int e = es * kUpdThreads + tid;
+        const int e = es * ES + el;
         const bool ok = e < RR;
         const int aa = ok ? e / R : 0, bb = ok ? e - aa * R : 0;
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         for (int i0 = r0; i0 < r1; i0 += 64) {
             __syncthreads();
             const int nr = min(64, r1 - i0);
-            for (int q = tid; q < 64 * RS; q += kUpdThreads) Ms[q] = q < nr * RS ? __ldcg(a.X + (size_t)i0 * RS + q) : 0.0;
+            const int nq = nr * RS;
+            const double* src = a.X + (size_t)i0 * RS;
+            for (int q0 = 0; q0 < 64 * RS; q0 += 8 * kUpdThreads) {      // 8 loads in flight per thread
+                double t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int q = q0 + u * kUpdThreads + tid; t[u] = q < nq ? __ldcg(src + q) : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int q = q0 + u * kUpdThreads + tid; if (q < 64 * RS) Ms[q] = t[u]; }
+            }
             __syncthreads();
             TRITD_STAMP(0, 11)
-            const int nr4 = (nr + 3) & ~3;
-            for (int i = 0; i < nr4; i += 4) {
-                s0 = fma(Ms[i * RS + aa], Ms[i * RS + bb], s0);
-                s1 = fma(Ms[(i + 1) * RS + aa], Ms[(i + 1) * RS + bb], s1);
-                s2 = fma(Ms[(i + 2) * RS + aa], Ms[(i + 2) * RS + bb], s2);
-                s3 = fma(Ms[(i + 3) * RS + aa], Ms[(i + 3) * RS + bb], s3);
+            const double* m = Ms + grp * rpg * RS;                       // rows rpg*grp .. rpg*(grp+1)-1 of the chunk
+#pragma unroll 4
+            for (int i = 0; i < rpg; i += 4) {
+                s0 = fma(m[i * RS + aa], m[i * RS + bb], s0);
+                s1 = fma(m[(i + 1) * RS + aa], m[(i + 1) * RS + bb], s1);
+                s2 = fma(m[(i + 2) * RS + aa], m[(i + 2) * RS + bb], s2);
+                s3 = fma(m[(i + 3) * RS + aa], m[(i + 3) * RS + bb], s3);
             }
         }
-        if (ok) a.gram_out[(size_t)rs * RS * RS + aa * RS + bb] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        red[grp * ES + el] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (grp == 0 && ok) {
+            double v = red[el];
+            for (int g2 = 1; g2 < RG; ++g2) v += red[g2 * ES + el];
+            if (a.gr == 1) a.gram_out[aa * RS + bb] = v;
+            else a.gram_part[(size_t)rs * RS * RS + aa * RS + bb] = v;
+        }
+        if (a.gr > 1) {
+            // the last row slice to arrive for this entry slice sums the gr partials in slice order
+            __syncthreads();
+            if (tid == 0) s_lastslice = atom_acq_rel_add_u32(&a.gram_cnt[es], 1u) == (unsigned)a.gr - 1;
+            __syncthreads();
+            if (s_lastslice) {
+                if (grp == 0 && ok) {
+                    double t[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) t[u] = u < a.gr ? __ldcg(a.gram_part + (size_t)u * RS * RS + aa * RS + bb) : 0.0;
+                    double v = t[0];
+#pragma unroll
+                    for (int u = 1; u < 8; ++u) v += t[u];
+                    a.gram_out[aa * RS + bb] = v;
+                }
+                if (tid == 0) a.gram_cnt[es] = 0u;
+            }
+        }
     }
     __syncthreads();
     TRITD_STAMP(0, 12)
     if (tid == 0) {
-        const unsigned parts = (unsigned)min(nslice, (int)gridDim.x);
-        if (atom_acq_rel_add_u32(&a.flags[2], 1u) == parts - 1) {      // last Gram CTA: leave the flags zero for the next launch
+        if (atom_acq_rel_add_u32(&a.flags[2], 1u) == (unsigned)npart - 1) {      // last Gram CTA: leave the flags zero for the next launch
             a.flags[0] = 0u; a.flags[1] = 0u; a.flags[2] = 0u;
         }
     }

@@ -23,6 +23,7 @@
 #include "kernels_contract.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_update.cuh"
+#include <climits>
 
 using namespace tritd;
 
@@ -243,6 +244,8 @@ struct tritd_problem {
     double *bufA = nullptr;              // [rhsA (n1*RS) ; SC (RS*RS)] -- one all-reduce
     double *rhsB = nullptr, *rhsC = nullptr, *P = nullptr, *partM = nullptr;
     double *norm_part = nullptr, *norms = nullptr;
+    double* gpart = nullptr;             // [3][kGramSlices][RS][RS] row-slice partial Grams of k_upd
+    double* ones = nullptr;              // [64] vector of ones: the weights of a plain-sum RHS source
     double* Minv = nullptr;              // [3][RS][RS] inverses of the three ridge systems (written by k_upd's block 0)
     long long* dbg = nullptr;            // optional globaltimer stamps of k_upd (TRITD_DEBUG_STAMPS=1)
     unsigned* flags = nullptr;           // [3][4] k_upd hand-shake words (A, B, C) + [12] the k_admm completion ticket
@@ -379,36 +382,44 @@ static int launch_admm(tritd_problem* p) {
 // One factor update (k_upd): RHS rows from `src`, X = RHS * inv(S1 o S2 + alpha I), S_out = X'X, optionally X
 // transposed.  which = 0/1/2 (A/B/C) selects the scratch inverse and the hand-shake flags.  apply == false: only
 // reduce the RHS rows into rhs_out (the all-reduce comes next).
-constexpr int kGramSlices = 8;     // SA / SB / SC are stacks of up to 8 row-slice partial Grams
-static int gram_slices(int n, bool single_matrix) { return single_matrix ? 1 : std::max(1, std::min(kGramSlices, (n + 63) / 64)); }
+constexpr int kGramSlices = 8;     // row slices of k_upd's Gram phase
+static int gram_slices(int n) { return std::max(1, std::min(kGramSlices, (n + 63) / 64)); }
+
+enum UpdSrc { kSrcDirect = 0, kSrcPartF = 1, kSrcPB = 2, kSrcPC = 3 };
 
 static int launch_upd(tritd_problem* p, int which, int src, bool apply, const double* rhs_direct, double* rhs_out,
-                      const double* S1, int ns1, const double* S2, int ns2, double alpha, double* X, double* XT, int n,
-                      double* S_out, int gr) {
+                      const double* S1, const double* S2, double alpha, double* X, double* XT, int n, double* S_out) {
     tritd_ctx* c = p->ctx;
     UpdArgs a;
     memset(&a, 0, sizeof(a));
-    a.rhs = rhs_direct;
-    a.part = p->partF; a.part_count = p->gridA / p->nitA; a.nit = p->nitA; a.tile_h = p->tileH;
-    a.P = p->P; a.W = src == kSrcPB ? p->C3 : p->B2; a.n2 = p->n2; a.n3 = p->n3;
-    a.S1 = S1; a.S2 = S2; a.ns1 = ns1; a.ns2 = ns2; a.alpha = alpha; a.gr = gr;
+    const long RS = p->RS;
+    a.w = p->ones; a.wstride = 0; a.tile_h = INT_MAX; a.tile_stride = 0; a.row_stride = RS; a.wpr = 1;
+    switch (src) {
+        case kSrcDirect: a.v = rhs_direct; a.stride = 0; a.count = 1; break;
+        case kSrcPartF:
+            a.v = p->partF; a.stride = (long)p->nitA * 128 * RS; a.count = p->gridA / p->nitA;
+            a.tile_h = p->tileH; a.tile_stride = 128 * RS; a.wpr = 8;
+            break;
+        case kSrcPB: a.v = p->P; a.stride = (long)p->n2 * RS; a.count = p->n3; a.w = p->C3; a.wstride = RS; a.wpr = 8; break;
+        case kSrcPC: a.v = p->P; a.stride = RS; a.count = p->n2; a.row_stride = (long)p->n2 * RS; a.w = p->B2; a.wstride = RS; a.wpr = 8; break;
+        default: return fail(TRITD_ERR_INVALID, "bad update source");
+    }
+    a.S1 = S1; a.S2 = S2; a.alpha = alpha; a.gr = gram_slices(n);
+    a.gram_part = p->gpart + (size_t)which * kGramSlices * p->RS * p->RS; a.gram_cnt = p->flags + 16 + 64 * which;
     a.Minv = p->Minv + (size_t)which * p->RS * p->RS;
     a.rhs_out = rhs_out; a.X = X; a.XT = XT; a.gram_out = S_out;
     a.st = p->st; a.flags = p->flags + 4 * which; a.apply = apply ? 1 : 0;
     a.n = n; a.R = p->R; a.RS = p->RS; a.ldt = p->ldt;
     a.dbg = p->dbg ? p->dbg + 16 * which : nullptr;
     const size_t sm = upd_smem_bytes(p->RS);
-#define UPD_LAUNCH(SRC_, WPR_, GRID_)                                                                  \
-    if (p->RS <= 32) k_upd<SRC_, WPR_, 1><<<(GRID_), kUpdThreads, sm, c->stream>>>(a);                  \
-    else k_upd<SRC_, WPR_, 2><<<(GRID_), kUpdThreads, sm, c->stream>>>(a);
-    switch (src) {
-        case kSrcDirect: UPD_LAUNCH(kSrcDirect, 1, (n + 7) / 8 + 1) break;
-        case kSrcPartF: UPD_LAUNCH(kSrcPartF, 1, (n + 7) / 8 + 1) break;
-        case kSrcPB: UPD_LAUNCH(kSrcPB, 4, (n + 1) / 2 + 1) break;
-        case kSrcPC: UPD_LAUNCH(kSrcPC, 4, (n + 1) / 2 + 1) break;
-        default: return fail(TRITD_ERR_INVALID, "bad update source");
+    const int rows = 8 / a.wpr;
+    const unsigned grid = (unsigned)((n + rows - 1) / rows + 1);
+    switch ((p->R + 15) / 16) {
+        case 1: k_upd<1><<<grid, kUpdThreads, sm, c->stream>>>(a); break;
+        case 2: k_upd<2><<<grid, kUpdThreads, sm, c->stream>>>(a); break;
+        case 3: k_upd<3><<<grid, kUpdThreads, sm, c->stream>>>(a); break;
+        default: k_upd<4><<<grid, kUpdThreads, sm, c->stream>>>(a); break;
     }
-#undef UPD_LAUNCH
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     return TRITD_OK;
@@ -459,8 +470,9 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     PALLOC(D, p->Np); PALLOC(E, p->Np); PALLOC(YL, p->Np); PALLOC(YO, p->Np); PALLOC(T, p->Np); PALLOC(O, p->Np);
     PALLOC(A1, (size_t)p->n1 * p->RS); PALLOC(B2, (size_t)p->n2 * p->RS); PALLOC(C3, (size_t)p->n3 * p->RS);
     PALLOC(A1T, (size_t)p->RS * p->ldt);
-    PALLOC(SA, (size_t)kGramSlices * p->RS * p->RS); PALLOC(SB, (size_t)kGramSlices * p->RS * p->RS);
-    PALLOC(bufA, (size_t)p->n1 * p->RS + (size_t)kGramSlices * p->RS * p->RS);
+    PALLOC(SA, (size_t)p->RS * p->RS); PALLOC(SB, (size_t)p->RS * p->RS);
+    PALLOC(gpart, (size_t)3 * kGramSlices * p->RS * p->RS);
+    PALLOC(bufA, (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS);
     PALLOC(rhsB, (size_t)p->n2 * p->RS); PALLOC(rhsC, (size_t)p->n3 * p->RS);
     PALLOC(P, (size_t)p->n3 * p->n2 * p->RS);
 
@@ -487,7 +499,9 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         const int nmax = std::max(p->n1, std::max(p->n2, p->n3));
         (void)nmax;
         PALLOC(Minv, (size_t)3 * p->RS * p->RS);
-        PALLOC(flags, 16);
+        PALLOC(flags, 16 + 3 * 64);
+        PALLOC(ones, 64);
+        { double h1[64]; for (double& x : h1) x = 1.0; cudaMemcpy(p->ones, h1, sizeof(h1), cudaMemcpyHostToDevice); }
         if (getenv("TRITD_DEBUG_STAMPS")) { PALLOC(dbg, 48); cudaMemset(p->dbg, 0, 48 * 8); }
         PALLOC(tile0, p->gridM); PALLOC(tile1, p->gridM);
         std::vector<int> t0(p->gridM), t1(p->gridM);
@@ -499,7 +513,7 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         }
         cudaMemcpy(p->tile0, t0.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
         cudaMemcpy(p->tile1, t1.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
-        cudaMemset(p->flags, 0, 64);
+        cudaMemset(p->flags, 0, (16 + 3 * 64) * 4);
         // k_admm: one CTA per SM.  The i-tiles are as even as 16-row warp strips allow (240 rows -> 128 + 112,
         // 130 rows -> 80 + 50) and every tile gets the same number of CTAs: a stage costs the same whether
         // 7 or 8 warps work on it, so equal stage counts finish together.
@@ -682,7 +696,7 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
     iter_state_derive(h);
     *p->st_host = h;
     CU_TRY(cudaMemcpyAsync(p->st, p->st_host, sizeof(IterState), cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemsetAsync(p->flags, 0, 64, st));
+    CU_TRY(cudaMemsetAsync(p->flags, 0, (16 + 3 * 64) * 4, st));
 
     // history buffers sized by maxIter
     if (o->maxIter > p->hist_cap) {
@@ -702,9 +716,7 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
     k_set_normD<<<1, 32, 0, st>>>(p->st, p->norms);
     c->launches += 3;
 
-    // small Grams of the initial factors: SB = B2'B2, SC (partial over local rows) = C3'C3 -- slice 0 of their stacks
-    CU_TRY(cudaMemsetAsync(p->SB, 0, (size_t)kGramSlices * p->RS * p->RS * 8, st));
-    CU_TRY(cudaMemsetAsync(p->bufA + (size_t)p->n1 * p->RS, 0, (size_t)kGramSlices * p->RS * p->RS * 8, st));
+    // small Grams of the initial factors: SB = B2'B2, SC (partial over local rows) = C3'C3 -- 
     ST_TRY(launch_small_gram(p, p->B2, p->n2, p->SB));
     ST_TRY(launch_small_gram(p, p->C3, p->n3, p->bufA + (size_t)p->n1 * p->RS));
     CU_TRY(cudaStreamSynchronize(st));
@@ -733,33 +745,31 @@ static int enqueue_iteration(tritd_problem* p) {
     ST_TRY(mark());
 
     const bool multi = c->nranks > 1;
-    // SA, SB, SC are stacks of row-slice partial Grams (one matrix for SC when it has to be all-reduced)
-    const int gA = gram_slices(p->n1, false), gB = gram_slices(p->n2, false), gC = gram_slices(p->n3, multi);
     // update_A (:73-81): RHS = X1*F', Gram = (B2'B2) o (C3'C3) + lambda2*I.  From the second iteration on the
     // previous k_admm left per-CTA partials of X1*F' (accumulated from registers); single rank: k_upd sums them,
     // applies the inverse and forms A1'A1 in one launch.
     const bool direct_A = !p->rhsA_ready || multi;
     if (!p->rhsA_ready) ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, rhsA));
-    else if (multi) ST_TRY(launch_upd(p, 0, kSrcPartF, false, nullptr, rhsA, nullptr, 0, nullptr, 0, 0.0, nullptr, nullptr, p->n1, nullptr, 1));
+    else if (multi) ST_TRY(launch_upd(p, 0, kSrcPartF, false, nullptr, rhsA, nullptr, nullptr, 0.0, nullptr, nullptr, p->n1, nullptr));
     ST_TRY(mark());
     ST_TRY(allreduce_sum(c, p->bufA, (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS));
-    ST_TRY(launch_upd(p, 0, direct_A ? kSrcDirect : kSrcPartF, true, rhsA, nullptr, p->SB, gB, SC, gC, p->opts.lambda2, p->A1, p->A1T,
-                      p->n1, p->SA, gA));
+    ST_TRY(launch_upd(p, 0, direct_A ? kSrcDirect : kSrcPartF, true, rhsA, nullptr, p->SB, SC, p->opts.lambda2, p->A1, p->A1T,
+                      p->n1, p->SA));
     ST_TRY(mark());
 
     // update_B (:83-88) with the new A: RHS = X2*G' = sum_t C3(t,:) .* P(t,j,:), Gram = (A1'A1) o (C3'C3) + lambda2*I
     ST_TRY(launch_ppass(p, p->mapT));
     ST_TRY(mark());
     if (multi) {
-        ST_TRY(launch_upd(p, 1, kSrcPB, false, nullptr, p->rhsB, nullptr, 0, nullptr, 0, 0.0, nullptr, nullptr, p->n2, nullptr, 1));
+        ST_TRY(launch_upd(p, 1, kSrcPB, false, nullptr, p->rhsB, nullptr, nullptr, 0.0, nullptr, nullptr, p->n2, nullptr));
         ST_TRY(allreduce_sum(c, p->rhsB, (size_t)p->n2 * p->RS));
     }
-    ST_TRY(launch_upd(p, 1, multi ? kSrcDirect : kSrcPB, true, p->rhsB, nullptr, p->SA, gA, SC, gC, p->opts.lambda2, p->B2, nullptr,
-                      p->n2, p->SB, gB));
+    ST_TRY(launch_upd(p, 1, multi ? kSrcDirect : kSrcPB, true, p->rhsB, nullptr, p->SA, SC, p->opts.lambda2, p->B2, nullptr,
+                      p->n2, p->SB));
 
     // update_C (:90-95) with the new A, B: slice-local; ridge fixed at 1e-9.  Leaves SC = C3'C3 over the local
     // slices in bufA, where the next all-reduce sums it over the ranks.
-    ST_TRY(launch_upd(p, 2, kSrcPC, true, nullptr, nullptr, p->SA, gA, p->SB, gB, 1e-9, p->C3, nullptr, p->n3, SC, gC));
+    ST_TRY(launch_upd(p, 2, kSrcPC, true, nullptr, nullptr, p->SA, p->SB, 1e-9, p->C3, nullptr, p->n3, SC));
 
     ST_TRY(mark());
     // L, O, E, duals, next T, residual norms (:38-59, :33); single rank: its last CTA also does :56-65
