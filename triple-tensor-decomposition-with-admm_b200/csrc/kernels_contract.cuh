@@ -200,10 +200,10 @@ __global__ void __launch_bounds__(256) k_mttkrp1_reduce(const double* part, size
 
 // ---------------------------------------------------------------------------
 // k_ppass: P[t][j][k] = sum_i T(i,j,t) * A1(i,k)      (shared by the B and C updates)
-// CTA = 8 consumer warps + 1 TMA producer warp.  Row blocks rb = t * n_jb + jb (32 rows j
-// of slice t); a work unit is 8 consecutive row blocks, one per warp.  Per K-chunk of 16 i
+// CTA = 16 consumer warps + 1 TMA producer warp.  Row blocks rb = t * n_jb + jb (32 rows j
+// of slice t); a pass is 8 consecutive row blocks, two warps (16 rows each) per block.  Per K-chunk of 16 i
 // a stage holds 8 T boxes [32 j][16 i] and one factor box A1T[RS k][16 i], all 128B-swizzled.
-// MMA roles: M = j (4 m-tiles per warp, rows permuted by rho8), K = i, N = k (columns permuted by rho8).
+// MMA roles: M = j (2 m-tiles per warp, rows permuted by rho8), K = i, N = k (columns permuted by rho8).
 // ---------------------------------------------------------------------------
 struct PpassArgs {
     double* P;          // [n3][n2][RS]
@@ -211,11 +211,13 @@ struct PpassArgs {
     int n1, n2, n3, RS;
     int n_jb;           // ceil(n2 / 32)
     long n_rb;          // n3 * n_jb
-    long units;         // ceil(n_rb / 8)
+    long units;         // ceil(n_rb / 8) (grid sizing)
 };
 
+constexpr int kPW = 16;           // k_ppass consumer warps: two per row block (m-tiles 0,1 / 2,3), 4 per scheduler
+
 template <int NT>
-__global__ void __launch_bounds__((kCW + 1) * 32, 1)
+__global__ void __launch_bounds__((kPW + 1) * 32, 1)
 k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapA1T, const PpassArgs a) {
     if (*a.stop) return;
     constexpr int kStageDoubles = kCW * (kBoxBytes / 8) + NT * 8 * 16;
@@ -227,23 +229,26 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
     const int nkc = (a.n1 + 15) >> 4;
-    const long u0 = a.units * blockIdx.x / gridDim.x;
-    const long u1 = a.units * (blockIdx.x + 1) / gridDim.x;
+    // each CTA owns a contiguous range of row blocks, balanced to ONE row block (the DMMA pipe is the limit, so
+    // time follows the row-block count, not the number of 8-block passes); a pass = 8 consecutive row blocks
+    const long rbA = a.n_rb * blockIdx.x / gridDim.x;
+    const long rbB = a.n_rb * (blockIdx.x + 1) / gridDim.x;
+    const long npass = (rbB - rbA + kCW - 1) / kCW;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kCW); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kPW); }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == kCW) {
+    if (warp == kPW) {
         if (lane == 0) {
             tma_prefetch_desc(&mapT);
             tma_prefetch_desc(&mapA1T);
             int s = 0; uint32_t ph = 0;
-            for (long u = u0; u < u1; ++u) {
-                const long rb0 = u * kCW;
-                const int nvalid = (int)min((long)kCW, a.n_rb - rb0);
+            for (long u = 0; u < npass; ++u) {
+                const long rb0 = rbA + u * kCW;
+                const int nvalid = (int)min((long)kCW, rbB - rb0);
                 for (int kc = 0; kc < nkc; ++kc) {
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], nvalid * kBoxBytes + NT * 8 * 128);
@@ -263,32 +268,33 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
 
     int s = 0; uint32_t ph = 0;
     const int rg = rho8(g);
-    for (long u = u0; u < u1; ++u) {
-        const long rb = u * kCW + warp;
-        const bool valid = rb < a.n_rb;
-        double acc[4][NT][2];
+    const int bw = warp & (kCW - 1), mh = warp >> 3;      // row block of the pass, half of its 32 rows (m-tiles 2mh, 2mh+1)
+    for (long u = 0; u < npass; ++u) {
+        const long rb = rbA + u * kCW + bw;
+        const bool valid = rb < rbB;
+        double acc[2][NT][2];
 #pragma unroll
-        for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
             for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
 
         for (int kc = 0; kc < nkc; ++kc) {
             mbar_wait(&full[s], ph);
             const double* st = stage_base + (size_t)s * kStageDoubles;
-            const double* box = st + warp * (kBoxBytes / 8);
+            const double* box = st + bw * (kBoxBytes / 8);
             const double* fbox = st + kCW * (kBoxBytes / 8);
             if (valid) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     // k-steps (h,e) cover i = kc*16 + 8h + 2*tig + e
-                    double2 af[4];
+                    double2 af[2];
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) af[m] = lds_swz128(box, 8 * m + rg, 4 * h + tig);
+                    for (int m = 0; m < 2; ++m) af[m] = lds_swz128(box, 8 * (2 * mh + m) + rg, 4 * h + tig);
 #pragma unroll
                     for (int n = 0; n < NT; ++n) {
                         const double2 b = lds_swz128(fbox, 8 * n + rg, 4 * h + tig);
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
+                        for (int m = 0; m < 2; ++m) {
                             dmma884(acc[m][n][0], acc[m][n][1], af[m].x, b.x);
                             dmma884(acc[m][n][0], acc[m][n][1], af[m].y, b.y);
                         }
@@ -301,10 +307,10 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
         }
         if (valid) {
             const int t = (int)(rb / a.n_jb), jb = (int)(rb - (long)t * a.n_jb);
-            // C fragment: row = 8m + rho8(g); columns n = 2*tig + c map to k = 8n' + rho8(2*tig + c) = 8n' + tig + 4c
+            // C fragment: row = 8m' + rho8(g); columns n = 2*tig + c map to k = 8n' + rho8(2*tig + c) = 8n' + tig + 4c
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int j = jb * kBoxRows + 8 * m + rg;
+            for (int m = 0; m < 2; ++m) {
+                const int j = jb * kBoxRows + 8 * (2 * mh + m) + rg;
                 if (j < a.n2) {
                     double* p = a.P + ((size_t)t * a.n2 + j) * a.RS;
 #pragma unroll

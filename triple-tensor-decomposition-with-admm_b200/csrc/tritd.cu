@@ -336,7 +336,7 @@ static int launch_ppass(tritd_problem* p, const CUtensorMap& mapT) {
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS;
     a.n_jb = p->n_jc; a.n_rb = (long)p->n3 * p->n_jc; a.units = p->unitsP;
 #define CALL(NT_, KS_) \
-    k_ppass<NT_><<<p->gridP, (kCW + 1) * 32, p->smemP, c->stream>>>(mapT, p->mapA1T, a);
+    k_ppass<NT_><<<p->gridP, (kPW + 1) * 32, p->smemP, c->stream>>>(mapT, p->mapA1T, a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
     CU_TRY(cudaGetLastError());
@@ -480,7 +480,7 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     p->unitsM = (long)p->n_it * p->n_jc * p->n3;
     p->gridM = (int)std::min<long>(p->unitsM, std::max(2 * p->n_it, c->num_sms));
     p->unitsP = ((long)p->n3 * p->n_jc + kCW - 1) / kCW;
-    p->gridP = (int)std::min<long>(p->unitsP, c->num_sms);
+    p->gridP = (int)std::min<long>((long)p->n3 * p->n_jc, c->num_sms);       // row blocks are the unit of balance
     p->smemM = smem_mttkrp1(p->NT);
     p->smemP = smem_ppass(p->NT);
     int occ = 1;
