@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "kernels_contract.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_xchg.cuh"
 
 namespace tritd {
 
@@ -34,6 +35,11 @@ struct AdmmArgs {
     double *errHist, *errL, *errO;     // history (written by the last CTA when finalize)
     unsigned* ticket;                  // CTA completion counter (zero between launches)
     int finalize;                      // 1: the last CTA also runs the errHist / mu / stopping-rule step (:56-65)
+    // N>1 peer exchange (kernels_xchg.cuh): the last CTA writes the pair into this rank's slot of every mailbox
+    double* const* peers;              // nullptr: pair left in norms[] (NCCL path)
+    long norm_off, nflag_off;          // offsets in doubles inside a mailbox: this rank's pair / the flag row
+    int rank, nranks;
+    unsigned xbase;
     double* partM;                     // [grid][128][RS]: this CTA's partial of the next X1*F'
     const int* cta_tab;                // [grid][3]: i-tile, index within the tile's CTAs, CTAs of that tile
     int n1, n2, n3, RS;
@@ -350,7 +356,15 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
     if (threadIdx.x == 0) {
         *a.ticket = 0u;
         if (a.finalize) iter_finalize(a.st, sa, sb, a.errHist, a.errL, a.errO);
-        else { a.norms[0] = sa; a.norms[1] = sb; }
+        else { a.norms[0] = sa; a.norms[1] = sb; red[0] = sa; red[1] = sb; }
+    }
+    if (!a.finalize && a.peers) {
+        __syncthreads();
+        if (threadIdx.x < (unsigned)a.nranks) {      // data and flag of one mailbox come from the same thread: release orders them
+            double* box = a.peers[threadIdx.x];
+            *reinterpret_cast<double2*>(box + a.norm_off) = make_double2(red[0], red[1]);
+            st_release_sys_u32(reinterpret_cast<unsigned*>(box + a.nflag_off) + a.rank, a.xbase + (unsigned)a.st->k + 1u);
+        }
     }
 }
 

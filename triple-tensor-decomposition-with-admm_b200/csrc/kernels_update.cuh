@@ -19,6 +19,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_fused.cuh"
+#include "kernels_xchg.cuh"
 
 namespace tritd {
 
@@ -39,7 +40,19 @@ struct UpdArgs {
     int tile_h;               // rows per tile of the source (INT_MAX when rows are simply row_stride apart)
     int count;                // items per row
     int wpr;                  // warps that share a row: 1 (8 rows per CTA) or 8 (1 row per CTA)
-    const double *S1, *S2;    // [RS][RS] small Grams of the two other factors
+    const double *S1, *S2;    // [RS][RS] small Grams of the two other factors; S2 may be a stack of ns2 matrices
+    int ns2;                  // (the per-rank partials of C3'C3 in the exchange mailbox), summed in order
+    long s2stride;
+    const unsigned* xflags;   // N>1 peer exchange: wait until these xn flags reached epoch xbase + k + 1 before
+    int xn;                   // reading v / S2 (nullptr: no wait)
+    unsigned xbase;
+    // N>1 peer exchange, producer side (apply == 0): rows go straight into this rank's slot of every rank's
+    // mailbox; block 0 adds `extra_n` doubles (the local C3'C3) behind them; the last CTA raises the flags
+    double* const* peers;     // [nranks] mailbox bases (nullptr: rows go to rhs_out only)
+    long push_off, pflag_off; // offsets in doubles: this rank's slot / the flag row of the exchange
+    const double* extra_src;
+    long extra_off;
+    int extra_n, rank, nranks;
     double alpha;
     double* Minv;             // [R][RS] scratch: inv(S1 o S2 + alpha I), written by block 0
     double* rhs_out;          // apply == 0: reduced rows [n][RS]
@@ -94,7 +107,7 @@ __device__ __forceinline__ double rcp_newton(double x) {
 // column pass through shared memory (double-buffered, published by their owners as they are produced): one
 // barrier, 2*PQ+1 shared loads, one reciprocal, PQ*PQ FMAs.  Returns true when a pivot was bad.
 template <int PQ>
-__device__ bool invert_ridge_system(const double* S1, const double* S2, double alpha, int R, int RS, double* out,
+__device__ bool invert_ridge_system(const double* S1, const double* S2, int ns2, long s2stride, double alpha, int R, int RS, double* out,
                                     double* sm /* >= 256 doubles */, long long* dbg = nullptr) {
     double* prow = sm;        // [2][64]
     double* pcol = sm + 128;  // [2][64]
@@ -112,6 +125,21 @@ __device__ bool invert_ridge_system(const double* S1, const double* S2, double a
                 t1[p][q] = ok ? S1[i * RS + j] : 0.0;
                 t2[p][q] = ok ? S2[i * RS + j] : 0.0;
             }
+        if (ns2 > 1) {                      // S2 is a stack of per-rank partials: add the others in rank order
+#pragma unroll
+            for (int p = 0; p < PQ; ++p)
+#pragma unroll
+                for (int q = 0; q < PQ; ++q) {
+                    const int i = ty + 16 * p, j = tx + 16 * q;
+                    if (i < R && j < R) {
+                        double t[7];
+#pragma unroll
+                        for (int u = 0; u < 7; ++u) t[u] = u + 1 < ns2 ? S2[(u + 1) * s2stride + i * RS + j] : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 7; ++u) t2[p][q] += t[u];
+                    }
+                }
+        }
 #pragma unroll
         for (int p = 0; p < PQ; ++p)
 #pragma unroll
@@ -242,11 +270,17 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
     }
     TRITD_STAMP(0, 0)
     TRITD_STAMP(1, 4)
+    if (a.xflags && (blockIdx.x != 0 || a.apply)) cta_wait_ranks(a.xflags, a.xn, a.xbase + (unsigned)a.st->k + 1u);
 
-    if (blockIdx.x == 0) {
-        if (!a.apply) return;
+    if (blockIdx.x == 0 && !a.apply) {
+        if (!a.peers) return;
+        for (int r = 0; r < a.nranks; ++r) {
+            double* dst = a.peers[(a.rank + 1 + r) % a.nranks] + a.push_off + a.extra_off;
+            for (int e = tid; e < a.extra_n; e += kUpdThreads) dst[e] = a.extra_src[e];
+        }
+    } else if (blockIdx.x == 0) {
         // ---------------- the ridge system, inverted while the row CTAs reduce ----------------
-        const bool bad = invert_ridge_system<PQ>(a.S1, a.S2, a.alpha, R, RS, a.Minv, red, a.dbg);
+        const bool bad = invert_ridge_system<PQ>(a.S1, a.S2, a.ns2, a.s2stride, a.alpha, R, RS, a.Minv, red, a.dbg);
         if (bad && tid == 0) atomicExch(&a.st->status, kStatusCholesky);
         __syncthreads();
         if (tid == 0) st_release_u32(&a.flags[0], 1u);
@@ -303,11 +337,32 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
                     double v = red[(warp * wpr) * 64 + k];
                     for (int s2 = 1; s2 < wpr; ++s2) v += red[(warp * wpr + s2) * 64 + k];
                     rhs_s[warp * 64 + k] = v;
-                    if (!a.apply && row0 + warp < a.n) a.rhs_out[(size_t)(row0 + warp) * RS + k] = v;
+                    if (!a.apply && row0 + warp < a.n) {
+                        if (!a.peers) a.rhs_out[(size_t)(row0 + warp) * RS + k] = v;
+                        else
+                            for (int r = 0; r < a.nranks; ++r)
+                                a.peers[(a.rank + 1 + r) % a.nranks][a.push_off + (size_t)(row0 + warp) * RS + k] = v;
+                    }
                 }
             }
         }
-        if (!a.apply) return;
+        if (!a.apply && !a.peers) return;
+    }
+    if (!a.apply) {
+        // producer of a peer exchange: once every CTA's stores are ordered at system scope, the last one raises
+        // this rank's flag in every mailbox
+        __shared__ int s_lastpush;
+        __syncthreads();
+        if (tid == 0) { __threadfence_system(); s_lastpush = atom_acq_rel_add_u32(&a.flags[3], 1u) == gridDim.x - 1; }
+        __syncthreads();
+        if (!s_lastpush) return;
+        if (tid < a.nranks)
+            st_release_sys_u32(reinterpret_cast<unsigned*>(a.peers[tid] + a.pflag_off) + a.rank, a.xbase + (unsigned)a.st->k + 1u);
+        if (tid == 0) a.flags[3] = 0u;
+        return;
+    }
+    if (blockIdx.x != 0) {
+        const int row0 = (blockIdx.x - 1) * rows;
         TRITD_STAMP(1, 5)
 
         // ---------------- apply the inverse: X[row][:] = RHS[row][:] * inv(G) ----------------

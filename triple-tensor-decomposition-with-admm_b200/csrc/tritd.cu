@@ -63,6 +63,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -83,6 +84,7 @@ static int nccl_load() {
     NCCL_SYM(CommInitRank, "ncclCommInitRank");
     NCCL_SYM(CommDestroy, "ncclCommDestroy");
     NCCL_SYM(AllReduce, "ncclAllReduce");
+    NCCL_SYM(AllGather, "ncclAllGather");
     NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef NCCL_SYM
     g_nccl.h = h;
@@ -111,6 +113,7 @@ struct tritd_ctx {
     int64_t launches = 0;
     PFN_encodeTiled encode = nullptr;
     tritd_problem* cached = nullptr;     // device state of the last tritd_admm_f64 call, reused when the shape repeats
+    unsigned xepoch = 0;                 // peer exchange: first unused epoch (advances identically on every rank)
 };
 
 struct RankCfg { int NT, KS; };
@@ -245,6 +248,13 @@ struct tritd_problem {
     double *rhsB = nullptr, *rhsC = nullptr, *P = nullptr, *partM = nullptr;
     double *norm_part = nullptr, *norms = nullptr;
     double* gpart = nullptr;             // [3][kGramSlices][RS][RS] row-slice partial Grams of k_upd
+    // N>1 peer exchange (kernels_xchg.cuh): local mailbox, the peers' mailboxes mapped with CUDA IPC
+    bool xchg = false;
+    double* box = nullptr;               // [A: nranks x slotA | B: nranks x slotB | N: nranks x 8 | flags 3 x nranks (u32)]
+    size_t slotA = 0, slotB = 0, offB = 0, offN = 0, offF = 0, box_doubles = 0;
+    std::vector<void*> peer_map;         // cudaIpcOpenMemHandle mappings (nullptr for the own rank)
+    double** peers = nullptr;            // device array [nranks] of mailbox bases
+    unsigned xbase = 0;
     double* ones = nullptr;              // [64] vector of ones: the weights of a plain-sum RHS source
     double* Minv = nullptr;              // [3][RS][RS] inverses of the three ridge systems (written by k_upd's block 0)
     long long* dbg = nullptr;            // optional globaltimer stamps of k_upd (TRITD_DEBUG_STAMPS=1)
@@ -368,6 +378,8 @@ static int launch_admm(tritd_problem* p) {
     a.A1 = p->A1; a.B2 = p->B2; a.C3 = p->C3; a.st = p->st; a.norm_part = p->norm_part; a.partM = p->partF;
     a.norms = p->norms; a.errHist = p->errHist; a.errL = p->errL; a.errO = p->errO;
     a.ticket = p->flags + 12; a.finalize = c->nranks == 1 ? 1 : 0;
+    a.peers = p->xchg ? p->peers : nullptr; a.norm_off = (long)(p->offN + 8 * (size_t)c->rank); a.nflag_off = (long)p->offF + 8;
+    a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase;
     a.cta_tab = p->ctaTab;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc; a.tile_h = p->tileH;
 #define CALL(NT_, KS_) \
@@ -385,7 +397,7 @@ static int launch_admm(tritd_problem* p) {
 constexpr int kGramSlices = 8;     // row slices of k_upd's Gram phase
 static int gram_slices(int n) { return std::max(1, std::min(kGramSlices, (n + 63) / 64)); }
 
-enum UpdSrc { kSrcDirect = 0, kSrcPartF = 1, kSrcPB = 2, kSrcPC = 3 };
+enum UpdSrc { kSrcDirect = 0, kSrcPartF = 1, kSrcPB = 2, kSrcPC = 3, kSrcBoxA = 4, kSrcBoxB = 5 };
 
 static int launch_upd(tritd_problem* p, int which, int src, bool apply, const double* rhs_direct, double* rhs_out,
                       const double* S1, const double* S2, double alpha, double* X, double* XT, int n, double* S_out) {
@@ -402,9 +414,28 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
             break;
         case kSrcPB: a.v = p->P; a.stride = (long)p->n2 * RS; a.count = p->n3; a.w = p->C3; a.wstride = RS; a.wpr = 8; break;
         case kSrcPC: a.v = p->P; a.stride = RS; a.count = p->n2; a.row_stride = (long)p->n2 * RS; a.w = p->B2; a.wstride = RS; a.wpr = 8; break;
+        // the all-reduced RHS = sum over the ranks' mailbox slots, in rank order
+        case kSrcBoxA: a.v = p->box; a.stride = (long)p->slotA; a.count = c->nranks; break;
+        case kSrcBoxB: a.v = p->box + p->offB; a.stride = (long)p->slotB; a.count = c->nranks; break;
         default: return fail(TRITD_ERR_INVALID, "bad update source");
     }
     a.S1 = S1; a.S2 = S2; a.alpha = alpha; a.gr = gram_slices(n);
+    a.ns2 = 1; a.s2stride = 0;
+    if (p->xchg) {
+        // C3'C3 lives in the exchange mailbox as per-rank partials behind the RHS_A slots
+        if (S2 == p->bufA + (size_t)p->n1 * p->RS) { a.S2 = p->box + (size_t)p->n1 * p->RS; a.ns2 = c->nranks; a.s2stride = (long)p->slotA; }
+        if (!apply) {        // producer: rows (and, for exchange 0, the local C3'C3) go straight into the mailboxes
+            const int ex = which;               // exchange 0 = update A, 1 = update B
+            a.peers = p->peers; a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase;
+            a.push_off = (long)((ex == 0 ? 0 : p->offB) + (ex == 0 ? p->slotA : p->slotB) * c->rank);
+            a.pflag_off = (long)p->offF + 4 * ex;
+            if (ex == 0) { a.extra_src = p->bufA + (size_t)p->n1 * p->RS; a.extra_off = (long)p->n1 * p->RS; a.extra_n = p->RS * p->RS; }
+        }
+        if (src == kSrcBoxA || src == kSrcBoxB) {
+            a.xflags = reinterpret_cast<const unsigned*>(p->box + p->offF) + (src == kSrcBoxA ? 0 : 8);
+            a.xn = c->nranks; a.xbase = p->xbase;
+        }
+    }
     a.gram_part = p->gpart + (size_t)which * kGramSlices * p->RS * p->RS; a.gram_cnt = p->flags + 16 + 64 * which;
     a.Minv = p->Minv + (size_t)which * p->RS * p->RS;
     a.rhs_out = rhs_out; a.X = X; a.XT = XT; a.gram_out = S_out;
@@ -425,6 +456,70 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
     return TRITD_OK;
 }
 
+// Push `n` doubles of a local partial into this rank's slot of every rank's mailbox and raise the flag of
+// exchange `which` (0 = [RHS_A ; C3'C3], 1 = RHS_B, 2 = residual sums) there.
+static int launch_push(tritd_problem* p, int which, const double* src, size_t n) {
+    tritd_ctx* c = p->ctx;
+    XchgPushArgs a;
+    a.src = src; a.n = (long)n; a.peers = p->peers;
+    const size_t region = which == 0 ? 0 : (which == 1 ? p->offB : p->offN);
+    const size_t slot = which == 0 ? p->slotA : (which == 1 ? p->slotB : 8);
+    a.dst_off = (long)(region + slot * c->rank);
+    a.flag_off = (long)p->offF + 4 * which;       // flag rows of 8 u32 (= 4 doubles) per exchange
+    a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase; a.st = p->st; a.ticket = p->flags + 13;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(16, (n / 2 + 1023) / 1024));
+    k_xchg_push<<<grid, 256, 0, c->stream>>>(a);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+// Map every rank's mailbox (CUDA IPC handles exchanged through NCCL once per problem).
+static int setup_exchange(tritd_problem* p) {
+    tritd_ctx* c = p->ctx;
+    const int nr = c->nranks;
+    p->xchg = false;
+    if (nr < 2 || nr > 8 || getenv("TRITD_XCHG_NCCL")) return TRITD_OK;       // NCCL all-reduces instead
+    const size_t RS = p->RS;
+    p->slotA = (size_t)p->n1 * RS + RS * RS;
+    p->slotB = (size_t)p->n2 * RS;
+    p->offB = p->slotA * nr;
+    p->offN = p->offB + p->slotB * nr;
+    p->offF = p->offN + (size_t)8 * nr;
+    p->box_doubles = p->offF + 64;                  // 3 flag rows of 8 u32
+    int s = dalloc(p, &p->box, p->box_doubles);
+    if (s != TRITD_OK) return s;
+    CU_TRY(cudaMemsetAsync(p->box, 0, p->box_doubles * 8, c->stream));
+    cudaIpcMemHandle_t mine;
+    CU_TRY(cudaIpcGetMemHandle(&mine, p->box));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    unsigned char* hdev = nullptr;
+    if ((s = dalloc(p, &hdev, (size_t)64 * (nr + 1))) != TRITD_OK) return s;
+    CU_TRY(cudaMemcpyAsync(hdev + 64 * nr, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(g_nccl.AllGather(hdev + 64 * nr, hdev, 64, ncclChar, c->comm, c->stream));
+    std::vector<cudaIpcMemHandle_t> all(nr);
+    CU_TRY(cudaMemcpyAsync(all.data(), hdev, (size_t)64 * nr, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<double*> bases(nr, nullptr);
+    p->peer_map.assign(nr, nullptr);
+    for (int r = 0; r < nr; ++r) {
+        if (r == c->rank) { bases[r] = p->box; continue; }
+        void* q = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(TRITD_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (set TRITD_XCHG_NCCL=1 to use NCCL all-reduces)", r,
+                        cudaGetErrorString(e));
+        }
+        p->peer_map[r] = q;
+        bases[r] = (double*)q;
+    }
+    if ((s = dalloc(p, &p->peers, (size_t)nr)) != TRITD_OK) return s;
+    CU_TRY(cudaMemcpy(p->peers, bases.data(), sizeof(double*) * nr, cudaMemcpyHostToDevice));
+    p->xchg = true;
+    return TRITD_OK;
+}
+
 static int launch_small_gram(tritd_problem* p, const double* X, int n, double* S) {
     tritd_ctx* c = p->ctx;
     k_small_gram<<<(p->RS * p->RS + 255) / 256, 256, 0, c->stream>>>(X, n, p->RS, S, &p->st->stop);
@@ -437,6 +532,7 @@ extern "C" void tritd_problem_destroy(tritd_problem* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
+    for (void* q : p->peer_map) if (q) cudaIpcCloseMemHandle(q);
     for (void* q : p->allocs) cudaFree(q);
     for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
     if (p->graph) cudaGraphExecDestroy(p->graph);
@@ -596,6 +692,7 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         if ((s = make_map(c, &p->mapA1T, p->A1T, 2, dims2, str2, box2)) != TRITD_OK) return bail(s);
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) return bail(fail(TRITD_ERR_CUDA, "sync failed"));
+    if ((s = setup_exchange(p)) != TRITD_OK) return bail(s);
     *out = p;
     return TRITD_OK;
 }
@@ -720,6 +817,8 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
     ST_TRY(launch_small_gram(p, p->B2, p->n2, p->SB));
     ST_TRY(launch_small_gram(p, p->C3, p->n3, p->bufA + (size_t)p->n1 * p->RS));
     CU_TRY(cudaStreamSynchronize(st));
+    p->xbase = c->xepoch;                 // epochs of this solve: xbase + 1 .. xbase + maxIter (same on every rank)
+    c->xepoch += (unsigned)o->maxIter + 1u;
     p->initialized = true;
     p->rhsA_ready = false;
     p->graph_off = getenv("TRITD_NO_GRAPH") != nullptr;
@@ -748,13 +847,16 @@ static int enqueue_iteration(tritd_problem* p) {
     // update_A (:73-81): RHS = X1*F', Gram = (B2'B2) o (C3'C3) + lambda2*I.  From the second iteration on the
     // previous k_admm left per-CTA partials of X1*F' (accumulated from registers); single rank: k_upd sums them,
     // applies the inverse and forms A1'A1 in one launch.
+    const bool xc = p->xchg;             // N>1: partials travel through the peer mailboxes (else NCCL all-reduces)
+    const size_t nA = (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS;
     const bool direct_A = !p->rhsA_ready || multi;
     if (!p->rhsA_ready) ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, rhsA));
     else if (multi) ST_TRY(launch_upd(p, 0, kSrcPartF, false, nullptr, rhsA, nullptr, nullptr, 0.0, nullptr, nullptr, p->n1, nullptr));
     ST_TRY(mark());
-    ST_TRY(allreduce_sum(c, p->bufA, (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS));
-    ST_TRY(launch_upd(p, 0, direct_A ? kSrcDirect : kSrcPartF, true, rhsA, nullptr, p->SB, SC, p->opts.lambda2, p->A1, p->A1T,
-                      p->n1, p->SA));
+    if (xc) { if (!p->rhsA_ready) ST_TRY(launch_push(p, 0, p->bufA, nA)); }     // later iterations: k_upd pushed its rows itself
+    else ST_TRY(allreduce_sum(c, p->bufA, nA));
+    ST_TRY(launch_upd(p, 0, xc ? kSrcBoxA : (direct_A ? kSrcDirect : kSrcPartF), true, rhsA, nullptr, p->SB, SC, p->opts.lambda2, p->A1,
+                      p->A1T, p->n1, p->SA));
     ST_TRY(mark());
 
     // update_B (:83-88) with the new A: RHS = X2*G' = sum_t C3(t,:) .* P(t,j,:), Gram = (A1'A1) o (C3'C3) + lambda2*I
@@ -762,13 +864,13 @@ static int enqueue_iteration(tritd_problem* p) {
     ST_TRY(mark());
     if (multi) {
         ST_TRY(launch_upd(p, 1, kSrcPB, false, nullptr, p->rhsB, nullptr, nullptr, 0.0, nullptr, nullptr, p->n2, nullptr));
-        ST_TRY(allreduce_sum(c, p->rhsB, (size_t)p->n2 * p->RS));
+        if (!xc) ST_TRY(allreduce_sum(c, p->rhsB, (size_t)p->n2 * p->RS));
     }
-    ST_TRY(launch_upd(p, 1, multi ? kSrcDirect : kSrcPB, true, p->rhsB, nullptr, p->SA, SC, p->opts.lambda2, p->B2, nullptr,
-                      p->n2, p->SB));
+    ST_TRY(launch_upd(p, 1, xc ? kSrcBoxB : (multi ? kSrcDirect : kSrcPB), true, p->rhsB, nullptr, p->SA, SC, p->opts.lambda2, p->B2,
+                      nullptr, p->n2, p->SB));
 
     // update_C (:90-95) with the new A, B: slice-local; ridge fixed at 1e-9.  Leaves SC = C3'C3 over the local
-    // slices in bufA, where the next all-reduce sums it over the ranks.
+    // slices in bufA, where the next exchange sums it over the ranks.
     ST_TRY(launch_upd(p, 2, kSrcPC, true, nullptr, nullptr, p->SA, p->SB, 1e-9, p->C3, nullptr, p->n3, SC));
 
     ST_TRY(mark());
@@ -776,7 +878,12 @@ static int enqueue_iteration(tritd_problem* p) {
     ST_TRY(launch_admm(p));
     p->rhsA_ready = true;
     ST_TRY(mark());
-    if (multi) {
+    if (xc) {
+        k_finalize_xchg<<<1, 32, 0, st>>>(p->st, p->box + p->offN, reinterpret_cast<const unsigned*>(p->box + p->offF) + 16,
+                                         c->nranks, p->xbase, p->errHist, p->errL, p->errO);
+        CU_TRY(cudaGetLastError());
+        c->launches += 1;
+    } else if (multi) {
         ST_TRY(allreduce_sum(c, p->norms, 2));
         k_finalize<<<1, 256, 0, st>>>(p->st, p->norm_part, p->gridA, p->norms, 1, p->errHist, p->errL, p->errO);
         CU_TRY(cudaGetLastError());
