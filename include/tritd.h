@@ -171,6 +171,18 @@ int tritd_problem_phase_ms(tritd_problem* p, double* ms_out, int32_t* iters_out)
 /* Number of kernels launched by this library on this context so far. */
 int64_t tritd_launch_count(const tritd_ctx* ctx);
 
+/* ---- the ALS solver -------------------------------- */
+
+/* [A,B,C,errHist] = triple_decomp_ALS(X, r, opts)      triple_decomp_ALS.m:1-40
+ * opts fields used by the reference: maxIter, tol (:2-3).  The relative error ||X - Xhat|| / ||X|| is taken
+ * BEFORE the updates of an iteration (:15-16); when the relative-change rule fires (:20-23) the updates of that
+ * iteration are skipped; all three ridge terms are 1e-9 (:27,:32,:37).  The reference prints
+ * "Iteration %d, relative error = %.4e" every 5th iteration unconditionally (:17-19); here only when disp != 0.
+ * Initial factors are injected like in tritd_admm_f64.  Single-rank contexts only. */
+int tritd_als_f64(tritd_ctx* ctx, const double* X_host, int64_t n1, int64_t n2, int64_t n3, int r, int32_t maxIter,
+                  double tol, int32_t disp, const double* A0, const double* B0, const double* C0,
+                  double* A, double* B, double* C, double* errHist, int32_t* iters_out);
+
 /* ---- standalone L2 helpers (host pointers, MATLAB shapes) --------------- */
 
 /* Xhat = triple_product(A,B,C)                      triple_product.m:1-8   */
@@ -186,6 +198,13 @@ int tritd_buildG_f64(tritd_ctx* ctx, const double* A, const double* C, int64_t n
 int tritd_buildH_f64(tritd_ctx* ctx, const double* A, const double* B, int64_t n1, int64_t n2, int r, double* H);
 /* O = soft_threshold(X, lam), n elements            soft_threshold.m:2     */
 int tritd_soft_threshold_f64(tritd_ctx* ctx, const double* X, int64_t n, double lam, double* out);
+/* [rmse, nrmse] = evaluate(Xhat, gt, mask) of the reference's drivers (traffic_triple_comparison.m:194-202) with
+ * Xhat = triple_product(A,B,C) formed on the device (the reconstruction never crosses PCIe).
+ * gt: dense n1 x n2 x n3 ground truth (entries outside the mask are ignored); mask: dense n1 x n2 x n3 bytes
+ * (non-zero = evaluated) or NULL for all entries, which gives the drivers' RRE ||Xhat - gt|| / ||gt||. */
+int tritd_evaluate_f64(tritd_ctx* ctx, const double* A, const double* B, const double* C, int64_t n1, int64_t n2,
+                       int64_t n3, int r, const double* gt_host, const unsigned char* mask_host, double* rmse,
+                       double* nrmse);
 /* The three contractions of one sweep at fixed factors (what update_A/B/C feed to pinv):
  * rhsA = X1*F' (n1 x r^2), rhsB = X2*G' (n2 x r^2), rhsC = X3*H' (n3 x r^2), column-major. */
 int tritd_mttkrp_f64(tritd_ctx* ctx, const double* X, const double* A, const double* B, const double* C,

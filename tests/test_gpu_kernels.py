@@ -5,6 +5,7 @@ import pytest
 import tritd
 import tritd_oracle as orc
 from conftest import rel_err
+from tritd import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -76,3 +77,19 @@ def test_unsupported_rank_is_an_error():
     with pytest.raises(tritd.TritdError) as ei:
         tritd.triple_product(A, B, C)
     assert ei.value.code == 5
+
+
+@pytest.mark.parametrize("shape,r", [((37, 29, 11), 3), ((64, 50, 20), 5)])
+def test_evaluate_on_device(shape, r):
+    """evaluate() of the drivers (traffic_triple_comparison.m:194-202) on the device = numpy on the oracle's reconstruction."""
+    rng = np.random.default_rng(5)
+    A0, B0, C0 = synth.init_factors(*shape, r, 6)
+    gt = np.asfortranarray(rng.standard_normal(shape))
+    Xhat = orc.triple_product(A0, B0, C0)
+    rmse, nrmse = tritd.evaluate(A0, B0, C0, gt)
+    ref = np.linalg.norm((Xhat - gt).ravel())
+    assert abs(rmse - ref) < 1e-11 * ref and abs(nrmse - ref / np.linalg.norm(gt.ravel())) < 1e-11 * nrmse
+    mask = rng.random(shape) < 0.3
+    rmse, nrmse = tritd.evaluate(A0, B0, C0, gt, mask)
+    ref = np.linalg.norm(Xhat[mask] - gt[mask])
+    assert abs(rmse - ref) < 1e-11 * ref and abs(nrmse - ref / np.linalg.norm(gt[mask])) < 1e-11 * nrmse

@@ -47,4 +47,23 @@ __global__ void __launch_bounds__(256) k_soft_threshold(const double* x, double*
     }
 }
 
+// evaluate() of the reference's drivers (traffic_triple_comparison.m:194-202): per-CTA partials of
+//   sum_{mask} (Xhat - gt)^2  and  sum_{mask} gt^2   over padded column-major arrays (ld1 rows per column);
+// mask is dense n1 x n2 x n3 bytes (nullptr = all true).  Fixed-order partial sums (deterministic).
+__global__ void __launch_bounds__(256) k_evaluate(const double* __restrict__ Xhat, const double* __restrict__ gt,
+                                                  const unsigned char* __restrict__ mask, int n1, int ld1, size_t ncols,
+                                                  double* part) {
+    __shared__ double red[64];
+    double a = 0.0, b = 0.0;
+    for (size_t col = blockIdx.x; col < ncols; col += gridDim.x)
+        for (int i = threadIdx.x; i < n1; i += 256) {
+            if (mask && !mask[col * (size_t)n1 + i]) continue;
+            const double g = gt[col * (size_t)ld1 + i], d = Xhat[col * (size_t)ld1 + i] - g;
+            a = fma(d, d, a);
+            b = fma(g, g, b);
+        }
+    block_sum2(a, b, red);
+    if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
+}
+
 }  // namespace tritd

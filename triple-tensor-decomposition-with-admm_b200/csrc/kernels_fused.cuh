@@ -74,7 +74,7 @@ template <int KS> struct FusedCfg {
 template <int KS, int MODE>
 __global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const FusedArgs a) {
     constexpr int PL = FusedCfg<KS>::PL;
-    if (MODE == 0 && a.st->stop) return;
+    if (MODE != 1 && a.st->stop) return;
     __shared__ double B2s[32 * PL];
     __shared__ double red[64];
     __shared__ IterState prm_s;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const F
             const int j = jc * 32 + jg * 8 + 2 * tig + c;
             const bool ok = i_ok && j < a.n2;
             const size_t off = ((size_t)t * a.n2 + j) * a.ld1 + i0;
-            b.d[c] = ok ? ldg_stream2(a.D + off) : make_double2(0.0, 0.0);
+            if (MODE != 1) b.d[c] = ok ? ldg_stream2(a.D + off) : make_double2(0.0, 0.0);
             if (MODE == 0) {
                 b.yl[c] = ok ? ldg_stream2(a.YL + off) : make_double2(0.0, 0.0);
                 b.e[c] = ok ? ldg_stream2(a.E + off) : make_double2(0.0, 0.0);
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const F
     double sL = 0.0, sO = 0.0;
     int cur_jc = -1;
     Buf cur, nxt;
-    if (MODE == 0 && v0 < v1) load(cur, v0, 0);
+    if (MODE != 1 && v0 < v1) load(cur, v0, 0);
 
     for (long v = v0; v < v1; ++v) {
         const int jc = (int)(v / a.n3), t = (int)(v - (long)jc * a.n3);
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const F
 
 #pragma unroll
         for (int jg = 0; jg < 4; ++jg) {
-            if (MODE == 0) {
+            if (MODE != 1) {
                 if (jg < 3) load(nxt, v, jg + 1);
                 else if (v + 1 < v1) load(nxt, v + 1, 0);
             }
@@ -158,6 +158,10 @@ __global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const F
                 const size_t off = ((size_t)t * a.n2 + j) * a.ld1 + i0;
                 if (MODE == 1) {
                     stg_stream2(a.O + off, make_double2(l[0][c], l[1][c]));
+                } else if (MODE == 2) {                 // sum((X - Xhat).^2) only (triple_decomp_ALS.m:15-16)
+                    const double e0 = __dsub_rn(cur.d[c].x, l[0][c]), e1 = __dsub_rn(cur.d[c].y, l[1][c]);
+                    sL = fma(e0, e0, sL);
+                    sL = fma(e1, e1, sL);
                 } else {
                     double2 o, tn;
                     admm_point(prm_s, cur.d[c].x, l[0][c], cur.yl[c].x, cur.e[c].x, cur.yo[c].x, o.x, tn.x, sL, sO);
@@ -169,10 +173,10 @@ __global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const F
                     stg_stream2(a.T + off, tn);
                 }
             }
-            if (MODE == 0) cur = nxt;
+            if (MODE != 1) cur = nxt;
         }
     }
-    if (MODE == 0) {
+    if (MODE != 1) {
         block_sum2(sL, sO, red);
         if (threadIdx.x == 0) { a.norm_part[2 * blockIdx.x] = sL; a.norm_part[2 * blockIdx.x + 1] = sO; }
     }
@@ -227,6 +231,23 @@ __global__ void __launch_bounds__(256) k_finalize(IterState* st, const double* p
     if (threadIdx.x != 0) return;
     if (reduced) { a = norms[0]; b = norms[1]; }
     iter_finalize(st, a, b, errHist, errL, errO);
+}
+
+// ALS (triple_decomp_ALS.m:14-22): errHist(k) = ||X - Xhat|| / ||X|| with the factors BEFORE the updates of
+// iteration k, then the relative-change stopping rule; when it fires the update kernels of this iteration see
+// the stop flag and do nothing, exactly like the reference's `break` before the updates.
+__global__ void __launch_bounds__(256) k_finalize_als(IterState* st, const double* part, int npart, double* errHist) {
+    if (st->stop) return;
+    __shared__ double red[64];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < npart; i += 256) a += part[2 * i];
+    block_sum2(a, b, red);
+    if (threadIdx.x != 0) return;
+    const int k = st->k;
+    errHist[k] = sqrt(a) / st->normD;
+    st->k = k + 1;
+    if (k >= 1 && fabs(errHist[k] - errHist[k - 1]) < st->tol * errHist[k - 1]) st->stop = 1;
+    if (st->status != 0) st->stop = 1;
 }
 
 // O of the last finished iteration, recovered from the state the iteration keeps:

@@ -363,6 +363,7 @@ static int launch_fused(tritd_problem* p, int mode, double* Lout) {
     a.n_it = p->n_it; a.n_jc = p->n_jc; a.gi = p->gi;
 #define CALL(NT_, KS_)                                                              \
     if (mode == 0) k_fused<KS_, 0><<<p->gridF, 256, 0, c->stream>>>(a);             \
+    else if (mode == 2) k_fused<KS_, 2><<<p->gridF, 256, 0, c->stream>>>(a);        \
     else k_fused<KS_, 1><<<p->gridF, 256, 0, c->stream>>>(a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
@@ -1146,6 +1147,69 @@ static int check_r(int r) {
     return TRITD_OK;
 }
 
+// ---------------------------------------------------------------------------
+// [A,B,C,errHist] = triple_decomp_ALS(X, r, opts)    (fast_robust_triple_tensor/triple_decomp_ALS.m:1-40)
+// The same kernels as the ADMM sweep with the target fixed at X and the ridge 1e-9 in all three updates; the
+// relative error is evaluated BEFORE the updates of an iteration (:15-16) and the stopping rule (:20-23)
+// skips them.  Single rank.
+// ---------------------------------------------------------------------------
+static int als_iteration(tritd_problem* p) {
+    tritd_ctx* c = p->ctx;
+    double* rhsA = p->bufA;
+    double* SC = p->bufA + (size_t)p->n1 * p->RS;
+    ST_TRY(launch_fused(p, 2, nullptr));                                   // sum((X - Xhat).^2) partials
+    k_finalize_als<<<1, 256, 0, c->stream>>>(p->st, p->norm_part, p->gridF, p->errHist);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, rhsA));                // X1*F'
+    ST_TRY(launch_upd(p, 0, kSrcDirect, true, rhsA, nullptr, p->SB, SC, 1e-9, p->A1, p->A1T, p->n1, p->SA));
+    ST_TRY(launch_ppass(p, p->mapT));
+    ST_TRY(launch_upd(p, 1, kSrcPB, true, nullptr, nullptr, p->SA, SC, 1e-9, p->B2, nullptr, p->n2, p->SB));
+    ST_TRY(launch_upd(p, 2, kSrcPC, true, nullptr, nullptr, p->SA, p->SB, 1e-9, p->C3, nullptr, p->n3, SC));
+    return TRITD_OK;
+}
+
+extern "C" int tritd_als_f64(tritd_ctx* c, const double* X_host, int64_t n1, int64_t n2, int64_t n3, int r, int32_t maxIter,
+                             double tol, int32_t disp, const double* A0, const double* B0, const double* C0, double* A,
+                             double* B, double* C, double* errHist, int32_t* iters_out) {
+    if (!c || !X_host || !A0 || !B0 || !C0 || !errHist) return fail(TRITD_ERR_INVALID, "NULL argument");
+    if (c->nranks != 1) return fail(TRITD_ERR_UNSUPPORTED, "triple_decomp_ALS runs on a single-rank context");
+    if (maxIter < 1) return fail(TRITD_ERR_INVALID, "opts.maxIter = %d", maxIter);
+    tritd_problem* p = nullptr;
+    ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
+    auto bail = [&](int code) { tritd_problem_destroy(p); return code; };
+    int s;
+    if ((s = tritd_problem_set_D_host(p, X_host)) != TRITD_OK) return bail(s);
+    // the ADMM state set-up also gives what ALS needs: T = X, ||X||, the small Grams of the initial factors
+    tritd_opts o;
+    memset(&o, 0, sizeof(o));
+    o.mu = 1.0; o.rho = 1.0; o.lambda_ = 0.0; o.lambda2 = 1e-9; o.tol = tol; o.maxIter = maxIter; o.disp = 0;
+    if ((s = tritd_problem_init(p, &o, A0, B0, C0)) != TRITD_OK) return bail(s);
+    int done = 0, printed = 0;
+    std::vector<double> eh(maxIter);
+    while (done < maxIter && !p->st_host->stop) {
+        const int batch = std::min(maxIter - done, 5);            // the reference prints every 5th iteration
+        for (int i = 0; i < batch; ++i)
+            if ((s = als_iteration(p)) != TRITD_OK) return bail(s);
+        if ((s = fetch_state(p)) != TRITD_OK) return bail(s);
+        done = p->st_host->k;
+        if (disp) {
+            if (cudaMemcpy(eh.data(), p->errHist, sizeof(double) * done, cudaMemcpyDeviceToHost) != cudaSuccess)
+                return bail(fail(TRITD_ERR_CUDA, "errHist copy failed"));
+            for (int k = printed + 1; k <= done; ++k)
+                if (k % 5 == 0) printf("Iteration %d, relative error = %.4e\n", k, eh[k - 1]);
+            printed = done;
+            fflush(stdout);
+        }
+        if (p->st_host->stop) break;
+    }
+    if (p->st_host->status != 0) return bail(fail(TRITD_ERR_NUMERIC, "ridge system not positive definite (ALS iteration %d)", done));
+    s = tritd_problem_get(p, A, B, C, nullptr, nullptr, errHist, nullptr, nullptr, nullptr);
+    if (iters_out) *iters_out = done;
+    tritd_problem_destroy(p);
+    return s;
+}
+
 extern "C" int tritd_triple_product_f64(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1,
                                         int64_t n2, int64_t n3, int r, double* Xhat) {
     if (!c || !A || !B || !C || !Xhat) return fail(TRITD_ERR_INVALID, "NULL argument");
@@ -1161,6 +1225,45 @@ extern "C" int tritd_triple_product_f64(tritd_ctx* c, const double* A, const dou
     if (s == TRITD_OK && cudaGetLastError() != cudaSuccess) s = fail(TRITD_ERR_CUDA, "triple_product kernel failed");
     tritd_problem_destroy(p);
     return s;
+}
+
+// [rmse, nrmse] = evaluate(Xhat, gt, mask) with Xhat = triple_product(A,B,C) formed on the device
+// (traffic_triple_comparison.m:194-202; the drivers' RRE).  gt is a dense n1 x n2 x n3 tensor (entries outside the
+// mask are ignored), mask dense bytes or NULL (all true): the reconstruction never crosses PCIe.
+extern "C" int tritd_evaluate_f64(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1, int64_t n2,
+                                  int64_t n3, int r, const double* gt_host, const unsigned char* mask_host, double* rmse,
+                                  double* nrmse) {
+    if (!c || !A || !B || !C || !gt_host) return fail(TRITD_ERR_INVALID, "NULL argument");
+    ST_TRY(check_r(r));
+    tritd_problem* p = nullptr;
+    ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
+    int s = upload_factors(p, A, B, C);
+    double* Lbuf = nullptr;
+    unsigned char* mdev = nullptr;
+    const size_t N = (size_t)n1 * n2 * n3;
+    double sums[2] = {0.0, 0.0};
+    if (s == TRITD_OK) s = reconstruct_L(p, &Lbuf);
+    if (s == TRITD_OK) s = copy_in(p, p->D, gt_host);
+    if (s == TRITD_OK && mask_host) {
+        if (cudaMalloc((void**)&mdev, N) != cudaSuccess) s = fail(TRITD_ERR_CUDA, "cudaMalloc(mask) failed");
+        else if (cudaMemcpyAsync(mdev, mask_host, N, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) s = fail(TRITD_ERR_CUDA, "mask copy failed");
+    }
+    if (s == TRITD_OK) {
+        k_evaluate<<<1024, 256, 0, c->stream>>>(Lbuf, p->D, mdev, p->n1, p->ld1, (size_t)p->n2 * p->n3, p->norm_part);
+        k_sum_pairs<<<1, 256, 0, c->stream>>>(p->norm_part, 1024, p->norms, nullptr);
+        c->launches += 2;
+        if (cudaMemcpyAsync(sums, p->norms, 16, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess)
+            s = fail(TRITD_ERR_CUDA, "evaluate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaStreamSynchronize(c->stream);
+    if (Lbuf) cudaFree(Lbuf);
+    if (mdev) cudaFree(mdev);
+    tritd_problem_destroy(p);
+    if (s != TRITD_OK) return s;
+    if (rmse) *rmse = sqrt(sums[0]);
+    if (nrmse) *nrmse = sqrt(sums[0]) / sqrt(sums[1]);
+    return TRITD_OK;
 }
 
 extern "C" int tritd_unfold_f64(tritd_ctx* c, const double* X, int64_t n1, int64_t n2, int64_t n3, int mode, double* Xn) {

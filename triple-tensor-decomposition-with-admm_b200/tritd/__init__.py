@@ -67,6 +67,10 @@ SYMBOLS = {
     "tritd_admm_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int, C.POINTER(tritd_opts), _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), C.POINTER(tritd_timing)]),
     "tritd_trim": (C.c_int, [_vp]),
+    "tritd_evaluate_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, C.c_int, _vp, _vp, C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double)]),
+    "tritd_als_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int32, C.c_double, C.c_int32, _vp, _vp, _vp,
+                                _vp, _vp, _vp, _vp, C.POINTER(C.c_int32)]),
     "tritd_problem_create": (C.c_int, [_vp, _i64, _i64, _i64, C.c_int, C.POINTER(_vp)]),
     "tritd_problem_destroy": (None, [_vp]),
     "tritd_problem_set_D_host": (C.c_int, [_vp, _vp]),
@@ -331,6 +335,45 @@ def triple_decomp_ADMM(D, r, opts, A0=None, B0=None, C0=None, rng=None, ctx=None
     return A, B, Cc, O, errHist
 
 
+def triple_decomp_ALS(X, r, opts, A0=None, B0=None, C0=None, rng=None, ctx=None, disp=None):
+    """[A,B,C,errHist] = triple_decomp_ALS(X, r, opts)   (triple_decomp_ALS.m:1-40).
+
+    ``opts`` needs ``maxIter`` and ``tol`` (:2-3; a missing one raises the reference's
+    ``Unrecognized field name``).  The reference prints its progress line every 5th iteration
+    unconditionally (:17-19); pass ``disp=False`` (or ``opts['disp'] = 0``) to silence it.
+    Initial factors: as in :func:`triple_decomp_ADMM`."""
+    X = np.asarray(X)
+    if X.ndim == 2:
+        X = X[:, :, None]
+    if X.ndim != 3:
+        raise ValueError("X must be a 3-D array")
+    if np.iscomplexobj(X):
+        raise TypeError("X must be real")
+    r = int(r)
+    if r < 1:
+        raise ValueError("r must be a positive integer")
+    for f in ("maxIter", "tol"):
+        if f not in opts:
+            raise KeyError('Unrecognized field name "%s".' % f)
+    maxIter, tol = int(opts["maxIter"]), float(opts["tol"])
+    if disp is None:
+        disp = bool(opts.get("disp", 1))
+    X = _f64(X)
+    n1, n2, n3 = X.shape
+    A0 = opts.get("A0", A0); B0 = opts.get("B0", B0); C0 = opts.get("C0", C0)
+    if A0 is None or B0 is None or C0 is None:
+        rng = rng or np.random.default_rng(0)
+        A0 = rng.standard_normal((n1, r, r)); B0 = rng.standard_normal((r, n2, r)); C0 = rng.standard_normal((r, r, n3))
+    A0 = _f64(A0, (n1, r, r)); B0 = _f64(B0, (r, n2, r)); C0 = _f64(C0, (r, r, n3))
+    ctx = ctx or default_context()
+    A = np.zeros((n1, r, r), order="F"); B = np.zeros((r, n2, r), order="F"); Cc = np.zeros((r, r, n3), order="F")
+    errHist = np.zeros(max(maxIter, 1))
+    k = C.c_int32()
+    _check(load_library().tritd_als_f64(ctx._h, _ptr(X), n1, n2, n3, r, maxIter, tol, int(bool(disp)), _ptr(A0), _ptr(B0),
+                                        _ptr(C0), _ptr(A), _ptr(B), _ptr(Cc), _ptr(errHist), C.byref(k)))
+    return A, B, Cc, errHist[:k.value].copy()
+
+
 def _factor_dims(A=None, B=None, Cc=None):
     r = None
     if A is not None:
@@ -359,6 +402,25 @@ def triple_product(A, B, Cc, ctx=None):
     ctx = ctx or default_context()
     _check(load_library().tritd_triple_product_f64(ctx._h, _ptr(A), _ptr(B), _ptr(Cc), n1, n2, n3, r, _ptr(X)))
     return X
+
+
+def evaluate(A, B, Cc, gt, mask=None, ctx=None):
+    """[rmse, nrmse] = evaluate(triple_product(A,B,C), gt(mask), mask)   (traffic_triple_comparison.m:194-202), with the
+    reconstruction formed and compared on the device.  ``gt`` is the dense ground-truth tensor, ``mask`` a boolean
+    tensor of the same shape (None = every entry, i.e. the drivers' RRE)."""
+    A, B, Cc, r = _factor_dims(A, B, Cc)
+    n1, n2, n3 = A.shape[0], B.shape[1], Cc.shape[2]
+    gt = _f64(gt, (n1, n2, n3))
+    m = None
+    if mask is not None:
+        m = np.asfortranarray(np.asarray(mask).astype(bool), dtype=np.uint8)
+        if m.shape != (n1, n2, n3):
+            raise ValueError("mask must have the shape of gt")
+    rmse, nrmse = C.c_double(), C.c_double()
+    ctx = ctx or default_context()
+    _check(load_library().tritd_evaluate_f64(ctx._h, _ptr(A), _ptr(B), _ptr(Cc), n1, n2, n3, r, _ptr(gt),
+                                             m.ctypes.data_as(_vp) if m is not None else None, C.byref(rmse), C.byref(nrmse)))
+    return rmse.value, nrmse.value
 
 
 def unfold(X, mode, ctx=None):
