@@ -20,7 +20,9 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, shape, r, iters, out_dir):
+def _worker(rank, world, port, shape, r, iters, out_dir, nccl_path):
+    if nccl_path:
+        os.environ["TRITD_XCHG_NCCL"] = "1"        # NCCL all-reduces instead of the NVLink peer mailboxes
     for p in (os.path.join(ROOT, "triple-tensor-decomposition-with-admm_b200"),):
         sys.path.insert(0, p)
     import torch
@@ -47,8 +49,9 @@ def _worker(rank, world, port, shape, r, iters, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shape,r,iters", [((40, 36, 25), 5, 8), ((130, 70, 11), 4, 5)])
-def test_two_gpus_equal_one_gpu_and_oracle(shape, r, iters, tmp_path):
+@pytest.mark.parametrize("nccl_path", [False, True], ids=["peer_mailboxes", "nccl_allreduce"])
+@pytest.mark.parametrize("shape,r,iters", [((40, 36, 25), 5, 8), ((130, 70, 11), 4, 5), ((96, 80, 9), 8, 4)])
+def test_two_gpus_equal_one_gpu_and_oracle(shape, r, iters, nccl_path, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -59,7 +62,7 @@ def test_two_gpus_equal_one_gpu_and_oracle(shape, r, iters, tmp_path):
     from tritd import synth
 
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), shape, r, iters, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), shape, r, iters, str(tmp_path), nccl_path), nprocs=world, join=True)
     w = synth.make_config("cfg1", shrink=shape)
     w["A0"], w["B0"], w["C0"] = synth.init_factors(*shape, r, 77)
     o = dict(w["opts"], maxIter=iters, tol=0.0)

@@ -503,17 +503,30 @@ static int setup_exchange(tritd_problem* p) {
     CU_TRY(cudaStreamSynchronize(c->stream));
     std::vector<double*> bases(nr, nullptr);
     p->peer_map.assign(nr, nullptr);
+    int ok = 1;
     for (int r = 0; r < nr; ++r) {
         if (r == c->rank) { bases[r] = p->box; continue; }
         void* q = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return fail(TRITD_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s (set TRITD_XCHG_NCCL=1 to use NCCL all-reduces)", r,
-                        cudaGetErrorString(e));
-        }
+        if (e != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
         p->peer_map[r] = q;
         bases[r] = (double*)q;
+    }
+    // every rank must take the same path: all-reduce(min) of the success flags; if any rank could not map its peers
+    // (no peer access between the GPUs, IPC disabled in the container) all of them use the NCCL all-reduces
+    {
+        double* flag = reinterpret_cast<double*>(hdev);           // scratch, no longer needed
+        const double mine_ok = ok;
+        CU_TRY(cudaMemcpyAsync(flag, &mine_ok, 8, cudaMemcpyHostToDevice, c->stream));
+        NCCL_TRY(g_nccl.AllReduce(flag, flag, 1, ncclDouble, ncclMin, c->comm, c->stream));
+        double all_ok = 0.0;
+        CU_TRY(cudaMemcpyAsync(&all_ok, flag, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (all_ok < 0.5) {
+            for (void*& q : p->peer_map) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+            if (c->rank == 0) fprintf(stderr, "libtritd: peer mailboxes unavailable (cudaIpcOpenMemHandle failed on some rank); using NCCL all-reduces\n");
+            return TRITD_OK;
+        }
     }
     if ((s = dalloc(p, &p->peers, (size_t)nr)) != TRITD_OK) return s;
     CU_TRY(cudaMemcpy(p->peers, bases.data(), sizeof(double*) * nr, cudaMemcpyHostToDevice));

@@ -1,0 +1,110 @@
+/* MEX gateway: [A,B,C,errHist] = triple_decomp_ALS(X, r, opts)
+ *
+ * Drop-in for fast_robust_triple_tensor/triple_decomp_ALS.m:1 -- same name, same three inputs
+ * (opts.maxIter and opts.tol are the fields the reference reads, :2-3), same four outputs.  The
+ * initial factors are drawn with MATLAB's own randn in the reference's order (:8-10) unless
+ * opts.A0/B0/C0 inject them; the reference's progress line "Iteration %d, relative error = %.4e"
+ * (every 5th iteration, :17-19) is printed by the library unless opts.disp is present and zero.
+ *
+ * Build (on a machine with MATLAB + CUDA):
+ *   mex -I../../include triple_decomp_ALS.c -L../tritd -ltritd
+ * This image has neither MATLAB nor Octave: the file is syntax-checked against stub/mex.h.
+ */
+#include <string.h>
+
+#include "mex.h"
+#include "tritd.h"
+
+static tritd_ctx* g_ctx = NULL;
+
+static void at_exit(void) {
+    if (g_ctx) { tritd_destroy(g_ctx); g_ctx = NULL; }
+}
+
+static double req_field(const mxArray* opts, const char* name) {
+    const mxArray* f = mxGetField(opts, 0, name);
+    if (!f) mexErrMsgIdAndTxt("MATLAB:nonExistentField", "Unrecognized field name \"%s\".", name);
+    if (!mxIsDouble(f) && mxGetNumberOfElements(f) != 1)
+        mexErrMsgIdAndTxt("tritd:opts", "opts.%s must be a real scalar.", name);
+    return mxGetScalar(f);
+}
+
+static const double* opt_factor(const mxArray* opts, const char* name, size_t numel) {
+    const mxArray* f = mxGetField(opts, 0, name);
+    if (!f || mxIsEmpty(f)) return NULL;
+    if (!mxIsDouble(f) || mxIsComplex(f) || mxGetNumberOfElements(f) != numel)
+        mexErrMsgIdAndTxt("tritd:opts", "opts.%s has the wrong size or class.", name);
+    return mxGetPr(f);
+}
+
+static mxArray* randn3(mwSize a, mwSize b, mwSize c) {
+    mxArray* dims = mxCreateDoubleMatrix(1, 3, mxREAL);
+    mxArray* out = NULL;
+    double* d = mxGetPr(dims);
+    d[0] = (double)a; d[1] = (double)b; d[2] = (double)c;
+    if (mexCallMATLAB(1, &out, 1, &dims, "randn") != 0) mexErrMsgIdAndTxt("tritd:randn", "randn failed.");
+    mxDestroyArray(dims);
+    return out;
+}
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (nrhs != 3) mexErrMsgIdAndTxt("tritd:nargin", "Usage: [A,B,C,errHist] = triple_decomp_ALS(X, r, opts)");
+    if (nlhs > 4) mexErrMsgIdAndTxt("MATLAB:TooManyOutputs", "Too many output arguments.");
+    const mxArray* Xm = prhs[0];
+    if (!mxIsDouble(Xm) || mxIsComplex(Xm) || mxIsSparse(Xm)) mexErrMsgIdAndTxt("tritd:X", "X must be a full real double array.");
+    const mwSize nd = mxGetNumberOfDimensions(Xm);
+    const mwSize* dd = mxGetDimensions(Xm);
+    if (nd < 2 || nd > 3) mexErrMsgIdAndTxt("tritd:X", "X must be n1 x n2 x n3.");
+    const mwSize n1 = dd[0], n2 = dd[1], n3 = nd == 3 ? dd[2] : 1;
+    if (n1 == 0 || n2 == 0 || n3 == 0) mexErrMsgIdAndTxt("tritd:X", "X must not be empty.");
+    if (mxGetNumberOfElements(prhs[1]) != 1) mexErrMsgIdAndTxt("tritd:r", "r must be a scalar.");
+    const int r = (int)mxGetScalar(prhs[1]);
+    if (r < 1 || (double)r != mxGetScalar(prhs[1])) mexErrMsgIdAndTxt("tritd:r", "r must be a positive integer.");
+    if (!mxIsStruct(prhs[2])) mexErrMsgIdAndTxt("tritd:opts", "opts must be a struct.");
+    const mxArray* om = prhs[2];
+    const int32_t maxIter = (int32_t)req_field(om, "maxIter");       /* :2 */
+    const double tol = req_field(om, "tol");                          /* :3 */
+    const mxArray* dm = mxGetField(om, 0, "disp");
+    const int32_t disp = dm ? (mxGetScalar(dm) != 0.0) : 1;           /* the reference always prints */
+
+    const size_t R = (size_t)r * r;
+    mxArray *A0m = NULL, *B0m = NULL, *C0m = NULL;
+    const double* A0 = opt_factor(om, "A0", n1 * R);
+    const double* B0 = opt_factor(om, "B0", n2 * R);
+    const double* C0 = opt_factor(om, "C0", n3 * R);
+    if (!A0) { A0m = randn3(n1, r, r); A0 = mxGetPr(A0m); }            /* :8  */
+    if (!B0) { B0m = randn3(r, n2, r); B0 = mxGetPr(B0m); }            /* :9  */
+    if (!C0) { C0m = randn3(r, r, n3); C0 = mxGetPr(C0m); }            /* :10 */
+
+    if (!g_ctx) {
+        const mxArray* dv = mxGetField(om, 0, "device");
+        if (tritd_create(dv ? (int)mxGetScalar(dv) : 0, &g_ctx) != TRITD_OK)
+            mexErrMsgIdAndTxt("tritd:cuda", "%s", tritd_last_error());
+        mexLock();
+        mexAtExit(at_exit);
+    }
+
+    const mwSize dA[3] = {n1, (mwSize)r, (mwSize)r}, dB[3] = {(mwSize)r, n2, (mwSize)r}, dC[3] = {(mwSize)r, (mwSize)r, n3};
+    mxArray* Am = mxCreateNumericArray(3, dA, mxDOUBLE_CLASS, mxREAL);
+    mxArray* Bm = mxCreateNumericArray(3, dB, mxDOUBLE_CLASS, mxREAL);
+    mxArray* Cm = mxCreateNumericArray(3, dC, mxDOUBLE_CLASS, mxREAL);
+    double* eh = (double*)mxMalloc(sizeof(double) * (size_t)(maxIter > 0 ? maxIter : 1));
+    int32_t iters = 0;
+    const int st = tritd_als_f64(g_ctx, mxGetPr(Xm), (int64_t)n1, (int64_t)n2, (int64_t)n3, r, maxIter, tol, disp, A0, B0, C0,
+                                 mxGetPr(Am), mxGetPr(Bm), mxGetPr(Cm), eh, &iters);
+    if (A0m) mxDestroyArray(A0m);
+    if (B0m) mxDestroyArray(B0m);
+    if (C0m) mxDestroyArray(C0m);
+    if (st != TRITD_OK) {
+        mxFree(eh);
+        mexErrMsgIdAndTxt("tritd:solve", "%s", tritd_last_error());
+    }
+    plhs[0] = Am;
+    if (nlhs >= 2) plhs[1] = Bm; else mxDestroyArray(Bm);
+    if (nlhs >= 3) plhs[2] = Cm; else mxDestroyArray(Cm);
+    if (nlhs >= 4) {                                /* errHist(1:k) when the rule fired (:21), else all maxIter entries */
+        plhs[3] = mxCreateDoubleMatrix((mwSize)iters, 1, mxREAL);
+        memcpy(mxGetPr(plhs[3]), eh, sizeof(double) * (size_t)iters);
+    }
+    mxFree(eh);
+}
