@@ -38,6 +38,8 @@ struct AdmmArgs {
     // N>1 peer exchange (kernels_xchg.cuh): the last CTA writes the pair into this rank's slot of every mailbox
     double* const* peers;              // nullptr: pair left in norms[] (NCCL path)
     long norm_off, nflag_off;          // offsets in doubles inside a mailbox: this rank's pair / the flag row
+    const double* nslots;              // own mailbox: the ranks' pairs, 8 doubles apart
+    const unsigned* nflags;            // own mailbox: flag row of this exchange
     int rank, nranks;
     unsigned xbase;
     double* partM;                     // [grid][128][RS]: this CTA's partial of the next X1*F'
@@ -359,11 +361,21 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         else { a.norms[0] = sa; a.norms[1] = sb; red[0] = sa; red[1] = sb; }
     }
     if (!a.finalize && a.peers) {
+        // peer exchange of the residual sums by this (last) CTA: pair and flag of one mailbox come from the same
+        // thread (the release orders them); then wait for all ranks, sum in rank order -- every rank takes the same
+        // stopping decision -- and finalise the iteration
         __syncthreads();
-        if (threadIdx.x < (unsigned)a.nranks) {      // data and flag of one mailbox come from the same thread: release orders them
+        const unsigned epoch = a.xbase + (unsigned)a.st->k + 1u;
+        if (threadIdx.x < (unsigned)a.nranks) {
             double* box = a.peers[threadIdx.x];
             *reinterpret_cast<double2*>(box + a.norm_off) = make_double2(red[0], red[1]);
-            st_release_sys_u32(reinterpret_cast<unsigned*>(box + a.nflag_off) + a.rank, a.xbase + (unsigned)a.st->k + 1u);
+            st_release_sys_u32(reinterpret_cast<unsigned*>(box + a.nflag_off) + a.rank, epoch);
+        }
+        cta_wait_ranks(a.nflags, a.nranks, epoch);
+        if (threadIdx.x == 0) {
+            double ta = 0.0, tb = 0.0;
+            for (int r = 0; r < a.nranks; ++r) { ta += __ldcg(a.nslots + 8 * r); tb += __ldcg(a.nslots + 8 * r + 1); }
+            iter_finalize(a.st, ta, tb, a.errHist, a.errL, a.errO);
         }
     }
 }

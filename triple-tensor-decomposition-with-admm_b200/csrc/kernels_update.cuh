@@ -43,16 +43,20 @@ struct UpdArgs {
     const double *S1, *S2;    // [RS][RS] small Grams of the two other factors; S2 may be a stack of ns2 matrices
     int ns2;                  // (the per-rank partials of C3'C3 in the exchange mailbox), summed in order
     long s2stride;
-    const unsigned* xflags;   // N>1 peer exchange: wait until these xn flags reached epoch xbase + k + 1 before
-    int xn;                   // reading v / S2 (nullptr: no wait)
-    unsigned xbase;
-    // N>1 peer exchange, producer side (apply == 0): rows go straight into this rank's slot of every rank's
-    // mailbox; block 0 adds `extra_n` doubles (the local C3'C3) behind them; the last CTA raises the flags
-    double* const* peers;     // [nranks] mailbox bases (nullptr: rows go to rhs_out only)
-    long push_off, pflag_off; // offsets in doubles: this rank's slot / the flag row of the exchange
+    // N>1 peer exchange inside the kernel (xmerge): every row CTA writes its reduced rows into this rank's slot of every
+    // rank's mailbox (block 0 adds `extra_n` doubles, the local C3'C3, behind them), raises its flag [rank][cta]
+    // everywhere, waits for the flags [r][cta] of all ranks in the own mailbox and sums the slots in rank order.
+    int xmerge;
+    long fstride;             // flags per rank in the flag block of this exchange (>= grid size)
+    double* const* peers;     // [nranks] mailbox bases
+    long push_off, pflag_off; // offsets in doubles inside a mailbox: this rank's slot / the flag row of the exchange
     const double* extra_src;
     long extra_off;
     int extra_n, rank, nranks;
+    const unsigned* xflags;   // flag row of the exchange in the own mailbox
+    const double* xbox;       // slot 0 of the exchange region in the own mailbox
+    long xslot;               // slot stride
+    unsigned xbase;           // epoch of iteration k = xbase + k + 1
     double alpha;
     double* Minv;             // [R][RS] scratch: inv(S1 o S2 + alpha I), written by block 0
     double* rhs_out;          // apply == 0: reduced rows [n][RS]
@@ -243,6 +247,22 @@ __global__ void __launch_bounds__(256) k_small_gram(const double* X, int n, int 
 }
 
 constexpr int kUpdThreads = 256;
+
+// In-kernel exchange, CTA side.  The rows are partitioned over the CTAs identically on every rank, so CTA c only
+// needs what the CTAs c of the other ranks pushed: after its own stores into the peers' mailboxes (ordered by the
+// barrier + the system-scope release) it raises flag [rank][c] in every mailbox, then waits for the flags [r][c] of
+// all ranks r in the own mailbox.  No grid-wide step, no CTA waits for a CTA of the same grid: nothing has to be
+// co-resident.  Flags hold epochs (monotonic), so they never need a reset.
+__device__ __forceinline__ void xchg_publish_and_wait(double* const* peers, long pflag_off, long fstride, int rank, int nranks,
+                                                      const unsigned* xflags, unsigned epoch) {
+    __syncthreads();
+    if (threadIdx.x < (unsigned)nranks) {
+        st_release_sys_u32(reinterpret_cast<unsigned*>(peers[threadIdx.x] + pflag_off) + rank * fstride + blockIdx.x, epoch);
+        const unsigned* f = xflags + threadIdx.x * fstride + blockIdx.x;
+        while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) __nanosleep(40);
+    }
+    __syncthreads();
+}
 constexpr int kUpdMaxGramCtas = 64;   // CTAs that may spin in the Gram phase (<< 148 SMs x resident CTAs)
 __host__ __device__ inline size_t upd_smem_bytes(int RS) {
     const int ms = RS * RS > 64 * RS ? RS * RS : 64 * RS;      // inv(G) tile / Gram row chunk [64][RS]
@@ -270,15 +290,18 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
     }
     TRITD_STAMP(0, 0)
     TRITD_STAMP(1, 4)
-    if (a.xflags && (blockIdx.x != 0 || a.apply)) cta_wait_ranks(a.xflags, a.xn, a.xbase + (unsigned)a.st->k + 1u);
+    const unsigned epoch = a.xbase + (unsigned)a.st->k + 1u;
 
     if (blockIdx.x == 0 && !a.apply) {
-        if (!a.peers) return;
-        for (int r = 0; r < a.nranks; ++r) {
-            double* dst = a.peers[(a.rank + 1 + r) % a.nranks] + a.push_off + a.extra_off;
-            for (int e = tid; e < a.extra_n; e += kUpdThreads) dst[e] = a.extra_src[e];
-        }
+        return;
     } else if (blockIdx.x == 0) {
+        if (a.xmerge && a.extra_n > 0) {   // the local C3'C3 travels behind the RHS rows; S2 below is the stack of all ranks' partials
+            for (int r = 0; r < a.nranks; ++r) {
+                double* dst = a.peers[(a.rank + 1 + r) % a.nranks] + a.push_off + a.extra_off;
+                for (int e = tid; e < a.extra_n; e += kUpdThreads) dst[e] = a.extra_src[e];
+            }
+            xchg_publish_and_wait(a.peers, a.pflag_off, a.fstride, a.rank, a.nranks, a.xflags, epoch);
+        }
         // ---------------- the ridge system, inverted while the row CTAs reduce ----------------
         const bool bad = invert_ridge_system<PQ>(a.S1, a.S2, a.ns2, a.s2stride, a.alpha, R, RS, a.Minv, red, a.dbg);
         if (bad && tid == 0) atomicExch(&a.st->status, kStatusCholesky);
@@ -337,29 +360,35 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
                     double v = red[(warp * wpr) * 64 + k];
                     for (int s2 = 1; s2 < wpr; ++s2) v += red[(warp * wpr + s2) * 64 + k];
                     rhs_s[warp * 64 + k] = v;
-                    if (!a.apply && row0 + warp < a.n) {
-                        if (!a.peers) a.rhs_out[(size_t)(row0 + warp) * RS + k] = v;
-                        else
+                    if (row0 + warp < a.n) {
+                        if (!a.apply) a.rhs_out[(size_t)(row0 + warp) * RS + k] = v;
+                        else if (a.xmerge)
                             for (int r = 0; r < a.nranks; ++r)
                                 a.peers[(a.rank + 1 + r) % a.nranks][a.push_off + (size_t)(row0 + warp) * RS + k] = v;
                     }
                 }
             }
         }
-        if (!a.apply && !a.peers) return;
-    }
-    if (!a.apply) {
-        // producer of a peer exchange: once every CTA's stores are ordered at system scope, the last one raises
-        // this rank's flag in every mailbox
-        __shared__ int s_lastpush;
-        __syncthreads();
-        if (tid == 0) { __threadfence_system(); s_lastpush = atom_acq_rel_add_u32(&a.flags[3], 1u) == gridDim.x - 1; }
-        __syncthreads();
-        if (!s_lastpush) return;
-        if (tid < a.nranks)
-            st_release_sys_u32(reinterpret_cast<unsigned*>(a.peers[tid] + a.pflag_off) + a.rank, a.xbase + (unsigned)a.st->k + 1u);
-        if (tid == 0) a.flags[3] = 0u;
-        return;
+        if (!a.apply) return;
+        if (a.xmerge) {
+            xchg_publish_and_wait(a.peers, a.pflag_off, a.fstride, a.rank, a.nranks, a.xflags, epoch);
+            // the all-reduced rows: the ranks' slots summed in rank order (the same on every rank)
+            if (warp < rows && row0 + warp < a.n) {
+#pragma unroll
+                for (int q = 0; q < KPL; ++q) {
+                    const int k = lane + 32 * q;
+                    if (k < RS) {
+                        double t[8];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) t[r] = r < a.nranks ? __ldcg(a.xbox + r * a.xslot + (size_t)(row0 + warp) * RS + k) : 0.0;
+                        double v = t[0];
+#pragma unroll
+                        for (int r = 1; r < 8; ++r) v += t[r];
+                        rhs_s[warp * 64 + k] = v;
+                    }
+                }
+            }
+        }
     }
     if (blockIdx.x != 0) {
         const int row0 = (blockIdx.x - 1) * rows;

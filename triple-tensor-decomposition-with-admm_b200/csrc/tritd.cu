@@ -250,8 +250,8 @@ struct tritd_problem {
     double* gpart = nullptr;             // [3][kGramSlices][RS][RS] row-slice partial Grams of k_upd
     // N>1 peer exchange (kernels_xchg.cuh): local mailbox, the peers' mailboxes mapped with CUDA IPC
     bool xchg = false;
-    double* box = nullptr;               // [A: nranks x slotA | B: nranks x slotB | N: nranks x 8 | flags 3 x nranks (u32)]
-    size_t slotA = 0, slotB = 0, offB = 0, offN = 0, offF = 0, box_doubles = 0;
+    double* box = nullptr;               // [A: nranks x slotA | B: nranks x slotB | N: nranks x 8 | flags (u32)]
+    size_t slotA = 0, slotB = 0, offB = 0, offN = 0, offF = 0, box_doubles = 0, fsA = 0, fsB = 0;
     std::vector<void*> peer_map;         // cudaIpcOpenMemHandle mappings (nullptr for the own rank)
     double** peers = nullptr;            // device array [nranks] of mailbox bases
     unsigned xbase = 0;
@@ -379,7 +379,8 @@ static int launch_admm(tritd_problem* p) {
     a.A1 = p->A1; a.B2 = p->B2; a.C3 = p->C3; a.st = p->st; a.norm_part = p->norm_part; a.partM = p->partF;
     a.norms = p->norms; a.errHist = p->errHist; a.errL = p->errL; a.errO = p->errO;
     a.ticket = p->flags + 12; a.finalize = c->nranks == 1 ? 1 : 0;
-    a.peers = p->xchg ? p->peers : nullptr; a.norm_off = (long)(p->offN + 8 * (size_t)c->rank); a.nflag_off = (long)p->offF + 8;
+    a.peers = p->xchg ? p->peers : nullptr; a.norm_off = (long)(p->offN + 8 * (size_t)c->rank); a.nflag_off = (long)p->offF;
+    a.nslots = p->xchg ? p->box + p->offN : nullptr; a.nflags = p->xchg ? reinterpret_cast<const unsigned*>(p->box + p->offF) : nullptr;
     a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase;
     a.cta_tab = p->ctaTab;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc; a.tile_h = p->tileH;
@@ -398,7 +399,7 @@ static int launch_admm(tritd_problem* p) {
 constexpr int kGramSlices = 8;     // row slices of k_upd's Gram phase
 static int gram_slices(int n) { return std::max(1, std::min(kGramSlices, (n + 63) / 64)); }
 
-enum UpdSrc { kSrcDirect = 0, kSrcPartF = 1, kSrcPB = 2, kSrcPC = 3, kSrcBoxA = 4, kSrcBoxB = 5 };
+enum UpdSrc { kSrcDirect = 0, kSrcPartF = 1, kSrcPB = 2, kSrcPC = 3 };
 
 static int launch_upd(tritd_problem* p, int which, int src, bool apply, const double* rhs_direct, double* rhs_out,
                       const double* S1, const double* S2, double alpha, double* X, double* XT, int n, double* S_out) {
@@ -415,9 +416,6 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
             break;
         case kSrcPB: a.v = p->P; a.stride = (long)p->n2 * RS; a.count = p->n3; a.w = p->C3; a.wstride = RS; a.wpr = 8; break;
         case kSrcPC: a.v = p->P; a.stride = RS; a.count = p->n2; a.row_stride = (long)p->n2 * RS; a.w = p->B2; a.wstride = RS; a.wpr = 8; break;
-        // the all-reduced RHS = sum over the ranks' mailbox slots, in rank order
-        case kSrcBoxA: a.v = p->box; a.stride = (long)p->slotA; a.count = c->nranks; break;
-        case kSrcBoxB: a.v = p->box + p->offB; a.stride = (long)p->slotB; a.count = c->nranks; break;
         default: return fail(TRITD_ERR_INVALID, "bad update source");
     }
     a.S1 = S1; a.S2 = S2; a.alpha = alpha; a.gr = gram_slices(n);
@@ -425,16 +423,20 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
     if (p->xchg) {
         // C3'C3 lives in the exchange mailbox as per-rank partials behind the RHS_A slots
         if (S2 == p->bufA + (size_t)p->n1 * p->RS) { a.S2 = p->box + (size_t)p->n1 * p->RS; a.ns2 = c->nranks; a.s2stride = (long)p->slotA; }
-        if (!apply) {        // producer: rows (and, for exchange 0, the local C3'C3) go straight into the mailboxes
-            const int ex = which;               // exchange 0 = update A, 1 = update B
+        if (apply && which < 2) {
+            // updates A and B: the exchange of the RHS rows (and, for A, of the local C3'C3) happens inside the kernel
+            const int ex = which;
+            a.xmerge = 1;
             a.peers = p->peers; a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase;
             a.push_off = (long)((ex == 0 ? 0 : p->offB) + (ex == 0 ? p->slotA : p->slotB) * c->rank);
-            a.pflag_off = (long)p->offF + 4 * ex;
+            // flag block of this exchange: u32 index 8 (+ nranks * fsA for B) from the start of the flag area
+            const size_t fu = 8 + (ex == 0 ? 0 : (size_t)c->nranks * p->fsA);
+            a.pflag_off = (long)(p->offF + fu / 2);
+            a.fstride = (long)(ex == 0 ? p->fsA : p->fsB);
+            a.xflags = reinterpret_cast<const unsigned*>(p->box + p->offF) + fu;
+            a.xbox = p->box + (ex == 0 ? 0 : p->offB);
+            a.xslot = (long)(ex == 0 ? p->slotA : p->slotB);
             if (ex == 0) { a.extra_src = p->bufA + (size_t)p->n1 * p->RS; a.extra_off = (long)p->n1 * p->RS; a.extra_n = p->RS * p->RS; }
-        }
-        if (src == kSrcBoxA || src == kSrcBoxB) {
-            a.xflags = reinterpret_cast<const unsigned*>(p->box + p->offF) + (src == kSrcBoxA ? 0 : 8);
-            a.xn = c->nranks; a.xbase = p->xbase;
         }
     }
     a.gram_part = p->gpart + (size_t)which * kGramSlices * p->RS * p->RS; a.gram_cnt = p->flags + 16 + 64 * which;
@@ -457,24 +459,6 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
     return TRITD_OK;
 }
 
-// Push `n` doubles of a local partial into this rank's slot of every rank's mailbox and raise the flag of
-// exchange `which` (0 = [RHS_A ; C3'C3], 1 = RHS_B, 2 = residual sums) there.
-static int launch_push(tritd_problem* p, int which, const double* src, size_t n) {
-    tritd_ctx* c = p->ctx;
-    XchgPushArgs a;
-    a.src = src; a.n = (long)n; a.peers = p->peers;
-    const size_t region = which == 0 ? 0 : (which == 1 ? p->offB : p->offN);
-    const size_t slot = which == 0 ? p->slotA : (which == 1 ? p->slotB : 8);
-    a.dst_off = (long)(region + slot * c->rank);
-    a.flag_off = (long)p->offF + 4 * which;       // flag rows of 8 u32 (= 4 doubles) per exchange
-    a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase; a.st = p->st; a.ticket = p->flags + 13;
-    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(16, (n / 2 + 1023) / 1024));
-    k_xchg_push<<<grid, 256, 0, c->stream>>>(a);
-    CU_TRY(cudaGetLastError());
-    c->launches += 1;
-    return TRITD_OK;
-}
-
 // Map every rank's mailbox (CUDA IPC handles exchanged through NCCL once per problem).
 static int setup_exchange(tritd_problem* p) {
     tritd_ctx* c = p->ctx;
@@ -486,8 +470,10 @@ static int setup_exchange(tritd_problem* p) {
     p->slotB = (size_t)p->n2 * RS;
     p->offB = p->slotA * nr;
     p->offN = p->offB + p->slotB * nr;
-    p->offF = p->offN + (size_t)8 * nr;
-    p->box_doubles = p->offF + 64;                  // 3 flag rows of 8 u32
+    p->offF = p->offN + (size_t)8 * nr;               // flags (u32): [norms: 8] [exchange A: nr x fsA] [exchange B: nr x fsB]
+    p->fsA = ((size_t)p->n1 + 1 + 7) & ~(size_t)7;   // one flag per k_upd CTA (<= n + 1 CTAs), per rank
+    p->fsB = ((size_t)p->n2 + 1 + 7) & ~(size_t)7;
+    p->box_doubles = p->offF + (8 + (size_t)nr * (p->fsA + p->fsB)) / 2 + 8;
     int s = dalloc(p, &p->box, p->box_doubles);
     if (s != TRITD_OK) return s;
     CU_TRY(cudaMemsetAsync(p->box, 0, p->box_doubles * 8, c->stream));
@@ -863,24 +849,23 @@ static int enqueue_iteration(tritd_problem* p) {
     // applies the inverse and forms A1'A1 in one launch.
     const bool xc = p->xchg;             // N>1: partials travel through the peer mailboxes (else NCCL all-reduces)
     const size_t nA = (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS;
-    const bool direct_A = !p->rhsA_ready || multi;
+    const bool direct_A = !p->rhsA_ready || (multi && !xc);
     if (!p->rhsA_ready) ST_TRY(launch_mttkrp1(p, p->mapT, p->B2, p->C3, rhsA));
-    else if (multi) ST_TRY(launch_upd(p, 0, kSrcPartF, false, nullptr, rhsA, nullptr, nullptr, 0.0, nullptr, nullptr, p->n1, nullptr));
+    else if (multi && !xc) ST_TRY(launch_upd(p, 0, kSrcPartF, false, nullptr, rhsA, nullptr, nullptr, 0.0, nullptr, nullptr, p->n1, nullptr));
     ST_TRY(mark());
-    if (xc) { if (!p->rhsA_ready) ST_TRY(launch_push(p, 0, p->bufA, nA)); }     // later iterations: k_upd pushed its rows itself
-    else ST_TRY(allreduce_sum(c, p->bufA, nA));
-    ST_TRY(launch_upd(p, 0, xc ? kSrcBoxA : (direct_A ? kSrcDirect : kSrcPartF), true, rhsA, nullptr, p->SB, SC, p->opts.lambda2, p->A1,
+    if (multi && !xc) ST_TRY(allreduce_sum(c, p->bufA, nA));
+    ST_TRY(launch_upd(p, 0, direct_A ? kSrcDirect : kSrcPartF, true, rhsA, nullptr, p->SB, SC, p->opts.lambda2, p->A1,
                       p->A1T, p->n1, p->SA));
     ST_TRY(mark());
 
     // update_B (:83-88) with the new A: RHS = X2*G' = sum_t C3(t,:) .* P(t,j,:), Gram = (A1'A1) o (C3'C3) + lambda2*I
     ST_TRY(launch_ppass(p, p->mapT));
     ST_TRY(mark());
-    if (multi) {
+    if (multi && !xc) {
         ST_TRY(launch_upd(p, 1, kSrcPB, false, nullptr, p->rhsB, nullptr, nullptr, 0.0, nullptr, nullptr, p->n2, nullptr));
-        if (!xc) ST_TRY(allreduce_sum(c, p->rhsB, (size_t)p->n2 * p->RS));
+        ST_TRY(allreduce_sum(c, p->rhsB, (size_t)p->n2 * p->RS));
     }
-    ST_TRY(launch_upd(p, 1, xc ? kSrcBoxB : (multi ? kSrcDirect : kSrcPB), true, p->rhsB, nullptr, p->SA, SC, p->opts.lambda2, p->B2,
+    ST_TRY(launch_upd(p, 1, multi && !xc ? kSrcDirect : kSrcPB, true, p->rhsB, nullptr, p->SA, SC, p->opts.lambda2, p->B2,
                       nullptr, p->n2, p->SB));
 
     // update_C (:90-95) with the new A, B: slice-local; ridge fixed at 1e-9.  Leaves SC = C3'C3 over the local
@@ -893,10 +878,7 @@ static int enqueue_iteration(tritd_problem* p) {
     p->rhsA_ready = true;
     ST_TRY(mark());
     if (xc) {
-        k_finalize_xchg<<<1, 32, 0, st>>>(p->st, p->box + p->offN, reinterpret_cast<const unsigned*>(p->box + p->offF) + 16,
-                                         c->nranks, p->xbase, p->errHist, p->errL, p->errO);
-        CU_TRY(cudaGetLastError());
-        c->launches += 1;
+        // nothing: k_admm's last CTA exchanged the residual sums and finalised the iteration
     } else if (multi) {
         ST_TRY(allreduce_sum(c, p->norms, 2));
         k_finalize<<<1, 256, 0, st>>>(p->st, p->norm_part, p->gridA, p->norms, 1, p->errHist, p->errL, p->errO);
