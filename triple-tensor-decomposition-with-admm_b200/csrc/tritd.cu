@@ -255,6 +255,7 @@ struct tritd_problem {
     std::vector<void*> peer_map;         // cudaIpcOpenMemHandle mappings (nullptr for the own rank)
     double** peers = nullptr;            // device array [nranks] of mailbox bases
     unsigned xbase = 0;
+    int upd_wave = 0;                    // k_upd CTAs resident at once (one wave)
     double* ones = nullptr;              // [64] vector of ones: the weights of a plain-sum RHS source
     double* Minv = nullptr;              // [3][RS][RS] inverses of the three ridge systems (written by k_upd's block 0)
     long long* dbg = nullptr;            // optional globaltimer stamps of k_upd (TRITD_DEBUG_STAMPS=1)
@@ -436,6 +437,9 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
             a.xflags = reinterpret_cast<const unsigned*>(p->box + p->offF) + fu;
             a.xbox = p->box + (ex == 0 ? 0 : p->offB);
             a.xslot = (long)(ex == 0 ? p->slotA : p->slotB);
+            // a CTA that waits for its counterparts on the other ranks keeps its slot: keep the grid within one wave
+            // (more rows per CTA) so that later waves do not each pay the exchange latency
+            while (a.wpr > 1 && (n + 8 / a.wpr - 1) / (8 / a.wpr) + 1 > p->upd_wave) a.wpr >>= 1;
             if (ex == 0) { a.extra_src = p->bufA + (size_t)p->n1 * p->RS; a.extra_off = (long)p->n1 * p->RS; a.extra_n = p->RS * p->RS; }
         }
     }
@@ -516,6 +520,17 @@ static int setup_exchange(tritd_problem* p) {
     }
     if ((s = dalloc(p, &p->peers, (size_t)nr)) != TRITD_OK) return s;
     CU_TRY(cudaMemcpy(p->peers, bases.data(), sizeof(double*) * nr, cudaMemcpyHostToDevice));
+    {
+        int occ = 0;
+        const size_t sm = upd_smem_bytes(p->RS);
+        switch ((p->R + 15) / 16) {
+            case 1: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<1>, kUpdThreads, sm)); break;
+            case 2: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<2>, kUpdThreads, sm)); break;
+            case 3: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<3>, kUpdThreads, sm)); break;
+            default: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<4>, kUpdThreads, sm)); break;
+        }
+        p->upd_wave = std::max(1, occ * c->num_sms);
+    }
     p->xchg = true;
     return TRITD_OK;
 }
