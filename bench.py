@@ -14,8 +14,8 @@ Prints ONE JSON line (rank 0):
   e2e       iterations/s of one reference-facing call (tritd_admm_f64 through ctypes) with HOST
             buffers: pinned D in, A/B/C/O/errHist out, H2D and D2H inside the timed region;
   roofline  the fused element-wise kernel: 64*N algorithmic bytes per launch / its CUDA-event time;
-  cpu_baseline  the numpy/OpenBLAS oracle port timed on this box's host cores (rank 0, N=1).
---impl reference times the oracle port alone (the MATLAB reference cannot run here).
+  cpu_baseline  the multi-threaded CPU port of the oracle timed on this box's host cores (rank 0, N=1).
+--impl reference times that port alone (the MATLAB reference cannot run here).
 """
 import argparse
 import json
@@ -105,28 +105,30 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_oracle_rate(name, steps, warmup, budget_s):
-    """ADMM iterations/s of the oracle port on the host cores: `warmup` untimed + `steps` timed
-    iterations (time stamps taken inside the loop).  To bound the run the tensor is cut to its
-    first `t_slices` mode-3 slices -- every pass of the iteration is linear in n3 -- and the rate
-    is scaled by t_slices/n3 to the full workload."""
+    """ADMM iterations/s of the CPU port on the host cores: `warmup` untimed + `steps` timed iterations (time stamps
+    taken inside the loop).  The port is oracle/tritd_oracle_mt.py -- the oracle's statements and passes with every
+    N-sized operation on all host threads, like MATLAB's multi-threaded built-ins (checked against the numpy oracle in
+    tests/test_oracle.py).  To bound the run the tensor is cut to its first `t_slices` mode-3 slices -- every pass of
+    the iteration is linear in n3 -- and the rate is scaled by t_slices/n3 to the full workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import tritd_oracle as orc
+    import tritd_oracle_mt as mt
+    cores = os.cpu_count() or 1
     D, r, opts, A0, B0, C0, (n1, n2, n3) = workload_arrays(name)
     cal = min(4, n3)
     t = time.perf_counter()
-    orc.triple_decomp_ADMM(np.asfortranarray(D[:, :, :cal]), r, dict(opts, maxIter=2, tol=0.0, disp=0), A0, B0,
-                           np.asfortranarray(C0[:, :, :cal]))
+    mt.triple_decomp_ADMM(np.asfortranarray(D[:, :, :cal]), r, dict(opts, maxIter=2, tol=0.0, disp=0), A0, B0,
+                          np.asfortranarray(C0[:, :, :cal]), threads=cores)
     per_slice_iter = (time.perf_counter() - t) / (2 * cal)
     t_slices = int(max(min(4, n3), min(n3, budget_s / max(per_slice_iter * (steps + warmup), 1e-9))))
     Ds = np.asfortranarray(D[:, :, :t_slices]); Cs = np.asfortranarray(C0[:, :, :t_slices])
     stamps = [time.perf_counter()]
-    orc.triple_decomp_ADMM(Ds, r, dict(opts, maxIter=steps + warmup, tol=0.0, disp=0), A0, B0, Cs,
-                           on_iter=lambda *a: stamps.append(time.perf_counter()))
+    mt.triple_decomp_ADMM(Ds, r, dict(opts, maxIter=steps + warmup, tol=0.0, disp=0), A0, B0, Cs,
+                          on_iter=lambda *a: stamps.append(time.perf_counter()), threads=cores)
     dt = stamps[-1] - stamps[warmup]
     rate_full = steps / dt * (t_slices / n3)
-    sample = (f"{warmup}+{steps} iterations of the numpy/OpenBLAS oracle on the first {t_slices} of {n3} mode-3 slices of {name} "
-              f"({n1}x{n2}x{t_slices}); rate scaled by {t_slices}/{n3} (every pass is linear in n3); BLAS threads = all "
-              f"{os.cpu_count()} cores, numpy element-wise passes single-threaded")
+    sample = (f"{warmup}+{steps} iterations of the multi-threaded CPU port (oracle/tritd_oracle_mt.py: the oracle's statements on "
+              f"torch CPU tensors, {cores} threads for every N-sized pass and dgemm) on the first {t_slices} of {n3} mode-3 slices of "
+              f"{name} ({n1}x{n2}x{t_slices}); rate scaled by {t_slices}/{n3} (every pass is linear in n3)")
     return rate_full, sample, dt
 
 
@@ -145,7 +147,7 @@ def run_reference(args):
         "data": "synthetic", "config": {"workload": f"{name}: {synth.DESCRIPTIONS[name]}", "n1": n1, "n2": n2, "n3": n3, "r": r},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is MATLAB and cannot run here (no MATLAB/Octave); this is the numpy/OpenBLAS oracle port",
+        "note": "reference is MATLAB and cannot run here (no MATLAB/Octave); this is the multi-threaded CPU port of the oracle",
     }
     print(json.dumps(line), flush=True)
 

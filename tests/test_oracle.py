@@ -118,3 +118,19 @@ def test_synth_slabs_and_bounds():
     assert np.array_equal(full, part)
     assert synth.slab_bounds(300, 8) == [(0, 38), (38, 76), (76, 114), (114, 152), (152, 189), (189, 226), (226, 263), (263, 300)]
     assert synth.slab_bounds(5, 2) == [(0, 3), (3, 5)]
+
+
+def test_multithreaded_port_equals_oracle():
+    """oracle/tritd_oracle_mt.py (the timed CPU baseline of bench.py) makes the same iterates as the numpy oracle."""
+    import tritd_oracle_mt as mt
+    for cfg, shape, k in (("cfg1", (20, 18, 12), 8), ("cfg3", (24, 32, 10), 6)):
+        w = synth.make_config(cfg, shrink=shape)
+        o = dict(w["opts"], maxIter=k, tol=0.0)
+        ref = orc.triple_decomp_ADMM(w["D"], w["r"], o, w["A0"], w["B0"], w["C0"])
+        res = mt.triple_decomp_ADMM(w["D"], w["r"], o, w["A0"], w["B0"], w["C0"], threads=2)
+        for a, b in zip(res, ref):
+            assert rel_err(a, b) < 1e-10
+    w = synth.make_config("cfg1", shrink=(30, 30, 30))
+    o = dict(w["opts"], maxIter=100, tol=2e-2)          # the stopping rule fires at the same iteration
+    assert len(mt.triple_decomp_ADMM(w["D"], 3, o, *synth.init_factors(30, 30, 30, 3, 101))[4]) == \
+        len(orc.triple_decomp_ADMM(w["D"], 3, o, *synth.init_factors(30, 30, 30, 3, 101))[4])
