@@ -198,6 +198,21 @@ int tritd_buildG_f64(tritd_ctx* ctx, const double* A, const double* C, int64_t n
 int tritd_buildH_f64(tritd_ctx* ctx, const double* A, const double* B, int64_t n1, int64_t n2, int r, double* H);
 /* O = soft_threshold(X, lam), n elements            soft_threshold.m:2     */
 int tritd_soft_threshold_f64(tritd_ctx* ctx, const double* X, int64_t n, double lam, double* out);
+/* Design matrices and product of the ORIGINAL (Qi) triple decomposition, the model the README's
+ * RPAS claim describes; origin_triple_tensor/buildF.m:4-6, buildG.m:9-11, buildH.m:9-11, triple_product.m.
+ *   which = 0: F = buildF(B,C), U = B (r x n2 x r), V = C (r x r x n3), na = n2, nb = n3,
+ *              F(q+(s-1)r, j+(t-1)n2) = sum_p B(p,j,s) C(p,q,t)
+ *   which = 1: G = buildG(A,C), U = A (n1 x r x r), V = C, na = n1, nb = n3,
+ *              G(p+(s-1)r, i+(t-1)n1) = sum_q A(i,q,s) C(p,q,t)
+ *   which = 2: H = buildH(A,B), U = A, V = B, na = n1, nb = n2,
+ *              H(p+(q-1)r, i+(j-1)n1) = sum_s A(i,q,s) B(p,j,s)
+ * out is r^2 x (na*nb) column-major.  Only these helpers exist for the Qi model; the solver implements the
+ * rank-r^2 CP form of fast_robust_triple_tensor/ (SURVEY fact 1). */
+int tritd_design_qi_f64(tritd_ctx* ctx, int which, const double* U, const double* V, int64_t na, int64_t nb, int r,
+                        double* out);
+/* Xhat(i,j,t) = sum_{p,q,s} A(i,q,s) B(p,j,s) C(p,q,t)     origin_triple_tensor/triple_product.m */
+int tritd_triple_product_qi_f64(tritd_ctx* ctx, const double* A, const double* B, const double* C, int64_t n1,
+                                int64_t n2, int64_t n3, int r, double* Xhat);
 /* [rmse, nrmse] = evaluate(Xhat, gt, mask) of the reference's drivers (traffic_triple_comparison.m:194-202) with
  * Xhat = triple_product(A,B,C) formed on the device (the reconstruction never crosses PCIe).
  * gt: dense n1 x n2 x n3 ground truth (entries outside the mask are ignored); mask: dense n1 x n2 x n3 bytes

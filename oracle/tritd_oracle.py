@@ -340,6 +340,67 @@ def triple_product_loops(A, B, C):
 # --------------------------------------------------------------------------
 # the n x R "unfolded factor" layout the CUDA library keeps on device
 # --------------------------------------------------------------------------
+# --------------------------------------------------------------------------
+# the ORIGINAL (Qi) triple decomposition's design matrices and product
+# (origin_triple_tensor/buildF.m:4-6, buildG.m:9-11, buildH.m:9-11, triple_product.m)
+# --------------------------------------------------------------------------
+def buildF_qi(B, C):
+    """origin_triple_tensor/buildF.m:4-6:  F(q+(s-1)r, j+(t-1)n2) = sum_p B(p,j,s) C(p,q,t)."""
+    r, n2, _ = B.shape
+    n3 = C.shape[2]
+    F = np.reshape(np.transpose(B, (1, 2, 0)), (n2 * r, r), order="F") @ np.reshape(C, (r, r * n3), order="F")
+    F = np.transpose(np.reshape(F, (n2, r, r, n3), order="F"), (2, 1, 0, 3))
+    return np.reshape(F, (r * r, n2 * n3), order="F")
+
+
+def buildG_qi(A, C):
+    """origin_triple_tensor/buildG.m:9-11:  G(p+(s-1)r, i+(t-1)n1) = sum_q A(i,q,s) C(p,q,t)."""
+    n1, r, _ = A.shape
+    n3 = C.shape[2]
+    G = np.reshape(np.transpose(A, (0, 2, 1)), (n1 * r, r), order="F") @ np.reshape(np.transpose(C, (1, 0, 2)), (r, r * n3), order="F")
+    G = np.transpose(np.reshape(G, (n1, r, r, n3), order="F"), (2, 1, 0, 3))
+    return np.reshape(G, (r * r, n1 * n3), order="F")
+
+
+def buildH_qi(A, B):
+    """origin_triple_tensor/buildH.m:9-11:  H(p+(q-1)r, i+(j-1)n1) = sum_s A(i,q,s) B(p,j,s)."""
+    n1, r, _ = A.shape
+    n2 = B.shape[1]
+    H = np.reshape(A, (n1 * r, r), order="F") @ np.reshape(np.transpose(B, (2, 0, 1)), (r, r * n2), order="F")
+    H = np.transpose(np.reshape(H, (n1, r, r, n2), order="F"), (2, 1, 0, 3))
+    return np.reshape(H, (r * r, n1 * n2), order="F")
+
+
+def triple_product_qi(A, B, C):
+    """origin_triple_tensor/triple_product.m:  X(i,j,t) = sum_{p,q,s} A(i,q,s) B(p,j,s) C(p,q,t)."""
+    return np.asfortranarray(np.einsum("iqs,pjs,pqt->ijt", A, B, C))
+
+
+def design_qi_loops(which, U, V):
+    """The commented scalar definitions (buildG.m:5-6, buildH.m:5-6 and the analogous one for F) as plain loops."""
+    if which == 0:      # F: U = B, V = C
+        r, na, _ = U.shape; nb = V.shape[2]
+    elif which == 1:    # G: U = A, V = C
+        na, r, _ = U.shape; nb = V.shape[2]
+    else:               # H: U = A, V = B
+        na, r, _ = U.shape; nb = V.shape[1]
+    out = np.zeros((r * r, na * nb), order="F")
+    for b in range(nb):
+        for a in range(na):
+            for k1 in range(r):
+                for k0 in range(r):
+                    s = 0.0
+                    for m in range(r):
+                        if which == 0:
+                            s += U[m, a, k1] * V[m, k0, b]        # sum_p B(p,j,s) C(p,q,t), row q + r s
+                        elif which == 1:
+                            s += U[a, m, k1] * V[k0, m, b]        # sum_q A(i,q,s) C(p,q,t), row p + r s
+                        else:
+                            s += U[a, k1, m] * V[k0, b, m]        # sum_s A(i,q,s) B(p,j,s), row p + r q
+                    out[k0 + r * k1, a + na * b] = s
+    return out
+
+
 def factors_to_unfolded(A, B, C):
     """A1 (n1 x R) = unfold(A,1); B2 (n2 x R) = unfold(B,2); C3 (n3 x R) = unfold(C,3)."""
     return unfold(A, 1), unfold(B, 2), unfold(C, 3)

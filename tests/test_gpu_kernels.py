@@ -93,3 +93,13 @@ def test_evaluate_on_device(shape, r):
     rmse, nrmse = tritd.evaluate(A0, B0, C0, gt, mask)
     ref = np.linalg.norm(Xhat[mask] - gt[mask])
     assert abs(rmse - ref) < 1e-11 * ref and abs(nrmse - ref / np.linalg.norm(gt[mask])) < 1e-11 * nrmse
+
+
+@pytest.mark.parametrize("shape,r", [((7, 6, 5), 3), ((33, 17, 9), 2), ((40, 36, 24), 5), ((20, 12, 9), 8)])
+def test_qi_design_matrices_and_product(shape, r):
+    """Design matrices / product of the original (Qi) model (origin_triple_tensor/buildF|G|H.m, triple_product.m)."""
+    A, B, C = _factors(*shape, r, 9)
+    assert rel_err(tritd.buildF_qi(B, C), orc.buildF_qi(B, C)) < TOL
+    assert rel_err(tritd.buildG_qi(A, C), orc.buildG_qi(A, C)) < TOL
+    assert rel_err(tritd.buildH_qi(A, B), orc.buildH_qi(A, B)) < TOL
+    assert rel_err(tritd.triple_product_qi(A, B, C), orc.triple_product_qi(A, B, C)) < TOL

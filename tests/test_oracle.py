@@ -134,3 +134,23 @@ def test_multithreaded_port_equals_oracle():
     o = dict(w["opts"], maxIter=100, tol=2e-2)          # the stopping rule fires at the same iteration
     assert len(mt.triple_decomp_ADMM(w["D"], 3, o, *synth.init_factors(30, 30, 30, 3, 101))[4]) == \
         len(orc.triple_decomp_ADMM(w["D"], 3, o, *synth.init_factors(30, 30, 30, 3, 101))[4])
+
+
+def test_qi_design_matrices_against_their_scalar_definitions():
+    """origin_triple_tensor/buildF|G|H.m restated with the reference's reshape/permute lines = the commented scalar sums;
+    A_(1) * F reproduces the six-loop triple product (origin_triple_tensor/triple_product.m)."""
+    rng = np.random.default_rng(3)
+    n1, n2, n3, r = 5, 4, 3, 2
+    A = np.asfortranarray(rng.standard_normal((n1, r, r))); B = np.asfortranarray(rng.standard_normal((r, n2, r)))
+    C = np.asfortranarray(rng.standard_normal((r, r, n3)))
+    assert np.allclose(orc.buildF_qi(B, C), orc.design_qi_loops(0, B, C), rtol=1e-14, atol=1e-14)
+    assert np.allclose(orc.buildG_qi(A, C), orc.design_qi_loops(1, A, C), rtol=1e-14, atol=1e-14)
+    assert np.allclose(orc.buildH_qi(A, B), orc.design_qi_loops(2, A, B), rtol=1e-14, atol=1e-14)
+    X = np.zeros((n1, n2, n3))
+    for i in range(n1):
+        for j in range(n2):
+            for t in range(n3):
+                X[i, j, t] = sum(A[i, q, s] * B[p, j, s] * C[p, q, t] for p in range(r) for q in range(r) for s in range(r))
+    assert np.allclose(orc.triple_product_qi(A, B, C), X, rtol=1e-13, atol=1e-13)
+    assert np.allclose(np.reshape(np.reshape(A, (n1, r * r), order="F") @ orc.buildF_qi(B, C), (n1, n2, n3), order="F"), X,
+                       rtol=1e-13, atol=1e-13)

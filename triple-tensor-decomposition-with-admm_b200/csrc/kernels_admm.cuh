@@ -12,11 +12,12 @@
 // A stage is JG (1 or 2) groups of 8 columns j of slice t for the whole i-tile, i.e. four 8*JG KB boxes
 // (D, Y_L, E, Y_O) fetched by ONE TMA op each through a 4-D view (i_lo=16, j, i_hi, t) of the
 // column-major arrays, which lands as [warp][8 j][16 i] with the 128B swizzle pattern the DMMA
-// accumulator layout reads conflict-free.  Consumers update the boxes in place (T over D) plus a fifth
-// box for O; the TMA warp then streams the five boxes back with one TMA store each and refills the
-// slot.  No thread touches HBM with a load/store instruction; rows/columns outside the tensor are
-// zero-filled on load and clipped on store by the tensor maps (ld1 is a multiple of 16 so the padded
-// rows exist and stay zero).  Algorithmic traffic: 4 reads + 5 writes = 72 bytes per element.
+// accumulator layout reads conflict-free.  Consumers update the boxes in place (T over D; with WRITE_O a
+// fifth box for O -- the solver does not store O inside the loop, k_recover_O rebuilds it on demand); the TMA
+// warp then streams the boxes back with one TMA store each and refills the slot.  No thread touches HBM with a
+// load/store instruction; rows/columns outside the tensor are zero-filled on load and clipped on store by the
+// tensor maps (ld1 is a multiple of 16 so the padded rows exist and stay zero).  Algorithmic traffic:
+// 4 reads + 4 writes = 64 bytes per element.
 #pragma once
 #include "common.cuh"
 #include "kernels_contract.cuh"

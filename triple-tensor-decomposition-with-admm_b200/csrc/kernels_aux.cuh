@@ -47,6 +47,48 @@ __global__ void __launch_bounds__(256) k_soft_threshold(const double* x, double*
     }
 }
 
+// Design matrices of the ORIGINAL (Qi) triple decomposition, origin_triple_tensor/buildF.m:4-6, buildG.m:9-11,
+// buildH.m:9-11 -- one summed index per entry.  Inputs are the MATLAB 3-D factor arrays
+// (column-major: A(i,q,s) at i + n1*(q + r*s), B(p,j,s) at p + r*(j + n2*s), C(p,q,t) at p + r*(q + r*t)):
+//   which = 0:  F(q + r*s, j + n2*t) = sum_p B(p,j,s) * C(p,q,t)        na = n2, nb = n3
+//   which = 1:  G(p + r*s, i + n1*t) = sum_q A(i,q,s) * C(p,q,t)        na = n1, nb = n3
+//   which = 2:  H(p + r*q, i + n1*j) = sum_s A(i,q,s) * B(p,j,s)        na = n1, nb = n2
+// One thread per output entry, entries of a column (r^2 consecutive doubles) written by consecutive threads.
+__global__ void __launch_bounds__(256) k_design_qi(const double* __restrict__ U, const double* __restrict__ V, double* __restrict__ out,
+                                                   long na, long nb, int r, int which) {
+    const int R = r * r;
+    const size_t total = (size_t)R * na * nb;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        const int k = (int)(e % R), k0 = k % r, k1 = k / r;
+        const size_t col = e / R;
+        const long a = (long)(col % na), b = (long)(col / na);
+        double s = 0.0;
+        if (which == 0) {           // U = B (r x n2 x r), V = C; k0 = q, k1 = s; a = j, b = t
+            for (int p = 0; p < r; ++p) s = fma(U[p + (size_t)r * (a + na * k1)], V[p + (size_t)r * (k0 + (size_t)r * b)], s);
+        } else if (which == 1) {    // U = A (n1 x r x r), V = C; k0 = p, k1 = s; a = i, b = t
+            for (int q = 0; q < r; ++q) s = fma(U[a + na * (q + (size_t)r * k1)], V[k0 + (size_t)r * (q + (size_t)r * b)], s);
+        } else {                    // U = A, V = B (r x n2 x r); k0 = p, k1 = q; a = i, b = j
+            for (int t = 0; t < r; ++t) s = fma(U[a + na * (k1 + (size_t)r * t)], V[k0 + (size_t)r * (b + nb * t)], s);
+        }
+        out[e] = s;
+    }
+}
+
+// Xhat = A_(1) * F for a materialised r^2 x ncols design matrix (the Qi triple product
+// X(i,j,t) = sum_{p,q,s} A(i,q,s) B(p,j,s) C(p,q,t), origin_triple_tensor/triple_product.m): thread per (i, col),
+// i fastest, so the loads of A(:,k) and the stores are coalesced and F(k,col) is a broadcast.
+__global__ void __launch_bounds__(256) k_unfold1_times(const double* __restrict__ A, const double* __restrict__ F,
+                                                       double* __restrict__ X, long n1, size_t ncols, int R) {
+    const size_t total = (size_t)n1 * ncols;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        const long i = (long)(e % n1);
+        const size_t col = e / n1;
+        double s = 0.0;
+        for (int k = 0; k < R; ++k) s = fma(A[i + n1 * (size_t)k], F[col * R + k], s);
+        X[e] = s;
+    }
+}
+
 // evaluate() of the reference's drivers (traffic_triple_comparison.m:194-202): per-CTA partials of
 //   sum_{mask} (Xhat - gt)^2  and  sum_{mask} gt^2   over padded column-major arrays (ld1 rows per column);
 // mask is dense n1 x n2 x n3 bytes (nullptr = all true).  Fixed-order partial sums (deterministic).

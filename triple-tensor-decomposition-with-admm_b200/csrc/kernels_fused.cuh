@@ -1,10 +1,8 @@
-// The fused HBM-bound kernel of one TriTD-ADMM iteration: reconstruction
-// L = triple_product(A,B,C) on the fly (never stored), O update, soft-threshold
-// of E, dual updates, next-iteration target T and both residual norms.
-// Reference: fast_robust_triple_tensor/triple_decomp_ADMM.m:38-59 and :33
-// (triple_product.m:6-7, soft_threshold.m:2), same statement order and the same
-// floating-point association as the MATLAB expressions; every add/mul/div is an
-// explicit round-to-nearest intrinsic so nvcc cannot contract them into FMAs.
+// Iteration scalars (IterState), the scalar step that ends an iteration, and k_fused: the reconstruction
+// L = triple_product(A,B,C) formed on the fly with DMMA (fast_robust_triple_tensor/triple_product.m:6-7), either
+// stored (MODE 1: tritd_triple_product_f64, L output, evaluate) or only compared with a tensor X
+// (MODE 2: sum((X - Xhat).^2) of triple_decomp_ALS.m:15-16).  The ADMM element-wise block itself lives in
+// kernels_admm.cuh (k_admm).
 #pragma once
 #include "common.cuh"
 
@@ -30,35 +28,14 @@ __host__ __device__ inline void iter_state_derive(IterState& s) {
 }
 
 struct FusedArgs {
-    const double* D;
-    double *E, *YL, *YO, *T, *O;       // mode 0: all N-sized state arrays; mode 1: O = output L, others unused
+    const double* D;                   // MODE 2: the tensor X compared with the reconstruction
+    double* O;                         // MODE 1: output L
     const double *A1, *B2, *C3;        // [n][RS]
     const IterState* st;
     double* norm_part;                 // [grid][2]
     int n1, n2, n3, ld1, RS;
     int n_it, n_jc, gi;                // i-tiles (128), j-chunks (32), CTAs per i-tile
 };
-
-// One element of triple_decomp_ADMM.m:41-53 and the next T (:33).
-__device__ __forceinline__ void admm_point(const IterState& p, double d, double l, double& yl, double& e, double& yo,
-                                           double& o, double& tn, double& sL, double& sO) {
-    const double dl = __dsub_rn(d, l);                                   // D - L
-    const double r1 = __dadd_rn(dl, __dmul_rn(p.rmuL, yl));              // R1 = D - L + (1/muL)*Y_L
-    const double my = __dmul_rn(p.rmuO, yo);                             // (1/muO)*Y_O
-    const double r2 = __dsub_rn(e, my);                                  // R2 = E - (1/muO)*Y_O
-    o = __ddiv_rn(__dadd_rn(__dmul_rn(p.muL, r1), __dmul_rn(p.muO, r2)), p.musum);
-    const double r3 = __dadd_rn(o, my);                                  // R3 = O + (1/muO)*Y_O
-    const double mx = fmax(__dsub_rn(fabs(r3), p.thr), 0.0);
-    const double en = r3 > 0.0 ? mx : (r3 < 0.0 ? -mx : 0.0);            // sign(R3).*max(|R3|-lambda/muO,0)
-    const double resL = __dsub_rn(dl, o);                                // D - L - O
-    const double resO = __dsub_rn(o, en);                                // O - E
-    yl = __dadd_rn(yl, __dmul_rn(p.muL, resL));
-    yo = __dadd_rn(yo, __dmul_rn(p.muO, resO));
-    e = en;
-    tn = __dadd_rn(__dsub_rn(d, o), __dmul_rn(p.rmuL_next, yl));         // next T = D - O + (1/muL')*Y_L
-    sL = fma(resL, resL, sL);
-    sO = fma(resO, resO, sO);
-}
 
 template <int KS> struct FusedCfg {
     static constexpr int PL = (KS & 1) ? 4 * KS : 4 * KS + 4;   // pitch of the B2 chunk: == 4 (mod 8) doubles
@@ -69,15 +46,14 @@ template <int KS> struct FusedCfg {
 // range of column blocks v = jc * n3 + t (32 columns j of slice t).  Each warp walks the
 // block in four groups of 8 columns; per group it forms a 16 x 8 patch of L with 2*KS DMMAs
 // (M = i, two m-tiles = even/odd i; N = j; K = k) whose accumulator layout is exactly the
-// 16-byte-vector layout of the element-wise pass, so the five state arrays are touched with
-// 128-byte-per-row coalesced v2 accesses straight from/to registers.
+// 16-byte-vector layout of the column-major tensor, so it is touched with 128-byte-per-row coalesced v2
+// accesses straight from/to registers.
 template <int KS, int MODE>
 __global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const FusedArgs a) {
     constexpr int PL = FusedCfg<KS>::PL;
     if (MODE != 1 && a.st->stop) return;
     __shared__ double B2s[32 * PL];
     __shared__ double red[64];
-    __shared__ IterState prm_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
@@ -87,14 +63,12 @@ __global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const F
     const int i0 = it * 128 + warp * 16 + 2 * g;          // this lane's even row; it also owns i0 + 1
     const bool i_ok = i0 < a.ld1;
 
-    if (MODE == 0 && threadIdx.x == 0) prm_s = *a.st;
-
     // rows of A1 this lane feeds into the A fragments (clamped; rows >= n1 are zeroed below)
     const double* a1r0 = a.A1 + (size_t)min(i0, a.n1 - 1) * a.RS + tig;
     const double* a1r1 = a.A1 + (size_t)min(i0 + 1, a.n1 - 1) * a.RS + tig;
     const double z0 = (i0 < a.n1) ? 1.0 : 0.0, z1 = (i0 + 1 < a.n1) ? 1.0 : 0.0;
 
-    struct Buf { double2 d[2], yl[2], e[2], yo[2]; };
+    struct Buf { double2 d[2]; };
     auto load = [&](Buf& b, long v, int jg) {
         const int jc = (int)(v / a.n3), t = (int)(v - (long)jc * a.n3);
 #pragma unroll
@@ -103,11 +77,6 @@ __global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const F
             const bool ok = i_ok && j < a.n2;
             const size_t off = ((size_t)t * a.n2 + j) * a.ld1 + i0;
             if (MODE != 1) b.d[c] = ok ? ldg_stream2(a.D + off) : make_double2(0.0, 0.0);
-            if (MODE == 0) {
-                b.yl[c] = ok ? ldg_stream2(a.YL + off) : make_double2(0.0, 0.0);
-                b.e[c] = ok ? ldg_stream2(a.E + off) : make_double2(0.0, 0.0);
-                b.yo[c] = ok ? ldg_stream2(a.YO + off) : make_double2(0.0, 0.0);
-            }
         }
     };
 
@@ -162,15 +131,6 @@ __global__ void __launch_bounds__(256, FusedCfg<KS>::kMinBlocks) k_fused(const F
                     const double e0 = __dsub_rn(cur.d[c].x, l[0][c]), e1 = __dsub_rn(cur.d[c].y, l[1][c]);
                     sL = fma(e0, e0, sL);
                     sL = fma(e1, e1, sL);
-                } else {
-                    double2 o, tn;
-                    admm_point(prm_s, cur.d[c].x, l[0][c], cur.yl[c].x, cur.e[c].x, cur.yo[c].x, o.x, tn.x, sL, sO);
-                    admm_point(prm_s, cur.d[c].y, l[1][c], cur.yl[c].y, cur.e[c].y, cur.yo[c].y, o.y, tn.y, sL, sO);
-                    stg_stream2(a.O + off, o);
-                    stg_stream2(a.E + off, cur.e[c]);
-                    stg_stream2(a.YL + off, cur.yl[c]);
-                    stg_stream2(a.YO + off, cur.yo[c]);
-                    stg_stream2(a.T + off, tn);
                 }
             }
             if (MODE != 1) cur = nxt;

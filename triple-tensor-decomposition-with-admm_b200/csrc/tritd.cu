@@ -358,13 +358,12 @@ static int launch_ppass(tritd_problem* p, const CUtensorMap& mapT) {
 static int launch_fused(tritd_problem* p, int mode, double* Lout) {
     tritd_ctx* c = p->ctx;
     FusedArgs a;
-    a.D = p->D; a.E = p->E; a.YL = p->YL; a.YO = p->YO; a.T = p->T; a.O = mode == 0 ? p->O : Lout;
+    a.D = p->D; a.O = Lout;
     a.A1 = p->A1; a.B2 = p->B2; a.C3 = p->C3; a.st = p->st; a.norm_part = p->norm_part;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.ld1 = p->ld1; a.RS = p->RS;
     a.n_it = p->n_it; a.n_jc = p->n_jc; a.gi = p->gi;
 #define CALL(NT_, KS_)                                                              \
-    if (mode == 0) k_fused<KS_, 0><<<p->gridF, 256, 0, c->stream>>>(a);             \
-    else if (mode == 2) k_fused<KS_, 2><<<p->gridF, 256, 0, c->stream>>>(a);        \
+    if (mode == 2) k_fused<KS_, 2><<<p->gridF, 256, 0, c->stream>>>(a);             \
     else k_fused<KS_, 1><<<p->gridF, 256, 0, c->stream>>>(a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
@@ -595,7 +594,7 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     p->smemM = smem_mttkrp1(p->NT);
     p->smemP = smem_ppass(p->NT);
     int occ = 1;
-#define CALL(NT_, KS_) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused<KS_, 0>, 256, 0));
+#define CALL(NT_, KS_) CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fused<KS_, 1>, 256, 0));
     {
         auto q = [&]() -> int { TRITD_DISPATCH_R(r, CALL) return TRITD_OK; };
         if ((s = q()) != TRITD_OK) return bail(s);
@@ -1235,6 +1234,56 @@ extern "C" int tritd_triple_product_f64(tritd_ctx* c, const double* A, const dou
     if (s == TRITD_OK && cudaGetLastError() != cudaSuccess) s = fail(TRITD_ERR_CUDA, "triple_product kernel failed");
     tritd_problem_destroy(p);
     return s;
+}
+
+// Design matrices / triple product of the original (Qi) triple decomposition -- origin_triple_tensor/buildF.m,
+// buildG.m, buildH.m, triple_product.m.  which: 0 = F(B,C), 1 = G(A,C), 2 = H(A,B).
+static int design_qi_dev(tritd_ctx* c, const double* U, size_t nU, const double* V, size_t nV, long na, long nb, int r, int which,
+                         DevBuf& u, DevBuf& v, DevBuf& o) {
+    const size_t total = (size_t)r * r * na * nb;
+    ST_TRY(u.alloc(nU)); ST_TRY(v.alloc(nV)); ST_TRY(o.alloc(total));
+    CU_TRY(cudaMemcpyAsync(u.p, U, nU * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(v.p, V, nV * 8, cudaMemcpyHostToDevice, c->stream));
+    k_design_qi<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 16), 256, 0, c->stream>>>(u.p, v.p, o.p, na, nb, r, which);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+extern "C" int tritd_design_qi_f64(tritd_ctx* c, int which, const double* U, const double* V, int64_t na, int64_t nb, int r,
+                                   double* out) {
+    if (!c || !U || !V || !out) return fail(TRITD_ERR_INVALID, "NULL argument");
+    if (which < 0 || which > 2 || na < 1 || nb < 1) return fail(TRITD_ERR_INVALID, "bad design-matrix request");
+    ST_TRY(check_r(r));
+    CU_TRY(cudaSetDevice(c->device));
+    const size_t R = (size_t)r * r;
+    // which 0: U = B (r x n2 x r), V = C (r x r x n3); 1: U = A (n1 x r x r), V = C; 2: U = A, V = B (r x n2 x r)
+    DevBuf u, v, o;
+    ST_TRY(design_qi_dev(c, U, R * na, V, R * nb, (long)na, (long)nb, r, which, u, v, o));
+    CU_TRY(cudaMemcpyAsync(out, o.p, R * na * nb * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return TRITD_OK;
+}
+
+extern "C" int tritd_triple_product_qi_f64(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1,
+                                           int64_t n2, int64_t n3, int r, double* Xhat) {
+    if (!c || !A || !B || !C || !Xhat) return fail(TRITD_ERR_INVALID, "NULL argument");
+    if (n1 < 1 || n2 < 1 || n3 < 1) return fail(TRITD_ERR_INVALID, "bad size");
+    ST_TRY(check_r(r));
+    CU_TRY(cudaSetDevice(c->device));
+    const size_t R = (size_t)r * r, N = (size_t)n1 * n2 * n3;
+    DevBuf u, v, f, a, x;
+    ST_TRY(design_qi_dev(c, B, R * n2, C, R * n3, (long)n2, (long)n3, r, 0, u, v, f));       // F (r^2 x n2 n3)
+    ST_TRY(a.alloc(R * n1)); ST_TRY(x.alloc(N));
+    CU_TRY(cudaMemcpyAsync(a.p, A, R * n1 * 8, cudaMemcpyHostToDevice, c->stream));
+    // Xhat = reshape(A, [n1, r^2]) * F : column k = q + r*s of unfold(A,1) is A(:,q,s)
+    k_unfold1_times<<<(unsigned)std::min<size_t>((N + 255) / 256, 148 * 16), 256, 0, c->stream>>>(a.p, f.p, x.p, (long)n1,
+                                                                                                 (size_t)n2 * n3, (int)R);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    CU_TRY(cudaMemcpyAsync(Xhat, x.p, N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return TRITD_OK;
 }
 
 // [rmse, nrmse] = evaluate(Xhat, gt, mask) with Xhat = triple_product(A,B,C) formed on the device

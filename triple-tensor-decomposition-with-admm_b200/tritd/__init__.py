@@ -69,6 +69,8 @@ SYMBOLS = {
     "tritd_trim": (C.c_int, [_vp]),
     "tritd_evaluate_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, C.c_int, _vp, _vp, C.POINTER(C.c_double),
                                      C.POINTER(C.c_double)]),
+    "tritd_design_qi_f64": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _i64, C.c_int, _vp]),
+    "tritd_triple_product_qi_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, C.c_int, _vp]),
     "tritd_als_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int, C.c_int32, C.c_double, C.c_int32, _vp, _vp, _vp,
                                 _vp, _vp, _vp, _vp, C.POINTER(C.c_int32)]),
     "tritd_problem_create": (C.c_int, [_vp, _i64, _i64, _i64, C.c_int, C.POINTER(_vp)]),
@@ -401,6 +403,41 @@ def triple_product(A, B, Cc, ctx=None):
     X = np.zeros((n1, n2, n3), order="F")
     ctx = ctx or default_context()
     _check(load_library().tritd_triple_product_f64(ctx._h, _ptr(A), _ptr(B), _ptr(Cc), n1, n2, n3, r, _ptr(X)))
+    return X
+
+
+def _design_qi(which, U, V, na, nb, r, ctx):
+    out = np.zeros((r * r, na * nb), order="F")
+    ctx = ctx or default_context()
+    _check(load_library().tritd_design_qi_f64(ctx._h, which, _ptr(U), _ptr(V), na, nb, r, _ptr(out)))
+    return out
+
+
+def buildF_qi(B, Cc, ctx=None):
+    """F = buildF(B,C) of the original (Qi) model   (origin_triple_tensor/buildF.m:4-6)."""
+    _, B, Cc, r = _factor_dims(None, B, Cc)
+    return _design_qi(0, B, Cc, B.shape[1], Cc.shape[2], r, ctx)
+
+
+def buildG_qi(A, Cc, ctx=None):
+    """G = buildG(A,C) of the original (Qi) model   (origin_triple_tensor/buildG.m:9-11)."""
+    A, _, Cc, r = _factor_dims(A, None, Cc)
+    return _design_qi(1, A, Cc, A.shape[0], Cc.shape[2], r, ctx)
+
+
+def buildH_qi(A, B, ctx=None):
+    """H = buildH(A,B) of the original (Qi) model   (origin_triple_tensor/buildH.m:9-11)."""
+    A, B, _, r = _factor_dims(A, B, None)
+    return _design_qi(2, A, B, A.shape[0], B.shape[1], r, ctx)
+
+
+def triple_product_qi(A, B, Cc, ctx=None):
+    """Xhat(i,j,t) = sum_{p,q,s} A(i,q,s) B(p,j,s) C(p,q,t)   (origin_triple_tensor/triple_product.m)."""
+    A, B, Cc, r = _factor_dims(A, B, Cc)
+    n1, n2, n3 = A.shape[0], B.shape[1], Cc.shape[2]
+    X = np.zeros((n1, n2, n3), order="F")
+    ctx = ctx or default_context()
+    _check(load_library().tritd_triple_product_qi_f64(ctx._h, _ptr(A), _ptr(B), _ptr(Cc), n1, n2, n3, r, _ptr(X)))
     return X
 
 
