@@ -32,7 +32,11 @@
  * with tritd_create_rank() is one rank of an NCCL communicator (one process
  * per GPU; the 128-byte unique id is exchanged by the caller, e.g. through
  * torch.distributed); every rank then passes only ITS slab of D / C0 and
- * receives its slab of O / C, while A and B are replicated.
+ * receives its slab of O / C, while A and B are replicated (bitwise equal on all ranks).
+ * With 2..8 ranks on one node the per-iteration partials are exchanged through NVLink peer
+ * mailboxes mapped with CUDA IPC (NCCL is then used for set-up only); TRITD_XCHG_NCCL=1 in the
+ * environment selects NCCL all-reduces instead.  tritd_problem_create(), tritd_problem_init() and
+ * the solver calls are collective: every rank must make them in the same order.
  */
 #ifndef TRITD_H
 #define TRITD_H
@@ -158,13 +162,15 @@ int tritd_problem_get(tritd_problem* p, double* A, double* B, double* C, double*
 /* Device-side views (dense column-major copies written to caller-owned device memory). */
 int tritd_problem_get_O_dev(tritd_problem* p, double* O_dev);
 int tritd_problem_get_L_dev(tritd_problem* p, double* L_dev);
-/* Per-phase device timing: when enabled, every enqueued iteration is bracketed by CUDA events on
- * the context's stream at its phase boundaries.  tritd_problem_phase_ms() synchronises, adds up
+/* Per-phase device timing: when enabled, every enqueued iteration is launched kernel by kernel (no graph replay)
+ * and bracketed by CUDA events on the context's stream at its phase boundaries.  tritd_problem_phase_ms() synchronises, adds up
  * the elapsed milliseconds of each phase over all iterations recorded since the last call into
  * ms_out[TRITD_NPHASE] and reports how many iterations that was.  Phases:
- *   0 mode-1 MTTKRP (+partial reduce)   1 all-reduce + solve A + Gram(A)   2 shared pass P = T x_1 A
- *   3 RHS_B/all-reduce/solve B/Gram(B)/RHS_C/solve C/Gram(C)   4 fused L/O/E/dual/T/norm kernel
- *   5 norm reduce + all-reduce + errHist/mu/stopping rule */
+ *   0 mode-1 MTTKRP (first iteration only; later the partials come from phase 4 and are summed in phase 1)
+ *   1 update A: RHS reduction (+exchange), ridge inverse, apply, Gram(A)   2 shared pass P = T x_1 A
+ *   3 updates B and C: RHS reductions (+exchange), ridge inverses, apply, Gram(B), Gram(C)
+ *   4 fused L/O/E/dual/T/norm kernel, on the peer-exchange and single-rank paths including errHist/mu/stopping rule
+ *   5 NCCL path only: all-reduce of the residual sums + errHist/mu/stopping rule */
 #define TRITD_NPHASE 6
 int tritd_problem_set_profiling(tritd_problem* p, int enable);
 int tritd_problem_phase_ms(tritd_problem* p, double* ms_out, int32_t* iters_out);
