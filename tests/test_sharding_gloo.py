@@ -1,6 +1,9 @@
 """N>1 host-side logic on CPU: world_size-2 gloo processes run the mode-3 sharded restatement of the
-iteration (oracle/tritd_oracle_sharded.py), all-reducing [RHS_A ; C3'C3], RHS_B and the residual norms
-exactly where libtritd calls NCCL, and must reproduce the unsharded oracle -- including an uneven split."""
+iteration (oracle/tritd_oracle_sharded.py), exchanging [RHS_A ; C3'C3], RHS_B and the residual norms
+exactly where libtritd does, and must reproduce the unsharded oracle -- including an uneven split.
+Two exchange models: a gloo all-reduce (libtritd's NCCL path) and the peer-mailbox rule of
+csrc/kernels_xchg.cuh (every rank receives all ranks' partials and sums them in RANK ORDER), under which
+the replicated factors and the error history must be BITWISE equal on all ranks."""
 import os
 import socket
 import sys
@@ -22,7 +25,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, n3, iters, out_dir):
+def _worker(rank, world, port, case, n3, iters, out_dir, exchange):
     for p in (os.path.join(ROOT, "triple-tensor-decomposition-with-admm_b200"), os.path.join(ROOT, "oracle"),
               os.path.join(ROOT, "tests", "golden")):
         sys.path.insert(0, p)
@@ -41,8 +44,15 @@ def _worker(rank, world, port, case, n3, iters, out_dir):
 
     def allreduce(x):
         t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).copy())
-        dist.all_reduce(t)
-        return t.numpy()
+        if exchange == "allreduce":
+            dist.all_reduce(t)
+            return t.numpy()
+        slots = [torch.empty_like(t) for _ in range(world)]        # the mailbox: one slot per source rank
+        dist.all_gather(slots, t)
+        acc = slots[0].numpy().copy()
+        for s_ in slots[1:]:                                         # rank order, the same on every rank
+            acc = acc + s_.numpy()
+        return acc
 
     A1, B2, C3 = orc.factors_to_unfolded(A0, B0, C0)
     A1s, B2s, C3s, Os, ehs = orcs.admm_sharded(np.asfortranarray(D[:, :, t0:t1]), r, o, A1, B2, C3[t0:t1], allreduce)
@@ -51,15 +61,16 @@ def _worker(rank, world, port, case, n3, iters, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["allreduce", "mailbox"])
 @pytest.mark.parametrize("case,n3,iters", [("small_40x36x24_r5", 24, 6), ("odd_33x17x9_r2", 9, 6)])
-def test_two_rank_sharded_iteration_equals_oracle(case, n3, iters, tmp_path):
+def test_two_rank_sharded_iteration_equals_oracle(case, n3, iters, exchange, tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     import make_golden
     import tritd_oracle as orc
     from conftest import rel_err
 
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), case, n3, iters, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), case, n3, iters, str(tmp_path), exchange), nprocs=world, join=True)
     D, r, o, A0, B0, C0 = make_golden.case_inputs(case)
     o = dict(o, maxIter=iters, tol=0.0)
     A, B, C, O, eh = orc.triple_decomp_ADMM(D, r, o, A0, B0, C0)
@@ -68,6 +79,9 @@ def test_two_rank_sharded_iteration_equals_oracle(case, n3, iters, tmp_path):
     for p in parts:
         assert rel_err(p["eh"], eh) < 1e-10                                                 # identical on every rank
         assert rel_err(p["A1"], orc.unfold(A, 1)) < 1e-9 and rel_err(p["B2"], orc.unfold(B, 2)) < 1e-9   # replicated
+    if exchange == "mailbox":          # rank-ordered sums: replicas are bitwise equal, no broadcast needed
+        assert np.array_equal(parts[0]["A1"], parts[1]["A1"]) and np.array_equal(parts[0]["B2"], parts[1]["B2"])
+        assert np.array_equal(parts[0]["eh"], parts[1]["eh"])
     C3 = np.concatenate([p["C3"] for p in parts], axis=0)
     Ocat = np.concatenate([p["O"] for p in parts], axis=2)
     assert rel_err(C3, orc.unfold(C, 3)) < 1e-9 and rel_err(Ocat, O) < 1e-9                  # slabs tile the tensor
