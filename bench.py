@@ -3,24 +3,36 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfgX] [--impl reference]
 
-One "step" = one ADMM iteration (triple_decomp_ADMM.m:31-66) on the synthetic tensor of the
-named BASELINE config.  N=1 default workload: cfg3 (240x320x300, r=5), the shape the metric is
-quoted on.  N>1 (launched by torch.distributed.run, one rank per GPU): the SAME tensor sharded
-along mode 3 over the ranks ("strong" scaling), [RHS ; Gram] partials all-reduced with NCCL.
+One "step" = one ADMM iteration (triple_decomp_ADMM.m:31-66) on the synthetic tensor of the named BASELINE config.
+N=1 default workload: cfg3 (240x320x300, r=5), the shape the metric is quoted on.  N>1 (launched by
+torch.distributed.run, one rank per GPU): the SAME tensor sharded along mode 3 over the ranks ("strong" scaling); the
+[RHS ; Gram] partials travel through NVLink peer mailboxes inside the update kernels (NCCL only for set-up).
 
 Prints ONE JSON line (rank 0):
-  value     iterations/s with all inputs resident in HBM, timed with CUDA events on the launching
-            stream over exactly K iterations after W warm-up iterations, max over ranks;
-  e2e       iterations/s of one reference-facing call (tritd_admm_f64 through ctypes) with HOST
-            buffers: pinned D in, A/B/C/O/errHist out, H2D and D2H inside the timed region;
-  roofline  the fused element-wise kernel: 64*N algorithmic bytes per launch / its CUDA-event time;
-  cpu_baseline  the multi-threaded CPU port of the oracle timed on this box's host cores (rank 0, N=1).
---impl reference times that port alone (the MATLAB reference cannot run here).
+  value     iterations/s with all inputs resident in HBM, timed with CUDA events on the launching stream over
+            exactly K iterations after W warm-up iterations, max over ranks; at N>1 an untimed device-side
+            rendezvous (1-element NCCL all-reduce on the timed stream) precedes the first event, so process start
+            skew is not billed to the K steps;
+  e2e       iterations/s of the reference-facing call (tritd_admm_f64 through ctypes) with HOST buffers: pinned
+            D in, A/B/C/O/errHist out, H2D and D2H inside the timed region;
+  roofline  k_admm, the fused element-wise kernel: 64*N algorithmic bytes per launch / its CUDA-event time / the
+            measured HBM peak; `ppass` and `fp64` carry the FP64-tensor fractions against the DMMA peak measured in
+            this run;
+  parity_vs_fixture  max relative deviation of the first errHist values of this very run (any N) from the committed
+            CPU-oracle fixture tests/golden/fullsize_errhist.json;
+  cpu_baseline  the multi-threaded CPU port of the oracle timed on this box's host cores (rank 0, N=1);
+  configs   (N=1) device-resident iterations/s of the other BASELINE configs; secondary = cfg5, the shape the north
+            star's scaling target names (every N).
+--impl reference times the CPU port alone (MATLAB cannot run here; with octave/matlab on PATH and
+TRITD_REFERENCE_DIR set, the reference's own .m is timed through tools/reference_dump.m instead).
 """
 import argparse
 import json
 import os
+import shutil
+import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -36,6 +48,7 @@ import numpy as np  # noqa: E402
 FUSED_BYTES = 64.0
 METRIC = "admm_iterations_per_second"
 UNIT = "iter/s"
+L2_MB = 126.0
 
 
 def load_peaks():
@@ -44,6 +57,29 @@ def load_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_fixture():
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "fullsize_errhist.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def make_config_dict(name, world):
+    """`config` of the JSON line -- built by the same function in both arms so the driver sees identical dicts."""
+    from tritd import synth
+    n1, n2, n3, r = synth.CONFIGS[name][:4]
+    n3l = -(-n3 // world)
+    mb = n1 * n2 * n3l * 8e-6
+    if 5 * mb > 2 * L2_MB:
+        l2 = "inputs larger than L2 (5 streamed state arrays x %.0f MB per rank vs %.0f MB L2), no flush" % (mb, L2_MB)
+    else:
+        l2 = ("per-rank state (5 streamed arrays x %.0f MB) is comparable to the %.0f MB L2: iterations run back to back exactly as "
+              "in a real solve, the state an iteration leaves in L2 is what the next one finds; no flush" % (mb, L2_MB))
+    return {"workload": f"{name}: {synth.DESCRIPTIONS[name]}", "n1": n1, "n2": n2, "n3": n3, "r": r,
+            "sharding": f"mode-3 slabs over {world} rank(s)", "l2": l2}
 
 
 def workload_arrays(name, t0=None, t1=None):
@@ -112,15 +148,23 @@ def cpu_oracle_rate(name, steps, warmup, budget_s):
     the iteration is linear in n3 -- and the rate is scaled by t_slices/n3 to the full workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import tritd_oracle_mt as mt
+    from tritd import synth
     cores = os.cpu_count() or 1
-    D, r, opts, A0, B0, C0, (n1, n2, n3) = workload_arrays(name)
+    n1, n2, n3, r, kind, frac, seed, opts = synth.CONFIGS[name]
     cal = min(4, n3)
+    big = n1 * n2 * n3 > 2e8           # cfg5: never materialise the whole tensor on the host for a CPU sample
+    Dfull = None
+    if big:
+        first = lambda k: synth.make_lowrank_sparse(n1, n2, n3, r, frac, seed, t0=0, t1=k)   # noqa: E731
+    else:
+        Dfull = workload_arrays(name)[0]
+        first = lambda k: np.asfortranarray(Dfull[:, :, :k])   # noqa: E731
+    A0, B0, C0 = synth.init_factors(n1, n2, n3, r, 100 + seed)
     t = time.perf_counter()
-    mt.triple_decomp_ADMM(np.asfortranarray(D[:, :, :cal]), r, dict(opts, maxIter=2, tol=0.0, disp=0), A0, B0,
-                          np.asfortranarray(C0[:, :, :cal]), threads=cores)
+    mt.triple_decomp_ADMM(first(cal), r, dict(opts, maxIter=2, tol=0.0, disp=0), A0, B0, np.asfortranarray(C0[:, :, :cal]), threads=cores)
     per_slice_iter = (time.perf_counter() - t) / (2 * cal)
     t_slices = int(max(min(4, n3), min(n3, budget_s / max(per_slice_iter * (steps + warmup), 1e-9))))
-    Ds = np.asfortranarray(D[:, :, :t_slices]); Cs = np.asfortranarray(C0[:, :, :t_slices])
+    Ds = first(t_slices); Cs = np.asfortranarray(C0[:, :, :t_slices])
     stamps = [time.perf_counter()]
     mt.triple_decomp_ADMM(Ds, r, dict(opts, maxIter=steps + warmup, tol=0.0, disp=0), A0, B0, Cs,
                           on_iter=lambda *a: stamps.append(time.perf_counter()), threads=cores)
@@ -132,22 +176,55 @@ def cpu_oracle_rate(name, steps, warmup, budget_s):
     return rate_full, sample, dt
 
 
+def matlab_reference_rate(name, steps):
+    """The reference's own .m under Octave / MATLAB, when an interpreter is on PATH and TRITD_REFERENCE_DIR points at
+    a checkout of the reference (it does not exist on the GPU box by default): tools/reference_dump.m with
+    maxIter = steps.  Returns (rate, sample, interpreter) or None."""
+    exe = shutil.which("octave") or shutil.which("matlab")
+    refdir = os.environ.get("TRITD_REFERENCE_DIR")
+    if not exe or not refdir or not os.path.isdir(os.path.join(refdir, "fast_robust_triple_tensor")):
+        return None
+    from scipy.io import loadmat, savemat
+    D, r, opts, A0, B0, C0, shape = workload_arrays(name)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.mat"), os.path.join(td, "out.mat")
+        o = {k: float(opts[k]) for k in ("mu", "rho", "lambda", "lambda2")}
+        o.update(maxIter=float(steps), tol=0.0, disp=0.0)
+        savemat(fin, dict(D=D, r=float(r), opts=o, A0=A0, B0=B0, C0=C0), format="5")
+        call = f"addpath('{os.path.join(ROOT, 'tools')}'); reference_dump('{refdir}', '{fin}', '{fout}');"
+        cmd = [exe, "--eval", call] if exe.endswith("octave") else [exe, "-batch", call]
+        subprocess.run(cmd, check=True, timeout=1800, stdout=subprocess.DEVNULL)
+        m = loadmat(fout)
+    sec = float(m["seconds"].ravel()[0])
+    its = int(m["errHist"].size)
+    return its / sec, f"{its} iterations of the unmodified fast_robust_triple_tensor/triple_decomp_ADMM.m under {os.path.basename(exe)} on {name}", exe
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     name = args.workload
     steps, warm = args.steps, args.warmup
-    rate, sample, dt = cpu_oracle_rate(name, steps, warm, budget_s=120.0)
-    from tritd import synth
-    n1, n2, n3, r = synth.CONFIGS[name][:4]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    kind, note = "port", "reference is MATLAB and cannot run here (no MATLAB/Octave); this is the multi-threaded CPU port of the oracle"
+    real = None
+    try:
+        real = matlab_reference_rate(name, max(2, min(steps, 5)))
+    except Exception as exc:
+        note += f" (an Octave/MATLAB attempt failed: {type(exc).__name__})"
+    if real:
+        rate, sample, exe = real
+        kind, note = "reference", f"the reference's own .m timed under {exe}"
+    else:
+        rate, sample, dt = cpu_oracle_rate(name, steps, warm, budget_s=120.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": f"{name}: {synth.DESCRIPTIONS[name]}", "n1": n1, "n2": n2, "n3": n3, "r": r},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "data": "synthetic", "config": make_config_dict(name, max(world, args.gpus, 1)),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is MATLAB and cannot run here (no MATLAB/Octave); this is the multi-threaded CPU port of the oracle",
+        "note": note,
     }
     print(json.dumps(line), flush=True)
 
@@ -162,6 +239,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--secondary", default="cfg5", help="second workload measured device-resident only (\"\" to skip)")
+    ap.add_argument("--configs", default="cfg1,cfg2,cfg4", help="other BASELINE configs measured device-resident at N=1 (\"\" to skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -187,9 +265,9 @@ def main():
     n1, n2, n3, r = synth.CONFIGS[name][:4]
     t0, t1 = tritd.slab_bounds(n3, world, rank) if world > 1 else (0, n3)
     D, r, opts, A0, B0, C0, _ = workload_arrays(name, t0 if world > 1 else None, t1 if world > 1 else None)
-    n3l = t1 - t0
     N_global = n1 * n2 * n3
     K, W = args.steps, args.warmup
+    fixture = load_fixture()
 
     if world > 1:
         idbuf = [tritd.Context.nccl_unique_id() if rank == 0 else None]
@@ -203,6 +281,7 @@ def main():
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
+    rdv = torch.zeros(1, dtype=torch.float64, device="cuda")
 
     def barrier():
         torch.cuda.synchronize()
@@ -210,12 +289,30 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def device_rendezvous():
+        """N>1: an untimed 1-element all-reduce on the timed stream -- every rank's stream waits here for the slowest
+        process, so the first timed exchange does not pay the processes' start skew."""
+        if world > 1:
+            dist.all_reduce(rdv)
+
     def max_over_ranks(x):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    dmma_peak = max_over_ranks(-ctx.measure_dmma_peak(60.0))
+    dmma_peak = -dmma_peak              # min over ranks (conservative denominator)
+
+    def parity(wname, eh):
+        f = fixture.get(wname)
+        if not f:
+            return None
+        k = min(len(f["errHist"]), len(eh))
+        ref = np.array(f["errHist"][:k])
+        return {"max_rel_dev": float(np.max(np.abs(np.asarray(eh[:k]) - ref) / ref)), "iterations": k, "tolerance": 1e-8,
+                "fixture": "tests/golden/fullsize_errhist.json (CPU oracle)"}
 
     def measure(wname, Dw, A0w, B0w, C0w, optsw, shape, rw, Kw, Ww, sample_clocks):
         """Device-resident throughput of `Kw` iterations after `Ww` warm-up iterations (+ per-kernel times)."""
@@ -234,6 +331,7 @@ def main():
             sampler.start()
         launches0 = ctx.launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        device_rendezvous()
         e0.record(stream)
         prob.enqueue(Kw)                      # Kw iterations back to back on `stream` (CUDA-graph replays), no host sync
         e1.record(stream)
@@ -254,16 +352,21 @@ def main():
         prob.sync()
         barrier()
         prob.set_profiling(True)
-        prob.enqueue(Kw)
+        device_rendezvous()
+        prob.enqueue(min(Kw, 50))
         phase_ms, nprof = prob.phase_ms()
         prob.set_profiling(False)
         prob.close()
         Nl = m1 * m2 * m3l
+        RSw = (rw * rw + 7) // 8 * 8
         fused_ms = phase_ms[4] / max(1, nprof)
+        ppass_ms = phase_ms[2] / max(1, nprof)
         return dict(value=Kw / (ms_total * 1e-3), ms_total=ms_total, launches=int(launches), N_local=Nl, N_global=m1 * m2 * m3,
                     fused_ms=fused_ms, achieved=FUSED_BYTES * Nl / (fused_ms * 1e-3) * 1e-9,
+                    ppass_ms=ppass_ms, ppass_tflops=2.0 * Nl * RSw / (ppass_ms * 1e-3) * 1e-12,
+                    fused_tflops=(2.0 * Nl * 4 * ((rw * rw + 3) // 4) + 2.0 * Nl * RSw) / (fused_ms * 1e-3) * 1e-12,
                     phase_ms={nm: phase_ms[i] / max(1, nprof) for i, nm in enumerate(tritd.PHASES)},
-                    clocks=sampler.summary() if sampler else None, state_mb=Nl * 8e-6)
+                    clocks=sampler.summary() if sampler else None, state_mb=Nl * 8e-6, parity=parity(wname, res["errHist"]))
 
     # ---------------- device-resident throughput ----------------
     m = measure(name, D, A0, B0, C0, opts, (n1, n2, n3), r, K, W, True)
@@ -272,23 +375,23 @@ def main():
     # ---------------- roofline of the dominant kernel (fused element-wise pass) ----------------
     peak, peak_src = load_peaks()
     fused_ms, achieved = m["fused_ms"], m["achieved"]
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "fused_traffic.json")) as f:
-            tj = json.load(f)
-            if tj.get("workload") == name and world == 1:
-                traffic = tj.get("dram_bytes_per_launch")
-    except Exception:
-        pass
     R = r * r
     flops_iter = 8.0 * N_global * R + 2.0 * R * R * (n2 * n3 + n1 * n3 + n1 * n2)
     roofline = {"bound": "hbm", "kernel": "k_admm (TMA in / DMMA L reconstruction + O/E/dual/T update + residual norms + next mode-1 MTTKRP / TMA out)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "traffic_source": "not measured in this run; one ncu --set full capture per change is committed under profiles/ "
+                                  "(dram__bytes_read.sum + dram__bytes_write.sum per launch, r02_*_ncu_summary.csv)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": FUSED_BYTES * N_local, "kernel_ms": fused_ms,
-                "kernel_ms_source": "CUDA events recorded by the library around k_admm on the launching stream, averaged over a second pass of the same K steps",
+                "kernel_ms_source": "CUDA events recorded by the library around k_admm on the launching stream, averaged over a second pass of the same steps",
                 "iteration_GBps_vs_96N": 96.0 * N_global / world / (ms_total / K * 1e-3) * 1e-9,
-                "iteration_fp64_TFLOPs": flops_iter / world / (ms_total / K * 1e-3) * 1e-12,
-                "dmma_peak_TFLOPs_measured": 37.2,
+                "fp64": {"dmma_peak_TFLOPs": dmma_peak, "dmma_peak_source": "measured in this run (tritd_measure_dmma_peak, 60 ms of DMMA.8x8x4 probes; "
+                                                                            "DMMA and DFMA share one FP64 datapath on B200, profiles/r02_microbench.log)",
+                         "iteration_TFLOPs": flops_iter / world / (ms_total / K * 1e-3) * 1e-12,
+                         "iteration_frac_of_dmma_peak": flops_iter / world / (ms_total / K * 1e-3) * 1e-12 / dmma_peak,
+                         "k_admm_dmma_TFLOPs": m["fused_tflops"], "k_admm_frac_of_dmma_peak": m["fused_tflops"] / dmma_peak},
+                "ppass": {"bound": "tensor", "kernel": "k_ppass (P = T x_1 A1: FP64 DMMA fed by TMA, shared by update_B and update_C)",
+                          "achieved": m["ppass_tflops"], "peak": dmma_peak, "unit": "TFLOP/s", "frac": m["ppass_tflops"] / dmma_peak,
+                          "algorithmic_flops_per_launch": 2.0 * N_local * ((R + 7) // 8 * 8), "kernel_ms": m["ppass_ms"]},
                 "phase_ms_per_iter": m["phase_ms"]}
 
     # ---------------- end to end through the reference-facing call, host buffers ----------------
@@ -324,17 +427,48 @@ def main():
                "iterations": ncalls * per_call, "seconds": dt,
                "h2d_ms_per_call": float(np.mean([i["h2d_ms"] for i in infos])),
                "iterate_ms_per_call": float(np.mean([i["iterate_ms"] for i in infos])),
-               "d2h_ms_per_call": float(np.mean([i["d2h_ms"] for i in infos]))}
+               "d2h_ms_per_call": float(np.mean([i["d2h_ms"] for i in infos])),
+               "parity_vs_fixture": parity(name, eh)}
         # time-to-tolerance with the reference's own options (tol 1e-5, maxIter 100)
         barrier()
         tw = time.perf_counter()
         out = tritd.triple_decomp_ADMM(Dn, r, dict(opts, disp=0), A0, B0, C0, ctx=ctx, return_info=True, out_O=On)
         torch.cuda.synchronize()
         dt2 = max_over_ranks(time.perf_counter() - tw)
-        ttt = {"seconds_host_buffers": dt2, "seconds_device_loop": out[5]["iterate_ms"] * 1e-3, "iterations": len(out[4]),
-               "tol": opts["tol"], "maxIter": opts["maxIter"], "final_errHist": float(out[4][-1])}
+        nit = len(out[4])
+        ttt = {"seconds_host_buffers": dt2, "seconds_device_loop": out[5]["iterate_ms"] * 1e-3, "iterations": nit,
+               "tol": opts["tol"], "maxIter": opts["maxIter"], "final_errHist": float(out[4][-1]),
+               "stopped_by": "tol" if nit < int(opts["maxIter"]) else "maxIter (the relative-change rule did not fire at the reference's tol: this is time to maxIter)"}
         ctx.trim()
         del Dp, Op, Dn, On
+        if world == 1:
+            # a case where the rule does fire (the golden 'stop' case: cfg1-like 30^3, r = 3, tol 2e-2)
+            ws = synth.make_config("cfg1", shrink=(30, 30, 30))
+            so = dict(ws["opts"], maxIter=100, tol=2e-2, disp=0)
+            f0 = synth.init_factors(30, 30, 30, 3, 101)
+            tritd.triple_decomp_ADMM(ws["D"], 3, so, *f0, ctx=ctx)
+            tw = time.perf_counter()
+            o2 = tritd.triple_decomp_ADMM(ws["D"], 3, so, *f0, ctx=ctx)
+            ttt["case_where_the_rule_fires"] = {"workload": "cfg1-like 30x30x30, r=3, tol=2e-2", "iterations": len(o2[4]),
+                                                "seconds_host_buffers": time.perf_counter() - tw}
+            ctx.trim()
+
+    # ---------------- the other BASELINE configs, device-resident (N=1) ----------------
+    others = []
+    del D
+    if world == 1 and args.configs:
+        for cname in [c for c in args.configs.split(",") if c and c != name and c != args.secondary]:
+            try:
+                Dc, rc, oc, a0, b0, c0, shp = workload_arrays(cname)
+                Kc = max(10, min(K, 200 if np.prod(shp) < 5e7 else 40))
+                mc = measure(cname, Dc, a0, b0, c0, oc, shp, rc, Kc, 5, False)
+                others.append({"workload": f"{cname}: {synth.DESCRIPTIONS[cname]}", "value": mc["value"], "unit": UNIT, "steps": Kc,
+                               "ms_per_step": mc["ms_total"] / Kc, "k_admm_GBps": mc["achieved"], "roofline_frac_k_admm": mc["achieved"] / peak,
+                               "ppass_frac_of_dmma_peak": mc["ppass_tflops"] / dmma_peak, "phase_ms_per_iter": mc["phase_ms"],
+                               "parity_vs_fixture": mc["parity"]})
+                del Dc
+            except Exception as exc:
+                others.append({"workload": cname, "error": f"{type(exc).__name__}: {exc}"})
 
     # ---------------- secondary workload: cfg5, the shape the north star's scaling target names ----------------
     secondary = None
@@ -342,7 +476,6 @@ def main():
         sname = args.secondary
         s1, s2, s3, sr = synth.CONFIGS[sname][:4]
         st0, st1 = tritd.slab_bounds(s3, world, rank) if world > 1 else (0, s3)
-        del D
         try:
             Ds, sr, sopts, sA0, sB0, sC0, _ = workload_arrays(sname, st0 if world > 1 else None, st1 if world > 1 else None)
             Ks = max(5, min(K, 30))
@@ -350,6 +483,7 @@ def main():
             secondary = {"workload": f"{sname}: {synth.DESCRIPTIONS[sname]}", "metric": METRIC, "value": ms_["value"], "unit": UNIT,
                          "steps": Ks, "warmup": 3, "ms_per_step": ms_["ms_total"] / Ks, "scaling": "strong",
                          "roofline_frac_k_admm": ms_["achieved"] / peak, "k_admm_GBps": ms_["achieved"],
+                         "k_admm_frac_of_dmma_peak": ms_["fused_tflops"] / dmma_peak, "ppass_frac_of_dmma_peak": ms_["ppass_tflops"] / dmma_peak,
                          "hbm_bound_iters_per_s_96N": peak * 1e9 / (96.0 * ms_["N_global"] / world),
                          "phase_ms_per_iter": ms_["phase_ms"], "state_MB_per_array_per_rank": ms_["state_mb"]}
         except Exception as exc:           # the headline line must not depend on the secondary workload
@@ -364,20 +498,22 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         rate, sample, _ = cpu_oracle_rate(name, steps=3, warmup=1, budget_s=20.0)
         cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
+        if secondary and "error" not in secondary:
+            try:
+                rate5, sample5, _ = cpu_oracle_rate(args.secondary, steps=2, warmup=1, budget_s=12.0)
+                secondary["cpu_baseline"] = {"value": rate5, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample5}
+            except Exception as exc:
+                secondary["cpu_baseline"] = {"skipped": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
+        cfg = make_config_dict(name, world)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{name}: {synth.DESCRIPTIONS[name]}", "n1": n1, "n2": n2, "n3": n3, "r": r,
-                       "sharding": f"mode-3 slabs over {world} rank(s)", "opts": {k: opts[k] for k in ("mu", "rho", "lambda", "lambda2")},
-                       "l2": ("inputs larger than L2 (5 streamed state arrays x %.0f MB per rank vs 126 MB L2), no flush" % (N_local * 8e-6))
-                             if 5 * N_local * 8e-6 > 2 * 126 else
-                             ("per-rank state (5 streamed arrays x %.0f MB) is comparable to the 126 MB L2: iterations run back to back "
-                              "exactly as in a real solve, the state an iteration leaves in L2 is what the next one finds; no flush" % (N_local * 8e-6))},
+            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "opts": {k: opts[k] for k in ("mu", "rho", "lambda", "lambda2")},
             "clocks": m["clocks"], "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "time_to_tol": ttt, "secondary": secondary,
+            "parity_vs_fixture": m["parity"], "time_to_tol": ttt, "configs": others, "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -56,7 +56,7 @@ typedef enum {
     TRITD_ERR_INVALID = 1,      /* bad argument (NULL, non-positive size, r out of range, ...) */
     TRITD_ERR_CUDA = 2,         /* CUDA runtime/driver failure or no device */
     TRITD_ERR_NCCL = 3,         /* NCCL missing or a collective failed */
-    TRITD_ERR_NUMERIC = 4,      /* ridge system not positive definite (Cholesky pivot <= 0 or non-finite) */
+    TRITD_ERR_NUMERIC = 4,      /* a ridge system contains NaN / Inf (MATLAB's pinv raises an error there too) */
     TRITD_ERR_UNSUPPORTED = 5   /* r > TRITD_MAX_R */
 } tritd_status;
 
@@ -101,6 +101,13 @@ void tritd_destroy(tritd_ctx* ctx);
 const char* tritd_last_error(void);
 const char* tritd_version(void);
 
+/* Sink of the progress lines ("Iter %d, errL=%.2e, errO=%.2e\n" every 10th iteration when opts.disp,
+ * triple_decomp_ADMM.m:60-62; "Iteration %d, relative error = %.4e\n" of triple_decomp_ALS.m:17-19).  Default: stdout.
+ * A MEX gateway points it at mexPrintf (the MATLAB desktop does not show the process's stdout); NULL restores the
+ * default.  Process-wide; called on the thread that runs the solver. */
+typedef void (*tritd_print_fn)(const char* line, void* user);
+void tritd_set_print(tritd_print_fn fn, void* user);
+
 /* Use an existing CUDA stream (a cudaStream_t passed as void*) for all work of this
  * context, so the caller can bracket it with its own events; NULL restores the
  * context's private stream. */
@@ -123,6 +130,21 @@ int tritd_admm_f64(tritd_ctx* ctx, const double* D_host, int64_t n1, int64_t n2,
                    double* A, double* B, double* C, double* O, double* L_or_null,
                    double* errHist, int32_t* iters_out, tritd_timing* timing_or_null);
 
+/* The same call with the two optional extensions of SURVEY 8f rank 2 (neither changes the default path):
+ *  - E_or_null: the auxiliary sparse variable E ("O,E : sparse components (clone E)", triple_decomp_ADMM.m:12), a
+ *    7th output of the gateway;
+ *  - mask_or_null: the completion variant the reference's drivers name but do not ship
+ *    ([A,B,C,O,E,Out] = triple_ADMM_masked(Y, ~mask_missing, r, opts), traffic_triple_comparison.m:53):
+ *    dense n1 x n2 x n3 bytes, non-zero = observed.  Unobserved entries carry no data-fit constraint: there
+ *    O = E = Y_L = Y_O = 0, they do not enter ||D||, resL or resO, and the low-rank target is imputed, T = L
+ *    (zero for the first iteration, the drivers' own zero-fill).  On the observed entries every statement of
+ *    :33-:65 is unchanged; an all-ones mask reproduces tritd_admm_f64 bit for bit.  Specified in DESIGN.md 4.6,
+ *    restated in oracle/tritd_oracle.py (triple_ADMM_masked). */
+int tritd_admm_ex_f64(tritd_ctx* ctx, const double* D_host, const unsigned char* mask_or_null, int64_t n1, int64_t n2,
+                      int64_t n3, int r, const tritd_opts* opts, const double* A0, const double* B0, const double* C0,
+                      double* A, double* B, double* C, double* O, double* E_or_null, double* L_or_null,
+                      double* errHist, int32_t* iters_out, tritd_timing* timing_or_null);
+
 /* tritd_admm_f64 keeps its device state (the N-sized arrays, tensor maps, the captured iteration graph) in the
  * context and reuses it when the next call has the same shape and rank; tritd_trim() releases it (tritd_destroy()
  * does so too). */
@@ -137,6 +159,10 @@ void tritd_problem_destroy(tritd_problem* p);
 /* Load this rank's slab of D (dense column-major n1 x n2 x n3_local). */
 int tritd_problem_set_D_host(tritd_problem* p, const double* D_host);
 int tritd_problem_set_D_dev(tritd_problem* p, const double* D_dev);
+/* Completion variant (see tritd_admm_ex_f64): mark the entries with mask == 0 as unobserved; call after set_D and
+ * before init.  set_D clears the mask again. */
+int tritd_problem_set_mask_host(tritd_problem* p, const unsigned char* mask_host);
+int tritd_problem_set_mask_dev(tritd_problem* p, const unsigned char* mask_dev);
 
 /* Reset the ADMM state (O = E = Y_L = Y_O = 0, mu = opts.mu, k = 0), install the
  * initial factors (host pointers, MATLAB 3-D shapes; C0 is this rank's slab) and
@@ -159,9 +185,20 @@ int tritd_problem_sync(tritd_problem* p);
  * `iters` doubles each. */
 int tritd_problem_get(tritd_problem* p, double* A, double* B, double* C, double* O, double* L,
                       double* errHist, double* errL, double* errO, int32_t* iters);
+/* E of the last finished iteration (host / device destination). */
+int tritd_problem_get_E(tritd_problem* p, double* E_host);
+int tritd_problem_get_E_dev(tritd_problem* p, double* E_dev);
 /* Device-side views (dense column-major copies written to caller-owned device memory). */
 int tritd_problem_get_O_dev(tritd_problem* p, double* O_dev);
 int tritd_problem_get_L_dev(tritd_problem* p, double* L_dev);
+/* [rmse, nrmse] = evaluate(triple_product(A,B,C), gt, mask) with the factors the solver holds on the device. */
+int tritd_problem_evaluate(tritd_problem* p, const double* gt_host, const unsigned char* mask_host, double* rmse,
+                           double* nrmse);
+/* pinv semantics of the ridge solves (:78/:86/:93): the solves invert the SPD system directly; when a pivot is not
+ * positive or min pivot / max pivot < 16 R eps they run a Jacobi eigen-decomposition and zero the singular values
+ * <= R * eps(sigma_max) exactly like MATLAB's pinv.  *fallbacks = solves of this run that took that path,
+ * *truncated = singular values they zeroed in total. */
+int tritd_problem_pinv_stats(tritd_problem* p, int32_t* fallbacks, int32_t* truncated);
 /* Per-phase device timing: when enabled, every enqueued iteration is launched kernel by kernel (no graph replay)
  * and bracketed by CUDA events on the context's stream at its phase boundaries.  tritd_problem_phase_ms() synchronises, adds up
  * the elapsed milliseconds of each phase over all iterations recorded since the last call into
@@ -176,6 +213,9 @@ int tritd_problem_set_profiling(tritd_problem* p, int enable);
 int tritd_problem_phase_ms(tritd_problem* p, double* ms_out, int32_t* iters_out);
 /* Number of kernels launched by this library on this context so far. */
 int64_t tritd_launch_count(const tritd_ctx* ctx);
+/* Measured FP64 tensor-core (DMMA.8x8x4) peak of the context's GPU in TFLOP/s: about `ms_budget` milliseconds of
+ * back-to-back probe launches.  The denominator of the FP64-tensor roofline fractions bench.py reports. */
+int tritd_measure_dmma_peak(tritd_ctx* ctx, double ms_budget, double* tflops);
 
 /* ---- the ALS solver -------------------------------- */
 
@@ -194,16 +234,25 @@ int tritd_als_f64(tritd_ctx* ctx, const double* X_host, int64_t n1, int64_t n2, 
 /* Xhat = triple_product(A,B,C)                      triple_product.m:1-8   */
 int tritd_triple_product_f64(tritd_ctx* ctx, const double* A, const double* B, const double* C,
                              int64_t n1, int64_t n2, int64_t n3, int r, double* Xhat);
+/* the same with the result left on the device (dense column-major, caller-owned device memory) */
+int tritd_triple_product_dev_f64(tritd_ctx* ctx, const double* A, const double* B, const double* C,
+                                 int64_t n1, int64_t n2, int64_t n3, int r, double* Xhat_dev);
 /* Xn = unfold(X, mode), mode in {1,2,3}             unfold.m:1-14          */
 int tritd_unfold_f64(tritd_ctx* ctx, const double* X, int64_t n1, int64_t n2, int64_t n3, int mode, double* Xn);
+int tritd_unfold_dev_f64(tritd_ctx* ctx, const double* X_dev, int64_t n1, int64_t n2, int64_t n3, int mode, double* Xn_dev);
 /* F = buildF(B,C)  r^2 x (n2 n3)                    buildF.m:17-21         */
 int tritd_buildF_f64(tritd_ctx* ctx, const double* B, const double* C, int64_t n2, int64_t n3, int r, double* F);
 /* G = buildG(A,C)  r^2 x (n1 n3)                    buildG.m:17-21         */
 int tritd_buildG_f64(tritd_ctx* ctx, const double* A, const double* C, int64_t n1, int64_t n3, int r, double* G);
 /* H = buildH(A,B)  r^2 x (n1 n2)                    buildH.m:17-21         */
 int tritd_buildH_f64(tritd_ctx* ctx, const double* A, const double* B, int64_t n1, int64_t n2, int r, double* H);
+/* device-pointer form of buildF/G/H: which = 0 F(B,C), 1 G(A,C), 2 H(A,B); U, V the MATLAB 3-D factor arrays,
+ * na / nb the two mode sizes (n2,n3 / n1,n3 / n1,n2); out r^2 x (na*nb) column-major */
+int tritd_build_design_dev_f64(tritd_ctx* ctx, int which, const double* U_dev, const double* V_dev, int64_t na, int64_t nb,
+                               int r, double* out_dev);
 /* O = soft_threshold(X, lam), n elements            soft_threshold.m:2     */
 int tritd_soft_threshold_f64(tritd_ctx* ctx, const double* X, int64_t n, double lam, double* out);
+int tritd_soft_threshold_dev_f64(tritd_ctx* ctx, const double* X_dev, int64_t n, double lam, double* out_dev);
 /* Design matrices and product of the ORIGINAL (Qi) triple decomposition, the model the README's
  * RPAS claim describes; origin_triple_tensor/buildF.m:4-6, buildG.m:9-11, buildH.m:9-11, triple_product.m.
  *   which = 0: F = buildF(B,C), U = B (r x n2 x r), V = C (r x r x n3), na = n2, nb = n3,
@@ -230,6 +279,13 @@ int tritd_evaluate_f64(tritd_ctx* ctx, const double* A, const double* B, const d
  * rhsA = X1*F' (n1 x r^2), rhsB = X2*G' (n2 x r^2), rhsC = X3*H' (n3 x r^2), column-major. */
 int tritd_mttkrp_f64(tritd_ctx* ctx, const double* X, const double* A, const double* B, const double* C,
                      int64_t n1, int64_t n2, int64_t n3, int r, int mode, double* rhs);
+
+/* One factor update in isolation -- what update_A/B/C do after the contraction (:77-78 / :86 / :93):
+ *   X = rhs * pinv(S1 o S2 + alpha*I)          rhs n x r^2, S1, S2 r^2 x r^2 (column-major), o = Hadamard product
+ * through the solver's own update kernel.  Optional outputs: the pseudo-inverse (r^2 x r^2), X'X (r^2 x r^2),
+ * info[0] = 1 when the truncating pinv path ran, info[1] = singular values it zeroed. */
+int tritd_factor_update_f64(tritd_ctx* ctx, const double* rhs, int64_t n, int r, const double* S1, const double* S2,
+                            double alpha, double* X, double* Ginv_or_null, double* XtX_or_null, int32_t* info_or_null);
 
 #ifdef __cplusplus
 }

@@ -16,16 +16,23 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import it, and only as the checker / timed CPU baseline.
 The product (libtritd.so) never calls into this file and has no CPU fallback.
 
-PARITY UNPINNED: the reference ships no golden vectors, no known-answer tests
+PARITY STATUS: the reference ships no golden vectors, no known-answer tests
 and no fixtures for this path, and neither MATLAB nor Octave is
-available to run it.  The third-party arithmetic it relies on is MathWorks
-MATLAB built-ins (pinv = LAPACK SVD with cutoff max(size)*eps(norm(G)),
-mtimes = BLAS dgemm, norm = dnrm2, randn), version not pinned by the
-reference.  The only pins that exist are *definitional*: the commented scalar
-loops in buildF.m:5-16, buildG.m:5-16, buildH.m:5-16 and the five-nested-loop
-triple_product in origin_triple_tensor/triple_decomp_ADMM.m:125-143.  Those are
-restated below as pure-Python loops (``*_loops``) and the vectorised oracle is
-checked against them in tests/test_oracle.py.
+available to run it.  What pins this oracle:
+  * the reference's OWN, UNMODIFIED .m sources executed in the build container
+    by the MATLAB-subset interpreter oracle/mlab.py (tests/golden/ref_m/*.npz,
+    generator tests/golden/make_ref_golden.py, checked in
+    tests/test_reference_pin.py): statement order, index conventions, operator
+    association, function resolution and the printed lines come from the
+    reference's source text;
+  * the definitional scalar loops the reference holds as comments (buildF.m:5-16,
+    buildG.m:5-16, buildH.m:5-16, origin_triple_tensor/triple_decomp_ADMM.m:125-143),
+    restated below as pure-Python loops (``*_loops``), tests/test_oracle.py;
+  * a MATLAB / Octave dump when one is dropped into tests/golden/matlab_*.mat
+    (tools/reference_dump.m); none is committed.
+STILL UNPINNED: MathWorks' built-ins themselves (pinv = LAPACK SVD with cutoff
+max(size)*eps(norm(G)), mtimes = BLAS dgemm, norm = dnrm2; MATLAB version not
+pinned by the reference) -- numpy / OpenBLAS / LAPACK stand in for them here.
 
 All arrays are column-major (``order='F'``) like MATLAB's.
 """
@@ -247,6 +254,61 @@ def triple_decomp_ADMM(D, r, opts, A0=None, B0=None, C0=None, rng=None,
         return A, B, C, O, errHist, dict(E=E, Y_L=Y_L, Y_O=Y_O, L=L, muL=muL, muO=muO,
                                          errL=errL_hist[:k], errO=errO_hist[:k])
     return A, B, C, O, errHist
+
+
+def triple_ADMM_masked(Y, mask, r, opts, A0, B0, C0):
+    """[A,B,C,O,E,Out] = triple_ADMM_masked(Y, mask, r, opts): the completion variant the reference's drivers name in
+    a comment (traffic_triple_comparison.m:53, video_triple_comparison.m:52) but do not ship -- there is NO reference
+    code for it, so this function IS the specification; it is an opt-in extension.
+
+    mask True = observed.  On the observed entries every statement is the one of triple_decomp_ADMM.m:33-59.  An
+    unobserved entry carries no data-fit constraint: O = E = Y_L = Y_O = 0 there, it does not enter ||D||, resL,
+    resO, and the low-rank target is imputed with the current estimate, T = L (zero before the first iteration: the
+    drivers' own zero-fill, traffic_triple_comparison.m:34-35).  With an all-true mask the statements reduce to
+    triple_decomp_ADMM exactly."""
+    for k in REQUIRED_OPTS:
+        if k not in opts:
+            raise KeyError(f"Unrecognized field name \"{k}\".")
+    Y = np.asfortranarray(Y, dtype=np.float64)
+    M = np.asfortranarray(mask).astype(bool)
+    n1, n2, n3 = Y.shape
+    muL = opts["mu"]; rhoL = opts["rho"]; muL_max = opts["mu"] * 1e6
+    muO = opts["mu"]; rhoO = opts["rho"]; muO_max = opts["mu"] * 1e6
+    lam = opts["lambda"]; lambda2 = opts["lambda2"]
+    maxIter = int(opts["maxIter"]); tol = opts["tol"]; disp = opts["disp"]
+    A = np.array(A0, dtype=np.float64, order="F"); B = np.array(B0, dtype=np.float64, order="F")
+    C = np.array(C0, dtype=np.float64, order="F")
+    D = np.where(M, Y, 0.0)
+    O = np.zeros((n1, n2, n3), order="F"); E = O.copy(); Y_L = O.copy(); Y_O = O.copy()
+    L = O.copy()                                       # imputation before the first iteration: zero fill
+    normD = np.linalg.norm(D.ravel(order="K"))
+    errHist = np.zeros(maxIter)
+    k = 0
+    for k in range(1, maxIter + 1):
+        T = np.where(M, D - O + (1 / muL) * Y_L, L)
+        A = update_A(T, A, B, C, lambda2)
+        B = update_B(T, A, B, C, lambda2)
+        C = update_C(T, A, B, C)
+        L = triple_product(A, B, C)
+        R1 = D - L + (1 / muL) * Y_L
+        R2 = E - (1 / muO) * Y_O
+        O = np.where(M, (muL * R1 + muO * R2) / (muL + muO), 0.0)
+        R3 = O + (1 / muO) * Y_O
+        E = np.where(M, np.sign(R3) * np.maximum(np.abs(R3) - lam / muO, 0), 0.0)
+        resL = np.where(M, D - L - O, 0.0)
+        resO = np.where(M, O - E, 0.0)
+        Y_L = Y_L + muL * resL
+        Y_O = Y_O + muO * resO
+        muL = min(muL * rhoL, muL_max)
+        muO = min(muO * rhoO, muO_max)
+        eL = np.linalg.norm(resL.ravel(order="K")) / normD
+        eO = np.linalg.norm(resO.ravel(order="K")) / normD
+        errHist[k - 1] = eL + eO
+        if disp and k % 10 == 0:
+            print("Iter %d, errL=%.2e, errO=%.2e" % (k, eL, eO))
+        if k > 1 and abs(errHist[k - 1] - errHist[k - 2]) < tol * errHist[k - 2]:
+            break
+    return A, B, C, O, E, dict(errHist=errHist[:k], L=L)
 
 
 def triple_decomp_ALS(X, r, opts, A0=None, B0=None, C0=None, rng=None, disp=False):

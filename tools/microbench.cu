@@ -40,6 +40,27 @@ __global__ void k_dfma(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA and DFMA in the same warp: CH DMMAs + NF DFMAs per iteration, all chains independent.  If the two share one
+// datapath the time is the SUM of the two pure loops, if they are separate pipes it is the MAX.
+template <int CH, int NF>
+__global__ void k_mix(double* out, int iters) {
+    double c[CH > 0 ? CH : 1][2], f[NF > 0 ? NF : 1];
+    for (int i = 0; i < CH; ++i) c[i][0] = c[i][1] = 0.0;
+    for (int i = 0; i < NF; ++i) f[i] = i;
+    double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4, fa = 1.0 + threadIdx.x * 1e-9, fb = threadIdx.x * 1e-7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < (CH > NF ? CH : NF); ++i) {
+            if (i < CH) dmma(c[i][0], c[i][1], a, b);
+            if (i < NF) f[i] = fma(f[i], fa, fb);
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < CH; ++i) s += c[i][0] + c[i][1];
+    for (int i = 0; i < NF; ++i) s += f[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void k_layout(const double* A, const double* B, double* C) {
     // C(8x8) = A(8x4, row-major) * B(4x8, stored B[k][n]) using the documented fragment ownership
     const int lane = threadIdx.x, g = lane >> 2, tig = lane & 3;
@@ -102,6 +123,20 @@ int main() {
             fl = (double)grid * warps * 32.0 * iters * 8 * 2.0;
             printf("DFMA 8 chains  warps/SM=%2d : %.3f ms  %.2f TFLOP/s\n", warps, ms, fl / ms * 1e-9);
         }
+    }
+    // do DMMA and DFMA share a datapath?  8 DMMA (8*512 flop/warp) + 8..64 DFMA (64 flop/warp each) per iteration
+    {
+        int grid = p.multiProcessorCount, warps = 16;
+        auto report = [&](const char* nm, float ms, double nd, double nf) {
+            double fd = (double)grid * warps * iters * nd * 512.0, ff = (double)grid * warps * 32.0 * iters * nf * 2.0;
+            printf("MIX %-18s: %.3f ms  DMMA %.2f + DFMA %.2f = %.2f TFLOP/s\n", nm, ms, fd / ms * 1e-9, ff / ms * 1e-9, (fd + ff) / ms * 1e-9);
+        };
+        report("8 dmma + 0 dfma", time_ms([&] { k_mix<8, 0><<<grid, warps * 32>>>(out, iters); }), 8, 0);
+        report("0 dmma + 16 dfma", time_ms([&] { k_mix<0, 16><<<grid, warps * 32>>>(out, iters); }), 0, 16);
+        report("8 dmma + 8 dfma", time_ms([&] { k_mix<8, 8><<<grid, warps * 32>>>(out, iters); }), 8, 8);
+        report("8 dmma + 16 dfma", time_ms([&] { k_mix<8, 16><<<grid, warps * 32>>>(out, iters); }), 8, 16);
+        report("8 dmma + 32 dfma", time_ms([&] { k_mix<8, 32><<<grid, warps * 32>>>(out, iters); }), 8, 32);
+        report("4 dmma + 32 dfma", time_ms([&] { k_mix<4, 32><<<grid, warps * 32>>>(out, iters); }), 4, 32);
     }
     // sustained DMMA (about 2 s) to see clocks under power
     {

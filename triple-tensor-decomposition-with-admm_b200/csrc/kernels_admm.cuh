@@ -12,8 +12,8 @@
 // A stage is JG (1 or 2) groups of 8 columns j of slice t for the whole i-tile, i.e. four 8*JG KB boxes
 // (D, Y_L, E, Y_O) fetched by ONE TMA op each through a 4-D view (i_lo=16, j, i_hi, t) of the
 // column-major arrays, which lands as [warp][8 j][16 i] with the 128B swizzle pattern the DMMA
-// accumulator layout reads conflict-free.  Consumers update the boxes in place (T over D; with WRITE_O a
-// fifth box for O -- the solver does not store O inside the loop, k_recover_O rebuilds it on demand); the TMA
+// accumulator layout reads conflict-free.  Consumers update the boxes in place (T over D; O is not stored
+// inside the loop, k_recover_O rebuilds it on demand); the TMA
 // warp then streams the boxes back with one TMA store each and refills the slot.  No thread touches HBM with a
 // load/store instruction; rows/columns outside the tensor are zero-filled on load and clipped on store by the
 // tensor maps (ld1 is a multiple of 16 so the padded rows exist and stay zero).  Algorithmic traffic:
@@ -48,11 +48,15 @@ struct AdmmArgs {
     int n1, n2, n3, RS;
     int n_jc;                          // j-chunks (32 columns)
     int tile_h;                        // rows per i-tile: 16 * (consumer warps used), <= 128
+    int refill_mode;                   // producer scheme: 0 deferred refill (one stage late), 1 immediate, 2 immediate with two producers
 };
 
-template <int KS, int NT, bool WRITE_O> struct AdmmCfg {
+// JGP: column groups per stage asked for (1 or 2).  Two-group stages give every warp two independent dependency
+// chains between barriers; one-group stages are half as large, so twice as many fit the ring and twice as many loads
+// are in flight per SM -- which wins depends on the shape (chosen at problem set-up, tritd.cu).
+template <int KS, int NT, int JGP = 2> struct AdmmCfg {
     static constexpr int PL = FusedCfg<KS>::PL;
-    static constexpr int NB = WRITE_O ? 5 : 4;                                  // boxes per stage
+    static constexpr int NB = 4;                                                // boxes per stage
     // large R: the B operand of L is read from the transposed chunk too (2-way bank conflict on a small share of
     // the shared-memory traffic) so that the second layout's 17 KB buy a two-group stage
     static constexpr bool kShareB = KS > 8;
@@ -60,10 +64,10 @@ template <int KS, int NT, bool WRITE_O> struct AdmmCfg {
     static constexpr int kAvail = 227 * 1024 - kFixed;
     // a stage holds JG groups of 8 columns: two when three such stages fit (more independent work per warp
     // between barriers), else one
-    static constexpr int JG = (kAvail / (NB * 2 * 8 * 128 * 8 + 1024)) >= 3 ? 2 : 1;
+    static constexpr int JG = (JGP >= 2 && (kAvail / (NB * 2 * 8 * 128 * 8 + 1024)) >= 3) ? 2 : 1;
     static constexpr int kBoxD = 8 * JG * 128;                                  // doubles per array per stage: [8 warps][8*JG j][16 i]
     static constexpr int kStageBytes = NB * kBoxD * 8 + 1024;                   // + the C3 row of the slice; keeps boxes 1 KB aligned
-    static constexpr int S = (kAvail / kStageBytes) > 6 ? 6 : (kAvail / kStageBytes);
+    static constexpr int S = (kAvail / kStageBytes) > 8 ? 8 : (kAvail / kStageBytes);
     static constexpr size_t kSmem = (size_t)S * kStageBytes + kFixed;
     static_assert(S >= 3, "ring too shallow");
 };
@@ -101,8 +105,13 @@ __device__ __forceinline__ double div_by(double a, double b, double y) {
 // expressions, every operation an explicit round-to-nearest intrinsic (no FMA contraction).
 struct AdmmPrm { double muL, muO, rmuL, rmuO, thr, musum, rmusum, rmuL_next; };
 
+template <bool MASKED>
 __device__ __forceinline__ void admm_point2(const AdmmPrm& p, double d, double l, double& yl, double& e, double& yo,
                                             double& o, double& tn, double& sL, double& sO) {
+    if (MASKED && d != d) {              // unobserved entry (NaN in D): no constraint, impute the low-rank estimate
+        yl = 0.0; e = 0.0; yo = 0.0; o = 0.0; tn = l;
+        return;
+    }
     const double dl = __dsub_rn(d, l);                                   // D - L
     const double r1 = __dadd_rn(dl, __dmul_rn(p.rmuL, yl));              // R1 = D - L + (1/muL)*Y_L
     const double my = __dmul_rn(p.rmuO, yo);                             // (1/muO)*Y_O
@@ -110,7 +119,8 @@ __device__ __forceinline__ void admm_point2(const AdmmPrm& p, double d, double l
     o = div_by(__dadd_rn(__dmul_rn(p.muL, r1), __dmul_rn(p.muO, r2)), p.musum, p.rmusum);
     const double r3 = __dadd_rn(o, my);                                  // R3 = O + (1/muO)*Y_O
     const double mx = fmax(__dsub_rn(fabs(r3), p.thr), 0.0);
-    const double en = r3 > 0.0 ? mx : (r3 < 0.0 ? -mx : 0.0);            // sign(R3).*max(|R3|-lambda/muO,0)
+    // sign(R3).*max(|R3|-lambda/muO,0); MATLAB: sign(NaN) = NaN, max(NaN,0) = 0, NaN*0 = NaN -> E = NaN where R3 is NaN
+    const double en = r3 > 0.0 ? mx : (r3 < 0.0 ? -mx : (r3 != r3 ? r3 : 0.0));
     const double resL = __dsub_rn(dl, o);                                // D - L - O
     const double resO = __dsub_rn(o, en);                                // O - E
     yl = __dadd_rn(yl, __dmul_rn(p.muL, resL));
@@ -126,9 +136,11 @@ __device__ __forceinline__ void admm_point2(const AdmmPrm& p, double d, double l
 // the consumers grow to 224 with setmaxnreg, so the DMMA accumulators and fragments never spill.
 constexpr int kAdmmThreads = 384;
 
-template <int KS, int NT, bool WRITE_O>
+// MASKED: the opt-in completion variant (tritd_admm_masked_f64): unobserved entries are stored as NaN
+// in D; there O = E = Y_L = Y_O = 0, the residuals do not count and the next target is T' = L (imputation).
+template <int KS, int NT, bool MASKED, int JGP = 2>
 __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant__ AdmmMaps maps, const AdmmArgs a) {
-    using Cfg = AdmmCfg<KS, NT, WRITE_O>;
+    using Cfg = AdmmCfg<KS, NT, JGP>;
     constexpr int PL = Cfg::PL, NB = Cfg::NB, S = Cfg::S, JG = Cfg::JG, kBoxD = Cfg::kBoxD;
     constexpr int kStageD = Cfg::kStageBytes / 8;
     constexpr int SPU = 4 / JG;           // stages per unit (32 columns of one slice)
@@ -160,10 +172,57 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
     if (warp >= 8) {
         // ---------------- TMA warpgroup: loads, stores, slot recycling ----------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (a.refill_mode != 0) {
+            // Producers: lane 0 of warp 8 (and of warp 9 when refill_mode == 2, alternating stages).  Stage q lives in
+            // slot q % S.  Once the consumers are done with stage q its four boxes go back with one TMA store each;
+            // as soon as those stores have READ shared memory the slot is refilled with stage q + S -- the slot never
+            // idles waiting for the next stage's completion.
+            const int np = a.refill_mode == 2 ? 2 : 1, me = warp - 8;
+            if (me < np && lane == 0 && nq > 0) {
+                tma_prefetch_desc(&maps.D); tma_prefetch_desc(&maps.YL); tma_prefetch_desc(&maps.E);
+                tma_prefetch_desc(&maps.YO); tma_prefetch_desc(&maps.T);
+                auto coords = [&](long q, int& j0, int& tt) {
+                    const long u = v0 + q / SPU;
+                    const int jg = (int)(q - (q / SPU) * SPU);
+                    const int jc = (int)(u / a.n3);
+                    tt = (int)(u - (long)jc * a.n3);
+                    j0 = jc * 32 + jg * (8 * JG);
+                };
+                auto issue_load = [&](long q) {
+                    const int sl = (int)(q % S);
+                    double* st = ring + (size_t)sl * kStageD;
+                    int j0, tt;
+                    coords(q, j0, tt);
+                    mbar_expect_tx(&full[sl], 4 * nw * JG * 1024 + NT * 8 * 8);
+                    tma_load_4d(st, &maps.D, &full[sl], 0, j0, it * nw, tt);
+                    tma_load_4d(st + kBoxD, &maps.YL, &full[sl], 0, j0, it * nw, tt);
+                    tma_load_4d(st + 2 * kBoxD, &maps.E, &full[sl], 0, j0, it * nw, tt);
+                    tma_load_4d(st + 3 * kBoxD, &maps.YO, &full[sl], 0, j0, it * nw, tt);
+                    bulk_load_1d(st + NB * kBoxD, a.C3 + (size_t)tt * a.RS, NT * 8 * 8, &full[sl]);   // C3 row of slice t
+                };
+                if (me == 0) for (long q = 0; q < S && q < nq; ++q) issue_load(q);
+                for (long q = me; q < nq; q += np) {
+                    const int sl = (int)(q % S);
+                    mbar_wait(&done[sl], (uint32_t)((q / S) & 1));
+                    double* st = ring + (size_t)sl * kStageD;
+                    int j0, tt;
+                    coords(q, j0, tt);
+                    tma_store_4d(&maps.T, st, 0, j0, it * nw, tt);
+                    tma_store_4d(&maps.YL, st + kBoxD, 0, j0, it * nw, tt);
+                    tma_store_4d(&maps.E, st + 2 * kBoxD, 0, j0, it * nw, tt);
+                    tma_store_4d(&maps.YO, st + 3 * kBoxD, 0, j0, it * nw, tt);
+                    tma_store_commit();
+                    if (q + S < nq) {
+                        tma_store_wait_read<0>();
+                        issue_load(q + S);
+                    }
+                }
+                tma_store_wait_all<0>();
+            }
+        } else
         if (warp == 8 && lane == 0 && nq > 0) {
             tma_prefetch_desc(&maps.D); tma_prefetch_desc(&maps.YL); tma_prefetch_desc(&maps.E);
             tma_prefetch_desc(&maps.YO); tma_prefetch_desc(&maps.T);
-            if (WRITE_O) tma_prefetch_desc(&maps.O);
             int ljc = jc0, lt = t0, ljg = 0, ls = 0;                 // load cursor
             auto issue_load = [&]() {
                 double* st = ring + (size_t)ls * kStageD;
@@ -188,7 +247,6 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
                 tma_store_4d(&maps.YL, st + kBoxD, 0, j0, it * nw, stt);
                 tma_store_4d(&maps.E, st + 2 * kBoxD, 0, j0, it * nw, stt);
                 tma_store_4d(&maps.YO, st + 3 * kBoxD, 0, j0, it * nw, stt);
-                if (WRITE_O) tma_store_4d(&maps.O, st + 4 * kBoxD, 0, j0, it * nw, stt);
                 tma_store_commit();
                 if (++sjg == SPU) { sjg = 0; if (++stt == a.n3) { stt = 0; ++sjc; } }
                 if (++ss == S) { ss = 0; sph ^= 1; }
@@ -295,13 +353,12 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
                         double2 e = s2[2 * (kBoxD / 2) + off];
                         double2 yo = s2[3 * (kBoxD / 2) + off];
                         double2 o;
-                        admm_point2(prm, d.x, l[0][c], yl.x, e.x, yo.x, o.x, tn[c].x, sL, sO);
-                        admm_point2(prm, d.y, l[1][c], yl.y, e.y, yo.y, o.y, tn[c].y, sL, sO);
+                        admm_point2<MASKED>(prm, d.x, l[0][c], yl.x, e.x, yo.x, o.x, tn[c].x, sL, sO);
+                        admm_point2<MASKED>(prm, d.y, l[1][c], yl.y, e.y, yo.y, o.y, tn[c].y, sL, sO);
                         s2[off] = tn[c];
                         s2[kBoxD / 2 + off] = yl;
                         s2[2 * (kBoxD / 2) + off] = e;
                         s2[3 * (kBoxD / 2) + off] = yo;
-                        if (WRITE_O) s2[4 * (kBoxD / 2) + off] = o;
                     }
                     // next iteration's X1*F': acc[m][n] += T'(i,j) B2(j,k) C3(t,k); k-step c covers j = j0 + 2*tig + c
 #pragma unroll

@@ -25,26 +25,66 @@ __global__ void __launch_bounds__(256) k_transpose(const double* in, double* out
     }
 }
 
-// Transposed Khatri-Rao product, the common form of buildF/G/H:
-//   out[k + R*(a + na*b)] = Xa[a][k] * Xb[b][k]      (Xa: na x RS, Xb: nb x RS row-major)
-// buildF: (Xa,Xb) = (B2,C3); buildG: (A1,C3); buildH: (A1,B2).
-__global__ void __launch_bounds__(256) k_khatri_rao_t(const double* Xa, const double* Xb, double* out, long na,
-                                                      long nb, int R, int RS) {
-    const size_t total = (size_t)R * na * nb;
-    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
-        const int k = (int)(e % R);
-        const size_t col = e / R;
-        const long aa = (long)(col % na), bb = (long)(col / na);
-        out[e] = Xa[(size_t)aa * RS + k] * Xb[(size_t)bb * RS + k];
+// The same transpose with 128-bit accesses on both sides (rows, cols even; 16-byte aligned bases): thread (tx, ty)
+// of a 16 x 16 grid moves the pairs (r0 + 2tx, r0 + 2tx + 1) of two columns in, and the pairs
+// (c0 + 2tx, c0 + 2tx + 1) of two rows out.
+__global__ void __launch_bounds__(256) k_transpose_v2(const double* in, double* out, long rows, long cols) {
+    __shared__ double tile[32][33];
+    const size_t boff = (size_t)blockIdx.z * rows * cols;
+    const long r0 = (long)blockIdx.x * 32, c0 = (long)blockIdx.y * 32;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int k = ty; k < 32; k += 16) {
+        const long r = r0 + 2 * tx, c = c0 + k;
+        if (r < rows && c < cols) {
+            const double2 v = *reinterpret_cast<const double2*>(in + boff + (size_t)c * rows + r);
+            tile[k][2 * tx] = v.x; tile[k][2 * tx + 1] = v.y;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = ty; k < 32; k += 16) {
+        const long c = c0 + 2 * tx, r = r0 + k;
+        if (r < rows && c < cols)
+            *reinterpret_cast<double2*>(out + boff + (size_t)r * cols + c) = make_double2(tile[2 * tx][k], tile[2 * tx + 1][k]);
     }
 }
 
-__global__ void __launch_bounds__(256) k_soft_threshold(const double* x, double* out, size_t n, double lam) {
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const double v = x[i];
-        const double mx = fmax(fabs(v) - lam, 0.0);
-        out[i] = v > 0.0 ? mx : (v < 0.0 ? -mx : 0.0);
+// buildF / buildG / buildH straight from the MATLAB factor arrays (no packed copies, no 64-bit div/mod per element):
+//   out[k + R*(a + na*b)] = U[uoff(k) + a*ua] * V[voff(k) + b*vb],   k = q + r*s
+//   which = 0  F(B,C): U = B (r x n2 x r): uoff = q + r*n2*s, ua = r;   V = C (r x r x n3): voff = k, vb = R
+//   which = 1  G(A,C): U = A (n1 x r x r): uoff = n1*k,       ua = 1;   V = C
+//   which = 2  H(A,B): U = A;                                           V = B (r x n2 x r): voff = q + r*nb*s, vb = r
+// A thread owns one (k, a) and walks over b: its U value is loaded once, consecutive threads write consecutive
+// doubles (coalesced), V(k, b) is a broadcast-like L1 hit.  grid = (ceil(R*na / 256), chunks of b).
+__global__ void __launch_bounds__(256) k_build_design(const double* __restrict__ U, const double* __restrict__ V,
+                                                      double* __restrict__ out, int na, int nb, int r, int which) {
+    const int R = r * r;
+    const unsigned e = blockIdx.x * 256u + threadIdx.x;
+    if (e >= (unsigned)R * (unsigned)na) return;
+    const int a = (int)(e / (unsigned)R), k = (int)(e - (unsigned)a * (unsigned)R);
+    const int q = k % r, sx = k / r;
+    const size_t uo = which == 0 ? (size_t)q + (size_t)r * na * sx + (size_t)a * r : (size_t)na * k + a;
+    const size_t vo = which == 2 ? (size_t)q + (size_t)r * nb * sx : (size_t)k;
+    const size_t vb = which == 2 ? (size_t)r : (size_t)R;
+    const double u = U[uo];
+    const size_t colstride = (size_t)R * na;
+    for (int b = blockIdx.y; b < nb; b += gridDim.y) out[e + colstride * b] = u * V[vo + vb * b];
+}
+
+__device__ __forceinline__ double soft1(double v, double lam) {
+    const double mx = fmax(fabs(v) - lam, 0.0);
+    return v > 0.0 ? mx : (v < 0.0 ? -mx : (v != v ? v : 0.0));     // sign(NaN) .* max(NaN, 0) = NaN * 0 = NaN in MATLAB
+}
+// 128-bit version (n2 = n / 2 pairs; the odd tail element is handled by the scalar kernel)
+__global__ void __launch_bounds__(256) k_soft_threshold_v2(const double2* __restrict__ x, double2* __restrict__ out, size_t n2, double lam) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n2; i += (size_t)gridDim.x * 256) {
+        const double2 v = x[i];
+        out[i] = make_double2(soft1(v.x, lam), soft1(v.y, lam));
     }
+}
+__global__ void __launch_bounds__(256) k_soft_threshold(const double* x, double* out, size_t n, double lam) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = soft1(x[i], lam);
 }
 
 // Design matrices of the ORIGINAL (Qi) triple decomposition, origin_triple_tensor/buildF.m:4-6, buildG.m:9-11,
@@ -90,22 +130,40 @@ __global__ void __launch_bounds__(256) k_unfold1_times(const double* __restrict_
 }
 
 // evaluate() of the reference's drivers (traffic_triple_comparison.m:194-202): per-CTA partials of
-//   sum_{mask} (Xhat - gt)^2  and  sum_{mask} gt^2   over padded column-major arrays (ld1 rows per column);
+//   sum_{mask} (Xhat - gt)^2  and  sum_{mask} gt^2   over column-major arrays with leading dimensions ldx / ldg;
 // mask is dense n1 x n2 x n3 bytes (nullptr = all true).  Fixed-order partial sums (deterministic).
 __global__ void __launch_bounds__(256) k_evaluate(const double* __restrict__ Xhat, const double* __restrict__ gt,
-                                                  const unsigned char* __restrict__ mask, int n1, int ld1, size_t ncols,
+                                                  const unsigned char* __restrict__ mask, int n1, int ldx, int ldg, size_t ncols,
                                                   double* part) {
     __shared__ double red[64];
     double a = 0.0, b = 0.0;
     for (size_t col = blockIdx.x; col < ncols; col += gridDim.x)
         for (int i = threadIdx.x; i < n1; i += 256) {
             if (mask && !mask[col * (size_t)n1 + i]) continue;
-            const double g = gt[col * (size_t)ld1 + i], d = Xhat[col * (size_t)ld1 + i] - g;
+            const double g = gt[col * (size_t)ldg + i], d = Xhat[col * (size_t)ldx + i] - g;
             a = fma(d, d, a);
             b = fma(g, g, b);
         }
     block_sum2(a, b, red);
     if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
+}
+
+// FP64 tensor-core peak probe: 8 independent DMMA.8x8x4 chains per warp (8 * 512 flop per warp and iteration).
+__global__ void __launch_bounds__(512) k_dmma_peak(double* out, int iters) {
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    const double a = threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-4;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * 512 + threadIdx.x] = s;
 }
 
 }  // namespace tritd

@@ -6,10 +6,10 @@
 // C3 = unfold(C,3) (n x R, R = r^2)
 //     X1*F' [i,k] = sum_{j,t} T(i,j,t) B2(j,k) C3(t,k)            (k_mttkrp1)
 //     P[t][j][k]  = sum_i     T(i,j,t) A1(i,k)                     (k_ppass)
-//     X2*G' [j,k] = sum_t C3(t,k) P[t][j][k]                       (k_rhsB)
-//     X3*H' [t,k] = sum_j B2(j,k) P[t][j][k]                       (k_rhsC)
+//     X2*G' [j,k] = sum_t C3(t,k) P[t][j][k]                       (k_upd, strided-sum source over t)
+//     X3*H' [t,k] = sum_j B2(j,k) P[t][j][k]                       (k_upd, strided-sum source over j)
 // P depends on T and the *new* A only, so one pass over T serves both the B and
-// the C update (Gauss-Seidel order is preserved: k_rhsC runs after B is solved).
+// the C update (Gauss-Seidel order is preserved: the sum over j runs after B is solved).
 //
 // Device layout: every N-sized array is column-major n1 x n2 x n3 with leading
 // dimension ld1 = n1 rounded up to even (16-byte columns for TMA / v2 access);
@@ -321,71 +321,6 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
                 }
             }
         }
-    }
-}
-
-// rhsB[j][k] = sum_t C3[t][k] * P[t][j][k]: one CTA per row j, 256 threads = 8 t-lanes x 32 k,
-// each lane sums t = l, l+8, ... in order, fixed tree over the lanes.
-__global__ void __launch_bounds__(256) k_rhsB(const double* P, const double* C3, double* rhsB, int n2, int n3, int RS,
-                                               const int* stop) {
-    if (*stop) return;
-    __shared__ double red[8][33];
-    const int j = blockIdx.x;
-    const int kl = threadIdx.x & 31, tl = threadIdx.x >> 5;
-    const size_t nrk = (size_t)n2 * RS;
-    for (int k0 = 0; k0 < RS; k0 += 32) {
-        const int k = k0 + kl;
-        double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        if (k < RS) {
-            int t = tl;
-            for (; t + 24 < n3; t += 32) {     // four independent chains
-                s = fma(C3[(size_t)t * RS + k], P[(size_t)t * nrk + (size_t)j * RS + k], s);
-                s1 = fma(C3[(size_t)(t + 8) * RS + k], P[(size_t)(t + 8) * nrk + (size_t)j * RS + k], s1);
-                s2 = fma(C3[(size_t)(t + 16) * RS + k], P[(size_t)(t + 16) * nrk + (size_t)j * RS + k], s2);
-                s3 = fma(C3[(size_t)(t + 24) * RS + k], P[(size_t)(t + 24) * nrk + (size_t)j * RS + k], s3);
-            }
-            for (; t < n3; t += 8) s = fma(C3[(size_t)t * RS + k], P[(size_t)t * nrk + (size_t)j * RS + k], s);
-            s = (s + s1) + (s2 + s3);
-        }
-        red[tl][kl] = s;
-        __syncthreads();
-        if (tl == 0 && k < RS)
-            rhsB[(size_t)j * RS + k] = ((red[0][kl] + red[1][kl]) + (red[2][kl] + red[3][kl])) +
-                                       ((red[4][kl] + red[5][kl]) + (red[6][kl] + red[7][kl]));
-        __syncthreads();
-    }
-}
-
-// rhsC[t][k] = sum_j B2[j][k] * P[t][j][k]: one CTA per slice t, 256 threads = 8 j-lanes x 32 k
-// (RS/32 column passes), fixed-order tree over the j-lanes.
-__global__ void __launch_bounds__(256) k_rhsC(const double* P, const double* B2, double* rhsC, int n2, int n3,
-                                               int RS, const int* stop) {
-    if (*stop) return;
-    __shared__ double red[8][33];
-    const int t = blockIdx.x;
-    const int kl = threadIdx.x & 31, jl = threadIdx.x >> 5;
-    for (int k0 = 0; k0 < RS; k0 += 32) {
-        const int k = k0 + kl;
-        double s = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        if (k < RS) {
-            int j = jl;
-            for (; j + 24 < n2; j += 32) {     // four independent chains
-                s = fma(B2[(size_t)j * RS + k], P[((size_t)t * n2 + j) * RS + k], s);
-                s1 = fma(B2[(size_t)(j + 8) * RS + k], P[((size_t)t * n2 + j + 8) * RS + k], s1);
-                s2 = fma(B2[(size_t)(j + 16) * RS + k], P[((size_t)t * n2 + j + 16) * RS + k], s2);
-                s3 = fma(B2[(size_t)(j + 24) * RS + k], P[((size_t)t * n2 + j + 24) * RS + k], s3);
-            }
-            for (; j < n2; j += 8) s = fma(B2[(size_t)j * RS + k], P[((size_t)t * n2 + j) * RS + k], s);
-            s = (s + s1) + (s2 + s3);
-        }
-        red[jl][kl] = s;
-        __syncthreads();
-        if (jl == 0 && k < RS) {
-            double v = ((red[0][kl] + red[1][kl]) + (red[2][kl] + red[3][kl])) +
-                       ((red[4][kl] + red[5][kl]) + (red[6][kl] + red[7][kl]));
-            rhsC[(size_t)t * RS + k] = v;
-        }
-        __syncthreads();
     }
 }
 

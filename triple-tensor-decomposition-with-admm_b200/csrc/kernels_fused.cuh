@@ -14,8 +14,12 @@ struct IterState {
     double rmuL, rmuO, thr, musum, rmuL_next;   // (1/muL), (1/muO), lambda/muO, muL+muO, 1/muL of the next iteration
     int k;         // iterations completed
     int stop;      // stopping rule fired or maxIter reached: all later launches are no-ops
-    int status;    // != 0: numerical failure (non-positive Cholesky pivot), see tritd.h
+    int status;    // != 0: numerical failure (NaN / Inf in a ridge system), see tritd.h
     int maxIter;
+    int pinv_fallbacks;   // ridge solves that went through the truncating pseudo-inverse (pinv_jacobi) ...
+    int pinv_truncated;   // ... and the number of singular values they zeroed, like MATLAB's pinv
+    int masked;           // completion variant: NaN in D marks an unobserved entry
+    int pad_;
 };
 
 __host__ __device__ inline void iter_state_derive(IterState& s) {
@@ -153,10 +157,14 @@ __global__ void __launch_bounds__(256) k_sum_pairs(const double* part, int n, do
 }
 
 // Per-CTA partial of sum(x^2) over a padded N-array (pad entries are zero).
-__global__ void __launch_bounds__(256) k_sumsq_part(const double* x, size_t n, double* part) {
+// (masked: NaN marks an unobserved entry, which does not count -- the norm of the observed data)
+__global__ void __launch_bounds__(256) k_sumsq_part(const double* x, size_t n, double* part, int masked) {
     __shared__ double red[64];
     double s = 0.0, z = 0.0;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) s = fma(x[i], x[i], s);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const double v = x[i];
+        if (!(masked && v != v)) s = fma(v, v, s);
+    }
     block_sum2(s, z, red);
     if (threadIdx.x == 0) { part[2 * blockIdx.x] = s; part[2 * blockIdx.x + 1] = 0.0; }
 }
@@ -218,8 +226,29 @@ __global__ void __launch_bounds__(256) k_recover_O(const double* __restrict__ D,
                                                    const double* __restrict__ YL, const IterState* st,
                                                    double* __restrict__ O, size_t n) {
     const double rmu = st->rmuL;
-    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
-        O[i] = __dsub_rn(D[i], __dsub_rn(T[i], __dmul_rn(rmu, YL[i])));
+    const bool masked = st->masked != 0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const double d = D[i];
+        O[i] = (masked && d != d) ? 0.0 : __dsub_rn(d, __dsub_rn(T[i], __dmul_rn(rmu, YL[i])));
+    }
+}
+
+// Completion variant: D(i) <- NaN where mask(i) == 0 (dense n1 x ncols byte mask, non-zero = observed), padded D.
+__global__ void __launch_bounds__(256) k_apply_mask(double* D, const unsigned char* mask, int n1, int ld1, size_t ncols) {
+    const double nan_ = __longlong_as_double(0x7ff8000000000000LL);
+    const size_t total = (size_t)n1 * ncols;
+    for (size_t e = (size_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (size_t)gridDim.x * 256) {
+        const size_t col = e / n1;
+        const int i = (int)(e - col * n1);
+        if (!mask[e]) D[col * ld1 + i] = nan_;
+    }
+}
+// first target of the completion variant: T = D on the observed entries, 0 on the unobserved ones
+__global__ void __launch_bounds__(256) k_fill_unobserved(const double* __restrict__ D, double* __restrict__ T, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const double d = D[i];
+        T[i] = d != d ? 0.0 : d;
+    }
 }
 
 __global__ void k_set_normD(IterState* st, const double* sumsq) {

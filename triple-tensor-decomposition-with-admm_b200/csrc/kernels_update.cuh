@@ -23,7 +23,7 @@
 
 namespace tritd {
 
-constexpr int kStatusCholesky = 1;
+constexpr int kStatusNumeric = 1;     // a ridge system contained NaN / Inf (MATLAB's pinv raises an error there too)
 
 // The RHS source is a strided sum: row `row` of the RHS is  sum_{m < count} w[m*wstride + k] * v[row_base + m*stride + k]
 // with row_base = (row / tile_h) * tile_stride + (row % tile_h) * row_stride, so ONE kernel body (one set of
@@ -109,14 +109,19 @@ __device__ __forceinline__ double rcp_newton(double x) {
 // In-place Gauss-Jordan inverse of G = S1 o S2 + alpha*I by one CTA of 256 threads, matrix in registers:
 // thread (ty,tx) of a 16 x 16 grid owns entries (ty + 16p, tx + 16q), p,q < PQ.  Per step only the pivot row and
 // column pass through shared memory (double-buffered, published by their owners as they are produced): one
-// barrier, 2*PQ+1 shared loads, one reciprocal, PQ*PQ FMAs.  Returns true when a pivot was bad.
+// barrier, 2*PQ+1 shared loads, one reciprocal, PQ*PQ FMAs.  Returns 0 when the inverse can be trusted to agree with
+// the reference's pinv, 1 when a pivot is non-positive / non-finite or min pivot / max pivot < 16 R eps (pinv's cutoff
+// max(size) * eps(sigma_max) may truncate: the caller runs pinv_jacobi instead), 2 in the threads whose entries of the
+// system itself are NaN / Inf (the caller votes).
+constexpr int kRidgeOk = 0, kRidgeIll = 1, kRidgeNonFinite = 2;
 template <int PQ>
-__device__ bool invert_ridge_system(const double* S1, const double* S2, int ns2, long s2stride, double alpha, int R, int RS, double* out,
+__device__ int invert_ridge_system(const double* S1, const double* S2, int ns2, long s2stride, double alpha, int R, int RS, double* out,
                                     double* sm /* >= 256 doubles */, long long* dbg = nullptr) {
     double* prow = sm;        // [2][64]
     double* pcol = sm + 128;  // [2][64]
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     double gq[PQ][PQ];
+    bool input_nonfinite = false;         // NaN / Inf in THIS thread's entries of the system (the caller votes over the CTA)
     {
         // all loads first (2*PQ*PQ in flight per thread), then the Hadamard product and the ridge
         double t1[PQ][PQ], t2[PQ][PQ];
@@ -151,6 +156,7 @@ __device__ bool invert_ridge_system(const double* S1, const double* S2, int ns2,
                 const int i = ty + 16 * p, j = tx + 16 * q;
                 double v = t1[p][q] * t2[p][q];
                 if (i == j && i < R) v += alpha;
+                input_nonfinite = input_nonfinite || !isfinite(v);
                 if (i == 0) prow[j] = v;
                 if (j == 0) pcol[i] = v;
                 gq[p][q] = v;
@@ -159,6 +165,7 @@ __device__ bool invert_ridge_system(const double* S1, const double* S2, int ns2,
     __syncthreads();
     if (dbg && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[13] = t_; }
     bool bad = false;
+    double pmin = 1.7976931348623157e308, pmax = 0.0;
     // Steps k = 16*KP + kl with the 16-block KP of the pivot a compile-time constant (unrolled), so the pivot row and
     // column are fixed registers: one generic FMA per entry, then per-step fix-ups of row k / column k.
 #pragma unroll
@@ -172,7 +179,8 @@ __device__ bool invert_ridge_system(const double* S1, const double* S2, int ns2,
             double* prn = prow + ((k + 1) & 1) * 64;
             double* pcn = pcol + ((k + 1) & 1) * 64;
             const double piv = pr[k];
-            bad = bad || !(piv > 0.0) || !isfinite(piv);
+            bad = bad || !(piv > 0.0) || !isfinite(piv);      // (a zero pivot makes the later ones Inf / NaN: still "ill", not an input error)
+            pmin = fmin(pmin, piv); pmax = fmax(pmax, piv);
             const double inv = rcp_newton(piv);
             double prj[PQ], pci[PQ];     // entries outside R x R see zeros here and stay zero
 #pragma unroll
@@ -224,7 +232,110 @@ __device__ bool invert_ridge_system(const double* S1, const double* S2, int ns2,
             const int i = ty + 16 * p, j = tx + 16 * q;
             if (i < R && j < R) out[i * RS + j] = gq[p][q];
         }
-    return bad;
+    if (input_nonfinite) return kRidgeNonFinite;
+    return (bad || pmin < pmax * (16.0 * 2.220446049250313e-16) * R) ? kRidgeIll : kRidgeOk;
+}
+
+// pinv(G) of the symmetric ridge system G = S1 o S2 + alpha*I exactly as the reference forms it (:78/:86/:93):
+// MATLAB's pinv is SVD based and zeroes the singular values <= max(size(G)) * eps(norm(G)).  For a symmetric
+// matrix the singular values are |eigenvalues|, so: cyclic Jacobi eigen-decomposition G = V diag(lam) V' (parallel
+// round-robin ordering, R/2 disjoint rotations per round, matrix and eigenvectors in shared memory), then
+// pinv = V diag(1/lam_k if |lam_k| > R * eps(max|lam|) else 0) V'.  Only block 0 runs this, and only when
+// invert_ridge_system reported kRidgeIll (rank-deficient or nearly so: duplicated factor columns, lambda2 = 0, the
+// 1e-9 ridge of update_C against sigma_max > ~1e5): a rare path, ~1 ms.  Returns the number of truncated values.
+__device__ int pinv_jacobi(const double* S1, const double* S2, int ns2, long s2stride, double alpha, int R, int RS, double* out,
+                           double* sm /* >= 2*R*(R+1) + 3*64 doubles */) {
+    const int tid = threadIdx.x, P = R + 1;
+    double* G = sm;                       // [R][P]
+    double* V = sm + R * P;               // [R][P]
+    double* cs = V + R * P;               // [32 pairs][2] rotations of the round, then [64] weights
+    __shared__ int s_rot, s_trunc;
+    for (int e = tid; e < R * R; e += blockDim.x) {
+        const int i = e / R, j = e - i * R;
+        double t2 = S2[i * RS + j];
+        for (int u = 1; u < ns2; ++u) t2 += S2[u * s2stride + i * RS + j];
+        double v = S1[i * RS + j] * t2;
+        if (i == j) v += alpha;
+        G[i * P + j] = v;
+        V[i * P + j] = i == j ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int n = (R + 1) & ~1, half = n >> 1;       // players of the round-robin tournament (a dummy one when R is odd)
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        if (tid == 0) s_rot = 0;
+        __syncthreads();
+        for (int rd = 0; rd < n - 1; ++rd) {
+            // pair q of round rd: (n-1, rd) for q = 0, else ((rd+q) mod (n-1), (rd-q) mod (n-1))
+            if (tid < half) {
+                int p_ = tid == 0 ? n - 1 : (rd + tid) % (n - 1), q_ = tid == 0 ? rd : (rd - tid + (n - 1)) % (n - 1);
+                if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
+                double c = 1.0, sn = 0.0;
+                if (q_ < R) {
+                    const double gpp = G[p_ * P + p_], gqq = G[q_ * P + q_], gpq = G[p_ * P + q_];
+                    if (gpq != 0.0 && fabs(gpq) > 1e-18 * sqrt(fabs(gpp) * fabs(gqq))) {
+                        const double tau = (gqq - gpp) / (2.0 * gpq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        sn = t * c;
+                        atomicAdd(&s_rot, 1);
+                    }
+                }
+                cs[2 * tid] = c; cs[2 * tid + 1] = sn;
+            }
+            __syncthreads();
+            // columns p,q of G and V for every row: (x_p, x_q) <- (c x_p - s x_q, s x_p + c x_q)
+            for (int e = tid; e < R * half; e += blockDim.x) {
+                const int i = e / half, pr = e - i * half;
+                int p_ = pr == 0 ? n - 1 : (rd + pr) % (n - 1), q_ = pr == 0 ? rd : (rd - pr + (n - 1)) % (n - 1);
+                if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
+                const double c = cs[2 * pr], sn = cs[2 * pr + 1];
+                if (q_ < R && sn != 0.0) {
+                    const double gp = G[i * P + p_], gq = G[i * P + q_];
+                    G[i * P + p_] = c * gp - sn * gq; G[i * P + q_] = sn * gp + c * gq;
+                    const double vp = V[i * P + p_], vq = V[i * P + q_];
+                    V[i * P + p_] = c * vp - sn * vq; V[i * P + q_] = sn * vp + c * vq;
+                }
+            }
+            __syncthreads();
+            // rows p,q of G for every column
+            for (int e = tid; e < R * half; e += blockDim.x) {
+                const int j = e / half, pr = e - j * half;
+                int p_ = pr == 0 ? n - 1 : (rd + pr) % (n - 1), q_ = pr == 0 ? rd : (rd - pr + (n - 1)) % (n - 1);
+                if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
+                const double c = cs[2 * pr], sn = cs[2 * pr + 1];
+                if (q_ < R && sn != 0.0) {
+                    const double gp = G[p_ * P + j], gq = G[q_ * P + j];
+                    G[p_ * P + j] = c * gp - sn * gq; G[q_ * P + j] = sn * gp + c * gq;
+                }
+            }
+            __syncthreads();
+        }
+        if (s_rot == 0) break;            // (uniform: read after the barrier that ended the last round)
+        __syncthreads();
+    }
+    // weights 1/lam_k above MATLAB's cutoff max(size(G)) * eps(norm(G)), eps(x) = 2^(floor(log2 x) - 52)
+    if (tid == 0) {
+        double lmax = 0.0;
+        for (int k = 0; k < R; ++k) lmax = fmax(lmax, fabs(G[k * P + k]));
+        const double tol = lmax > 0.0 ? (double)R * ldexp(1.0, ilogb(lmax) - 52) : 0.0;
+        int nt = 0;
+        for (int k = 0; k < R; ++k) {
+            const double l = G[k * P + k];
+            const bool keep = fabs(l) > tol;
+            cs[k] = keep ? 1.0 / l : 0.0;
+            nt += keep ? 0 : 1;
+        }
+        s_trunc = nt;
+    }
+    __syncthreads();
+    for (int e = tid; e < R * R; e += blockDim.x) {
+        const int i = e / R, j = e - i * R;
+        double acc = 0.0;
+        for (int k = 0; k < R; ++k) acc = fma(V[i * P + k] * cs[k], V[j * P + k], acc);
+        out[i * RS + j] = acc;
+    }
+    __syncthreads();
+    return s_trunc;
 }
 
 // S[a][b] = sum_i X[i][a] * X[i][b] over rows [0,n) of a row-major n x RS factor; S is RS x RS.
@@ -266,7 +377,9 @@ __device__ __forceinline__ void xchg_publish_and_wait(double* const* peers, long
 constexpr int kUpdMaxGramCtas = 64;   // CTAs that may spin in the Gram phase (<< 148 SMs x resident CTAs)
 __host__ __device__ inline size_t upd_smem_bytes(int RS) {
     const int ms = RS * RS > 64 * RS ? RS * RS : 64 * RS;      // inv(G) tile / Gram row chunk [64][RS]
-    return (size_t)(3 * 8 * 64 + ms) * sizeof(double);
+    const int jac = 2 * RS * (RS + 1) + 3 * 64;                // pinv_jacobi: G, V and the rotations (block 0 only)
+    const int tot = 3 * 8 * 64 + ms;
+    return (size_t)(tot > jac ? tot : jac) * sizeof(double);
 }
 
 template <int PQ>   // ceil(R / 16): the register patch of the inversion; also fixes the columns per lane (1 for RS <= 32, else 2)
@@ -303,8 +416,16 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
             xchg_publish_and_wait(a.peers, a.pflag_off, a.fstride, a.rank, a.nranks, a.xflags, epoch);
         }
         // ---------------- the ridge system, inverted while the row CTAs reduce ----------------
-        const bool bad = invert_ridge_system<PQ>(a.S1, a.S2, a.ns2, a.s2stride, a.alpha, R, RS, a.Minv, red, a.dbg);
-        if (bad && tid == 0) atomicExch(&a.st->status, kStatusCholesky);
+        const int cond = invert_ridge_system<PQ>(a.S1, a.S2, a.ns2, a.s2stride, a.alpha, R, RS, a.Minv, red, a.dbg);
+        // (every thread saw the same pivots, so `cond` is uniform; the votes are belt and braces)
+        const int nonfinite = __syncthreads_or(cond == kRidgeNonFinite), ill = __syncthreads_or(cond == kRidgeIll);
+        if (nonfinite) {
+            if (tid == 0) atomicExch(&a.st->status, kStatusNumeric);
+        } else if (ill) {
+            // the reference's pinv would (or might) truncate: do exactly what it does
+            const int nt = pinv_jacobi(a.S1, a.S2, a.ns2, a.s2stride, a.alpha, R, RS, a.Minv, sm);
+            if (tid == 0) { a.st->pinv_fallbacks += 1; a.st->pinv_truncated += nt; }
+        }
         __syncthreads();
         if (tid == 0) st_release_u32(&a.flags[0], 1u);
         TRITD_STAMP(0, 1)

@@ -40,6 +40,21 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+// progress lines ("Iter %d, errL=%.2e, errO=%.2e", :60-62) go through a replaceable sink so that a MEX gateway can
+// route them to mexPrintf (the MATLAB desktop does not show the process's stdout)
+static void default_print(const char* line, void*) { fputs(line, stdout); fflush(stdout); }
+static tritd_print_fn g_print = default_print;
+static void* g_print_user = nullptr;
+extern "C" void tritd_set_print(tritd_print_fn fn, void* user) { g_print = fn ? fn : default_print; g_print_user = fn ? user : nullptr; }
+static void emit(const char* fmt, ...) {
+    char buf[256];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_print(buf, g_print_user);
+}
+
 #define CU_TRY(expr)                                                                                  \
     do {                                                                                              \
         cudaError_t _e = (expr);                                                                      \
@@ -113,6 +128,7 @@ struct tritd_ctx {
     int64_t launches = 0;
     PFN_encodeTiled encode = nullptr;
     tritd_problem* cached = nullptr;     // device state of the last tritd_admm_f64 call, reused when the shape repeats
+    bool cache_poisoned = false;         // the last call failed half-way: the cached state must not be reused
     unsigned xepoch = 0;                 // peer exchange: first unused epoch (advances identically on every rank)
 };
 
@@ -193,6 +209,7 @@ extern "C" int tritd_create_rank(int device, int rank, int nranks, const void* n
 }
 
 extern "C" void tritd_problem_destroy(tritd_problem* p);
+extern "C" int tritd_problem_get_E(tritd_problem* p, double* E_host);
 
 extern "C" int tritd_trim(tritd_ctx* c) {
     if (!c) return fail(TRITD_ERR_INVALID, "ctx is NULL");
@@ -264,10 +281,14 @@ struct tritd_problem {
     IterState* st = nullptr;
     double *errHist = nullptr, *errL = nullptr, *errO = nullptr;
     IterState* st_host = nullptr;        // pinned mirror
+    IterState* poll = nullptr;           // pinned [2]: asynchronous copies of the iteration scalars (tritd_problem_iterate)
+    cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     CUtensorMap mapT, mapA1T;
     alignas(64) AdmmMaps maps;           // [8 j][16 i] boxes of D, Y_L, E, Y_O, T, O for k_admm
     double* partF = nullptr;             // [gridA][128][RS] fused mode-1 partials (next iteration's X1*F')
-    int *tileF = nullptr, *ctaTab = nullptr;   // i-tile of each k_admm CTA; (tile, index in tile, CTAs of tile)
+    int* ctaTab = nullptr;               // per k_admm CTA: (i-tile, index among the tile's CTAs, CTAs of that tile)
+    int refill_mode = 0;                 // k_admm producer scheme (AdmmArgs::refill_mode)
+    int jgp = 2;                         // k_admm: column groups per stage asked for (AdmmCfg::JGP)
     int gridA = 0, tileH = 128, nitA = 1;  // k_admm: rows per i-tile (16 x consumer warps used) and number of i-tiles
     bool rhsA_ready = false;             // partF holds X1*F' of the current T
     int n_it = 0, n_jc = 0, gridM = 0, gridP = 0, gridF = 0, gi = 0;
@@ -275,6 +296,8 @@ struct tritd_problem {
     size_t smemM = 0, smemP = 0;
     tritd_opts opts{};
     bool has_D = false, initialized = false;
+    bool masked = false;                 // completion variant: unobserved entries of D hold NaN (tritd_problem_set_mask_*)
+    int level = 0;                       // what is allocated: kLevelSolver / kLevelContract / kLevelFactors
     int printed_k = 0;
     int hist_cap = 0;
     bool profiling = false;
@@ -284,6 +307,12 @@ struct tritd_problem {
     bool graph_off = false;              // capture failed or TRITD_NO_GRAPH set: plain launches
     std::vector<void*> allocs;
 };
+
+// What a tritd_problem holds.  The solver needs everything; the standalone helpers only what they touch, so that
+// e.g. triple_product(A,B,C) after a solve costs one N-sized buffer, not six plus the exchange set-up.
+enum { kLevelSolver = 0,      // 6 N-arrays, tensor maps of k_admm, partials, (N>1) the peer exchange
+       kLevelContract = 1,    // T + its tensor map, A1T, P, the MTTKRP partials: tritd_mttkrp_f64
+       kLevelFactors = 2 };   // factors and the small state only: triple_product / evaluate (they allocate their N-arrays)
 
 template <typename Tp>
 static int dalloc(tritd_problem* p, Tp** ptr, size_t count) {
@@ -384,8 +413,11 @@ static int launch_admm(tritd_problem* p) {
     a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase;
     a.cta_tab = p->ctaTab;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc; a.tile_h = p->tileH;
-#define CALL(NT_, KS_) \
-    k_admm<KS_, NT_, false><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, false>::kSmem, c->stream>>>(p->maps, a);
+    a.refill_mode = p->refill_mode;
+#define CALL(NT_, KS_)                                                                                                       \
+    if (p->masked) k_admm<KS_, NT_, true, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream>>>(p->maps, a);  \
+    else if (p->jgp == 1) k_admm<KS_, NT_, false, 1><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream>>>(p->maps, a); \
+    else k_admm<KS_, NT_, false, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream>>>(p->maps, a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
     CU_TRY(cudaGetLastError());
@@ -551,10 +583,16 @@ extern "C" void tritd_problem_destroy(tritd_problem* p) {
     for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
     if (p->graph) cudaGraphExecDestroy(p->graph);
     if (p->st_host) cudaFreeHost(p->st_host);
+    if (p->poll) { cudaFreeHost(p->poll); cudaEventDestroy(p->poll_ev[0]); cudaEventDestroy(p->poll_ev[1]); }
     delete p;
 }
 
+static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int r, int level, tritd_problem** out);
 extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int r, tritd_problem** out) {
+    return problem_create(c, n1, n2, n3, r, kLevelSolver, out);
+}
+
+static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int r, int level, tritd_problem** out) {
     if (!c || !out) return fail(TRITD_ERR_INVALID, "ctx/out is NULL");
     *out = nullptr;
     if (n1 < 1 || n2 < 1 || n3 < 1) return fail(TRITD_ERR_INVALID, "tensor size %lld x %lld x %lld", (long long)n1, (long long)n2, (long long)n3);
@@ -564,6 +602,8 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     CU_TRY(cudaSetDevice(c->device));
     tritd_problem* p = new tritd_problem();
     p->ctx = c;
+    p->level = level;
+    const bool solver = level == kLevelSolver, contract = level <= kLevelContract;
     p->n1 = (int)n1; p->n2 = (int)n2; p->n3 = (int)n3; p->r = r; p->R = r * r;
     p->RS = (p->R + 7) / 8 * 8;
     const RankCfg rc = rank_cfg(r);
@@ -573,18 +613,21 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     p->Np = (size_t)p->ld1 * p->n2 * p->n3;
     p->n_it = (p->n1 + 127) / 128;
     p->n_jc = (p->n2 + kBoxRows - 1) / kBoxRows;
+    if (const char* e = getenv("TRITD_ADMM_JG")) p->jgp = atoi(e) == 1 ? 1 : 2;
+    if (const char* e = getenv("TRITD_ADMM_REFILL")) p->refill_mode = atoi(e);
 
     int s = TRITD_OK;
     auto bail = [&](int code) { tritd_problem_destroy(p); return code; };
 #define PALLOC(ptr, count) if ((s = dalloc(p, &p->ptr, (count))) != TRITD_OK) return bail(s)
-    PALLOC(D, p->Np); PALLOC(E, p->Np); PALLOC(YL, p->Np); PALLOC(YO, p->Np); PALLOC(T, p->Np); PALLOC(O, p->Np);
+    if (solver) { PALLOC(D, p->Np); PALLOC(E, p->Np); PALLOC(YL, p->Np); PALLOC(YO, p->Np); PALLOC(O, p->Np); }
+    if (contract) PALLOC(T, p->Np);
     PALLOC(A1, (size_t)p->n1 * p->RS); PALLOC(B2, (size_t)p->n2 * p->RS); PALLOC(C3, (size_t)p->n3 * p->RS);
     PALLOC(A1T, (size_t)p->RS * p->ldt);
     PALLOC(SA, (size_t)p->RS * p->RS); PALLOC(SB, (size_t)p->RS * p->RS);
     PALLOC(gpart, (size_t)3 * kGramSlices * p->RS * p->RS);
     PALLOC(bufA, (size_t)p->n1 * p->RS + (size_t)p->RS * p->RS);
     PALLOC(rhsB, (size_t)p->n2 * p->RS); PALLOC(rhsC, (size_t)p->n3 * p->RS);
-    PALLOC(P, (size_t)p->n3 * p->n2 * p->RS);
+    if (contract) PALLOC(P, (size_t)p->n3 * p->n2 * p->RS);
 
     // grids: one contraction CTA per SM (its pipeline fills shared memory); the fused kernel by occupancy
     p->unitsM = (long)p->n_it * p->n_jc * p->n3;
@@ -604,25 +647,25 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     p->gi = std::max(1, c->num_sms * occ / p->n_it);
     p->gridF = p->gi * p->n_it;
 
-    PALLOC(partM, (size_t)p->gridM * 2 * 128 * p->RS);
+    if (contract) PALLOC(partM, (size_t)p->gridM * 2 * 128 * p->RS);
     {
-        const int nmax = std::max(p->n1, std::max(p->n2, p->n3));
-        (void)nmax;
         PALLOC(Minv, (size_t)3 * p->RS * p->RS);
         PALLOC(flags, 16 + 3 * 64);
         PALLOC(ones, 64);
         { double h1[64]; for (double& x : h1) x = 1.0; cudaMemcpy(p->ones, h1, sizeof(h1), cudaMemcpyHostToDevice); }
         if (getenv("TRITD_DEBUG_STAMPS")) { PALLOC(dbg, 48); cudaMemset(p->dbg, 0, 48 * 8); }
-        PALLOC(tile0, p->gridM); PALLOC(tile1, p->gridM);
-        std::vector<int> t0(p->gridM), t1(p->gridM);
-        const long per_it = (long)p->n_jc * p->n3;
-        for (int q = 0; q < p->gridM; ++q) {
-            const long u0 = p->unitsM * q / p->gridM, u1 = p->unitsM * (q + 1) / p->gridM;
-            t0[q] = (int)(u0 / per_it);
-            t1[q] = u1 > u0 ? (int)((u1 - 1) / per_it) : t0[q] - 1;
+        if (contract) {
+            PALLOC(tile0, p->gridM); PALLOC(tile1, p->gridM);
+            std::vector<int> t0(p->gridM), t1(p->gridM);
+            const long per_it = (long)p->n_jc * p->n3;
+            for (int q = 0; q < p->gridM; ++q) {
+                const long u0 = p->unitsM * q / p->gridM, u1 = p->unitsM * (q + 1) / p->gridM;
+                t0[q] = (int)(u0 / per_it);
+                t1[q] = u1 > u0 ? (int)((u1 - 1) / per_it) : t0[q] - 1;
+            }
+            cudaMemcpy(p->tile0, t0.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
+            cudaMemcpy(p->tile1, t1.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
         }
-        cudaMemcpy(p->tile0, t0.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
-        cudaMemcpy(p->tile1, t1.data(), sizeof(int) * p->gridM, cudaMemcpyHostToDevice);
         cudaMemset(p->flags, 0, (16 + 3 * 64) * 4);
         // k_admm: one CTA per SM.  The i-tiles are as even as 16-row warp strips allow (240 rows -> 128 + 112,
         // 130 rows -> 80 + 50) and every tile gets the same number of CTAs: a stage costs the same whether
@@ -632,21 +675,19 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         p->tileH = 16 * ((nwr + p->nitA - 1) / p->nitA);
         p->gridA = std::max(c->num_sms / p->nitA, 1) * p->nitA;
         std::vector<int> per(p->nitA, p->gridA / p->nitA);
-        PALLOC(partF, (size_t)p->gridA * 128 * p->RS);
-        PALLOC(tileF, p->gridA);
-        PALLOC(ctaTab, 3 * p->gridA);
-        std::vector<int> tf(p->gridA), tab(3 * p->gridA);
-        {
+        if (solver) {
+            PALLOC(partF, (size_t)p->gridA * 128 * p->RS);
+            PALLOC(ctaTab, 3 * p->gridA);
+            std::vector<int> tab(3 * p->gridA);
             // interleave the tiles so neighbouring CTAs (launched together) work on the same columns
             std::vector<int> used(p->nitA, 0);
             int q = 0;
             for (int cta = 0; cta < p->gridA;) {
-                if (used[q] < per[q]) { tf[cta] = q; tab[3 * cta] = q; tab[3 * cta + 1] = used[q]++; tab[3 * cta + 2] = per[q]; ++cta; }
+                if (used[q] < per[q]) { tab[3 * cta] = q; tab[3 * cta + 1] = used[q]++; tab[3 * cta + 2] = per[q]; ++cta; }
                 q = (q + 1) % p->nitA;
             }
+            cudaMemcpy(p->ctaTab, tab.data(), sizeof(int) * 3 * p->gridA, cudaMemcpyHostToDevice);
         }
-        cudaMemcpy(p->tileF, tf.data(), sizeof(int) * p->gridA, cudaMemcpyHostToDevice);
-        cudaMemcpy(p->ctaTab, tab.data(), sizeof(int) * 3 * p->gridA, cudaMemcpyHostToDevice);
     }
     PALLOC(norm_part, (size_t)2 * std::max(std::max(p->gridF, c->num_sms), 1024));
     PALLOC(norms, 8);
@@ -660,10 +701,19 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
 #define CALL(NT_, KS_)                                                                                            \
     CU_TRY(cudaFuncSetAttribute(k_mttkrp1<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemM));    \
     CU_TRY(cudaFuncSetAttribute(k_ppass<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemP));      \
-    CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                (int)AdmmCfg<KS_, NT_, false>::kSmem));
+    CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                (int)AdmmCfg<KS_, NT_, 2>::kSmem));                                               \
+    CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                (int)AdmmCfg<KS_, NT_, 1>::kSmem));                                               \
+    CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                (int)AdmmCfg<KS_, NT_, 2>::kSmem));
             TRITD_DISPATCH_R(r, CALL)
 #undef CALL
+            const int usm = (int)upd_smem_bytes(p->RS);
+            CU_TRY(cudaFuncSetAttribute(k_upd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, usm));
+            CU_TRY(cudaFuncSetAttribute(k_upd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, usm));
+            CU_TRY(cudaFuncSetAttribute(k_upd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, usm));
+            CU_TRY(cudaFuncSetAttribute(k_upd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, usm));
             return TRITD_OK;
         };
         if ((s = q()) != TRITD_OK) return bail(s);
@@ -672,7 +722,7 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
     // zero everything once: pad rows / pad columns must be exact zeros forever
     cudaStream_t st = c->stream;
     for (double* q : {p->D, p->E, p->YL, p->YO, p->T, p->O})
-        if (cudaMemsetAsync(q, 0, p->Np * sizeof(double), st) != cudaSuccess) return bail(fail(TRITD_ERR_CUDA, "memset failed"));
+        if (q && cudaMemsetAsync(q, 0, p->Np * sizeof(double), st) != cudaSuccess) return bail(fail(TRITD_ERR_CUDA, "memset failed"));
     cudaMemsetAsync(p->A1T, 0, (size_t)p->RS * p->ldt * sizeof(double), st);
     cudaMemsetAsync(p->st, 0, sizeof(IterState), st);
 
@@ -681,14 +731,14 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         cuuint64_t dims[3] = {(cuuint64_t)p->n1, (cuuint64_t)p->n2, (cuuint64_t)p->n3};
         cuuint64_t str[2] = {(cuuint64_t)p->ld1 * 8, (cuuint64_t)p->ld1 * p->n2 * 8};
         cuuint32_t box[3] = {16, (cuuint32_t)kBoxRows, 1};
-        if ((s = make_map(c, &p->mapT, p->T, 3, dims, str, box)) != TRITD_OK) return bail(s);
+        if (contract && (s = make_map(c, &p->mapT, p->T, 3, dims, str, box)) != TRITD_OK) return bail(s);
         // k_admm views each N-array as (i_lo = 16, j, i_hi = ld1/16, t): one box = [8 i_hi][8 j][16 i_lo]
         cuuint64_t dims4[4] = {16, (cuuint64_t)p->n2, (cuuint64_t)(p->ld1 / 16), (cuuint64_t)p->n3};
         cuuint64_t str4[3] = {(cuuint64_t)p->ld1 * 8, 128, (cuuint64_t)p->ld1 * p->n2 * 8};
         int jgroups = 1;
         {
             auto q = [&]() -> int {
-#define CALL(NT_, KS_) jgroups = AdmmCfg<KS_, NT_, false>::JG;
+#define CALL(NT_, KS_) jgroups = p->jgp == 1 ? AdmmCfg<KS_, NT_, 1>::JG : AdmmCfg<KS_, NT_, 2>::JG;
                 TRITD_DISPATCH_R(r, CALL)
 #undef CALL
                 return TRITD_OK;
@@ -699,14 +749,14 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
         struct { CUtensorMap* m; double* base; } mm[6] = {{&p->maps.D, p->D}, {&p->maps.YL, p->YL}, {&p->maps.E, p->E},
                                                          {&p->maps.YO, p->YO}, {&p->maps.T, p->T}, {&p->maps.O, p->O}};
         for (auto& q : mm)
-            if ((s = make_map(c, q.m, q.base, 4, dims4, str4, box4)) != TRITD_OK) return bail(s);
+            if (solver && (s = make_map(c, q.m, q.base, 4, dims4, str4, box4)) != TRITD_OK) return bail(s);
         cuuint64_t dims2[2] = {(cuuint64_t)p->n1, (cuuint64_t)p->RS};
         cuuint64_t str2[1] = {(cuuint64_t)p->ldt * 8};
         cuuint32_t box2[2] = {16, (cuuint32_t)p->RS};
         if ((s = make_map(c, &p->mapA1T, p->A1T, 2, dims2, str2, box2)) != TRITD_OK) return bail(s);
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) return bail(fail(TRITD_ERR_CUDA, "sync failed"));
-    if ((s = setup_exchange(p)) != TRITD_OK) return bail(s);
+    if (solver && (s = setup_exchange(p)) != TRITD_OK) return bail(s);
     *out = p;
     return TRITD_OK;
 }
@@ -732,16 +782,42 @@ extern "C" int tritd_problem_set_D_host(tritd_problem* p, const double* D_host) 
     CU_TRY(cudaSetDevice(p->ctx->device));
     ST_TRY(copy_in(p, p->D, D_host));
     CU_TRY(cudaStreamSynchronize(p->ctx->stream));
-    p->has_D = true; p->initialized = false;
+    p->has_D = true; p->initialized = false; p->masked = false;
     return TRITD_OK;
 }
 extern "C" int tritd_problem_set_D_dev(tritd_problem* p, const double* D_dev) {
     if (!p || !D_dev) return fail(TRITD_ERR_INVALID, "NULL argument");
     CU_TRY(cudaSetDevice(p->ctx->device));
     ST_TRY(copy_in(p, p->D, D_dev));
-    p->has_D = true; p->initialized = false;
+    p->has_D = true; p->initialized = false; p->masked = false;
     return TRITD_OK;
 }
+
+// Completion variant (opt-in): mark the entries with mask == 0 as unobserved.  The mask is folded into
+// D itself (NaN), so the iteration moves not one byte more than the unmasked solver.
+static int apply_mask(tritd_problem* p, const unsigned char* mask, bool on_host) {
+    if (!p || !mask) return fail(TRITD_ERR_INVALID, "NULL argument");
+    if (!p->has_D) return fail(TRITD_ERR_INVALID, "tritd_problem_set_D_* must be called first");
+    tritd_ctx* c = p->ctx;
+    CU_TRY(cudaSetDevice(c->device));
+    const size_t ncols = (size_t)p->n2 * p->n3, nm = (size_t)p->n1 * ncols;
+    unsigned char* md = nullptr;
+    if (on_host) {
+        CU_TRY(cudaMalloc((void**)&md, nm));
+        if (cudaMemcpyAsync(md, mask, nm, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { cudaFree(md); return fail(TRITD_ERR_CUDA, "mask copy failed"); }
+    }
+    const unsigned grid = (unsigned)std::min<size_t>((nm + 255) / 256, (size_t)c->num_sms * 16);
+    k_apply_mask<<<grid, 256, 0, c->stream>>>(p->D, on_host ? md : mask, p->n1, p->ld1, ncols);
+    const cudaError_t e = cudaGetLastError();
+    c->launches += 1;
+    cudaStreamSynchronize(c->stream);
+    if (md) cudaFree(md);
+    if (e != cudaSuccess) return fail(TRITD_ERR_CUDA, "k_apply_mask: %s", cudaGetErrorString(e));
+    p->masked = true; p->initialized = false;
+    return TRITD_OK;
+}
+extern "C" int tritd_problem_set_mask_host(tritd_problem* p, const unsigned char* mask_host) { return apply_mask(p, mask_host, true); }
+extern "C" int tritd_problem_set_mask_dev(tritd_problem* p, const unsigned char* mask_dev) { return apply_mask(p, mask_dev, false); }
 
 // MATLAB 3-D factor shapes <-> row-major n x RS "unfolded" layout (reshape_*_from_*, :111-130, run backwards)
 static void pack_A(const double* A, int n1, int R, int RS, std::vector<double>& out) {
@@ -786,6 +862,7 @@ static int upload_factors(tritd_problem* p, const double* A0, const double* B0, 
 extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const double* A0, const double* B0,
                                   const double* C0) {
     if (!p || !o || !A0 || !B0 || !C0) return fail(TRITD_ERR_INVALID, "NULL argument");
+    if (p->level != kLevelSolver) return fail(TRITD_ERR_INVALID, "not a solver problem");
     if (!p->has_D) return fail(TRITD_ERR_INVALID, "tritd_problem_set_D_* must be called first");
     if (o->maxIter < 1) return fail(TRITD_ERR_INVALID, "opts.maxIter = %d", o->maxIter);
     if (!(o->mu > 0.0)) return fail(TRITD_ERR_INVALID, "opts.mu must be positive");
@@ -797,13 +874,19 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
 
     // O = E = Y_L = Y_O = 0 (:24-26); the first target T = D - O + (1/muL)*Y_L is D itself (:33)
     for (double* q : {p->E, p->YL, p->YO, p->O}) CU_TRY(cudaMemsetAsync(q, 0, p->Np * sizeof(double), st));
-    CU_TRY(cudaMemcpyAsync(p->T, p->D, p->Np * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (p->masked) {      // completion variant: the first target is the zero-filled data (the callers' own convention, traffic_triple_comparison.m:34-35)
+        k_fill_unobserved<<<(unsigned)std::min<size_t>((p->Np + 255) / 256, (size_t)c->num_sms * 16), 256, 0, st>>>(p->D, p->T, p->Np);
+        CU_TRY(cudaGetLastError());
+        c->launches += 1;
+    } else {
+        CU_TRY(cudaMemcpyAsync(p->T, p->D, p->Np * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
 
     IterState h;
     memset(&h, 0, sizeof(h));
     h.muL = o->mu; h.muO = o->mu; h.muL_max = o->mu * 1e6; h.muO_max = o->mu * 1e6;
     h.rhoL = o->rho; h.rhoO = o->rho; h.lambda = o->lambda_; h.tol = o->tol; h.normD = 0.0;
-    h.k = 0; h.stop = 0; h.status = 0; h.maxIter = o->maxIter;
+    h.k = 0; h.stop = 0; h.status = 0; h.maxIter = o->maxIter; h.masked = p->masked ? 1 : 0;
     iter_state_derive(h);
     *p->st_host = h;
     CU_TRY(cudaMemcpyAsync(p->st, p->st_host, sizeof(IterState), cudaMemcpyHostToDevice, st));
@@ -820,7 +903,7 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
     CU_TRY(cudaMemsetAsync(p->errHist, 0, (size_t)3 * p->hist_cap * 8, st));
 
     // normD = norm(D(:))  (:28), all-reduced over the slabs
-    k_sumsq_part<<<1024, 256, 0, st>>>(p->D, p->Np, p->norm_part);
+    k_sumsq_part<<<1024, 256, 0, st>>>(p->D, p->Np, p->norm_part, p->masked ? 1 : 0);
     k_sum_pairs<<<1, 256, 0, st>>>(p->norm_part, 1024, p->norms, nullptr);
     CU_TRY(cudaGetLastError());
     ST_TRY(allreduce_sum(c, p->norms, 2));
@@ -969,8 +1052,8 @@ extern "C" int tritd_problem_phase_ms(tritd_problem* p, double* ms_out, int32_t*
 static int fetch_state(tritd_problem* p) {
     CU_TRY(cudaMemcpyAsync(p->st_host, p->st, sizeof(IterState), cudaMemcpyDeviceToHost, p->ctx->stream));
     CU_TRY(cudaStreamSynchronize(p->ctx->stream));
-    if (p->st_host->status == kStatusCholesky)
-        return fail(TRITD_ERR_NUMERIC, "ridge system not positive definite at iteration %d (Cholesky pivot <= 0 or non-finite)",
+    if (p->st_host->status == kStatusNumeric)
+        return fail(TRITD_ERR_NUMERIC, "ridge system contains NaN / Inf at iteration %d (pinv: input must not contain NaN or Inf)",
                     p->st_host->k + 1);
     return TRITD_OK;
 }
@@ -995,26 +1078,51 @@ static int print_progress(tritd_problem* p) {
     std::vector<double> eL(k), eO(k);
     CU_TRY(cudaMemcpy(eL.data(), p->errL, (size_t)k * 8, cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(eO.data(), p->errO, (size_t)k * 8, cudaMemcpyDeviceToHost));
-    for (int q = p->printed_k / 10 * 10 + 10; q <= k; q += 10) printf("Iter %d, errL=%.2e, errO=%.2e\n", q, eL[q - 1], eO[q - 1]);
-    fflush(stdout);
+    for (int q = p->printed_k / 10 * 10 + 10; q <= k; q += 10) emit("Iter %d, errL=%.2e, errO=%.2e\n", q, eL[q - 1], eO[q - 1]);
     p->printed_k = k;
     return TRITD_OK;
 }
 
 extern "C" int tritd_problem_iterate(tritd_problem* p, int32_t max_more, int32_t* iters_total) {
     if (!p || !p->initialized) return fail(TRITD_ERR_INVALID, "problem not initialised");
-    CU_TRY(cudaSetDevice(p->ctx->device));
+    tritd_ctx* c = p->ctx;
+    CU_TRY(cudaSetDevice(c->device));
     ST_TRY(fetch_state(p));
     int remaining = std::min<int>(max_more, p->opts.maxIter - p->st_host->k);
-    // the stopping rule lives on the device; the host only looks at it every 10 iterations
-    // (the cadence of the reference's progress line), later launches of a stopped solve are no-ops
-    while (remaining > 0 && !p->st_host->stop) {
-        const int batch = std::min(remaining, 10 - p->st_host->k % 10);
-        for (int i = 0; i < batch; ++i) ST_TRY(run_iteration(p));
-        ST_TRY(fetch_state(p));
-        ST_TRY(print_progress(p));
-        remaining -= batch;
+    // The stopping rule lives on the device (later launches of a stopped solve are no-ops).  The host follows it
+    // WITHOUT stalling the GPU: after every batch of <= 10 iterations (the cadence of the reference's progress line)
+    // the iteration scalars are copied to a pinned slot, and the host looks at the slot of the batch BEFORE the one
+    // it has just enqueued -- the stream never runs dry, and with several ranks no rank waits for its host while
+    // its peers spin in an exchange.  At most one batch of no-op launches follows a stop.
+    if (!p->poll) {
+        CU_TRY(cudaMallocHost((void**)&p->poll, 2 * sizeof(IterState)));
+        CU_TRY(cudaEventCreateWithFlags(&p->poll_ev[0], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&p->poll_ev[1], cudaEventDisableTiming));
     }
+    bool pending[2] = {false, false};
+    int k_enq = p->st_host->k, slot = 0;
+    auto look = [&](int sl) -> int {
+        CU_TRY(cudaEventSynchronize(p->poll_ev[sl]));
+        pending[sl] = false;
+        *p->st_host = p->poll[sl];
+        if (p->st_host->status == kStatusNumeric)
+            return fail(TRITD_ERR_NUMERIC, "ridge system contains NaN / Inf at iteration %d (pinv: input must not contain NaN or Inf)",
+                        p->st_host->k + 1);
+        return print_progress(p);
+    };
+    while (remaining > 0 && !p->st_host->stop) {
+        const int batch = std::min(remaining, 10 - k_enq % 10);
+        for (int i = 0; i < batch; ++i) ST_TRY(run_iteration(p));
+        k_enq += batch; remaining -= batch;
+        CU_TRY(cudaMemcpyAsync(&p->poll[slot], p->st, sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaEventRecord(p->poll_ev[slot], c->stream));
+        pending[slot] = true;
+        if (pending[slot ^ 1]) ST_TRY(look(slot ^ 1));
+        slot ^= 1;
+    }
+    for (int q = 0; q < 2; ++q) { const int sl = (slot + q) & 1; if (pending[sl]) ST_TRY(look(sl)); }   // oldest first
+    ST_TRY(fetch_state(p));
+    ST_TRY(print_progress(p));
     if (iters_total) *iters_total = p->st_host->k;
     return TRITD_OK;
 }
@@ -1029,12 +1137,12 @@ static int recover_O(tritd_problem* p) {
     return TRITD_OK;
 }
 
+static int reconstruct_to(tritd_problem* p, double* dst, int ld);
 static int reconstruct_L(tritd_problem* p, double** Lbuf) {
     double* q = nullptr;
     cudaError_t e = cudaMalloc((void**)&q, p->Np * sizeof(double));
     if (e != cudaSuccess) return fail(TRITD_ERR_CUDA, "cudaMalloc(L): %s", cudaGetErrorString(e));
-    cudaMemsetAsync(q, 0, p->Np * sizeof(double), p->ctx->stream);
-    int s = launch_fused(p, 1, q);
+    int s = reconstruct_to(p, q, p->ld1);          // writes every entry of the padded array (pad rows: zeros)
     if (s != TRITD_OK) { cudaFree(q); return s; }
     *Lbuf = q;
     return TRITD_OK;
@@ -1085,6 +1193,30 @@ extern "C" int tritd_problem_get_L_dev(tritd_problem* p, double* L_dev) {
     return s;
 }
 
+// E of the last finished iteration (the reference's header documents "O,E : sparse components (clone E)", :12)
+extern "C" int tritd_problem_get_E(tritd_problem* p, double* E_host) {
+    if (!p || !E_host || !p->initialized) return fail(TRITD_ERR_INVALID, "NULL argument / not initialised");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    ST_TRY(copy_out(p, E_host, p->E));
+    CU_TRY(cudaStreamSynchronize(p->ctx->stream));
+    return TRITD_OK;
+}
+extern "C" int tritd_problem_get_E_dev(tritd_problem* p, double* E_dev) {
+    if (!p || !E_dev || !p->initialized) return fail(TRITD_ERR_INVALID, "NULL argument / not initialised");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    return copy_out(p, E_dev, p->E);
+}
+// How often the ridge solves of this solve took the truncating pseudo-inverse path and how many singular values
+// that zeroed in total (what MATLAB's pinv does silently at :78/:86/:93).
+extern "C" int tritd_problem_pinv_stats(tritd_problem* p, int32_t* fallbacks, int32_t* truncated) {
+    if (!p) return fail(TRITD_ERR_INVALID, "NULL problem");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    ST_TRY(fetch_state(p));
+    if (fallbacks) *fallbacks = p->st_host->pinv_fallbacks;
+    if (truncated) *truncated = p->st_host->pinv_truncated;
+    return TRITD_OK;
+}
+
 // ---------------------------------------------------------------------------
 // one-call solver
 // ---------------------------------------------------------------------------
@@ -1092,10 +1224,33 @@ static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-extern "C" int tritd_admm_f64(tritd_ctx* c, const double* D_host, int64_t n1, int64_t n2, int64_t n3, int r,
-                              const tritd_opts* o, const double* A0, const double* B0, const double* C0, double* A,
-                              double* B, double* C, double* O, double* L, double* errHist, int32_t* iters_out,
-                              tritd_timing* tm) {
+// Multi-rank: may the cached problem be reused?  The decision must be the same on every rank -- creating a problem
+// is collective (NCCL all-gather of the IPC handles), and a rank that frees its mailbox while a peer still has it
+// mapped would be written into after the free.  So the ranks agree (NCCL min) on "every rank has a usable cache hit".
+static int agree_on_cache_hit(tritd_ctx* c, bool local_hit, bool* all_hit) {
+    *all_hit = local_hit;
+    if (c->nranks == 1) return TRITD_OK;
+    double* flag = nullptr;
+    CU_TRY(cudaMalloc((void**)&flag, 8));
+    const double mine = local_hit ? 1.0 : 0.0;
+    double got = 0.0;
+    int s = TRITD_OK;
+    if (cudaMemcpyAsync(flag, &mine, 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) s = fail(TRITD_ERR_CUDA, "cache flag upload failed");
+    if (s == TRITD_OK) {
+        ncclResult_t r = g_nccl.AllReduce(flag, flag, 1, ncclDouble, ncclMin, c->comm, c->stream);
+        if (r != ncclSuccess) s = fail(TRITD_ERR_NCCL, "ncclAllReduce(cache flag): %s", g_nccl.GetErrorString(r));
+    }
+    if (s == TRITD_OK && (cudaMemcpyAsync(&got, flag, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                          cudaStreamSynchronize(c->stream) != cudaSuccess))
+        s = fail(TRITD_ERR_CUDA, "cache flag download failed");
+    cudaFree(flag);
+    *all_hit = got > 0.5;
+    return s;
+}
+
+static int admm_impl(tritd_ctx* c, const double* D_host, const unsigned char* mask_host, int64_t n1, int64_t n2, int64_t n3, int r,
+                     const tritd_opts* o, const double* A0, const double* B0, const double* C0, double* A, double* B, double* C,
+                     double* O, double* E, double* L, double* errHist, int32_t* iters_out, tritd_timing* tm) {
     if (!c || !D_host || !o || !A0 || !B0 || !C0 || !errHist) return fail(TRITD_ERR_INVALID, "NULL argument");
     const double t_begin = now_ms();
     const int64_t launches0 = c->launches;
@@ -1103,15 +1258,23 @@ extern "C" int tritd_admm_f64(tritd_ctx* c, const double* D_host, int64_t n1, in
     // reused when the next call has the same shape and rank -- a MATLAB session typically calls the solver
     // repeatedly on equally sized data; tritd_trim() / tritd_destroy() release it
     tritd_problem* p = c->cached;
-    if (p && !(p->n1 == n1 && p->n2 == n2 && p->n3 == n3 && p->r == r)) { tritd_trim(c); p = nullptr; }
+    const bool local_hit = p && !c->cache_poisoned && p->n1 == n1 && p->n2 == n2 && p->n3 == n3 && p->r == r;
+    bool hit = local_hit;
+    ST_TRY(agree_on_cache_hit(c, local_hit, &hit));
+    if (!hit) { tritd_trim(c); p = nullptr; }
     if (!p) {
         ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
         c->cached = p;
+        c->cache_poisoned = false;
     }
+    // a failure below leaves the cached state in place but poisoned: the next call re-creates it on EVERY rank
+    // (the decision above is collective), instead of this rank alone freeing memory its peers have mapped
+    auto poison = [&](int code) { c->cache_poisoned = true; if (c->nranks == 1) tritd_trim(c); return code; };
     int s;
     double t0 = now_ms();
-    if ((s = tritd_problem_set_D_host(p, D_host)) != TRITD_OK) { tritd_trim(c); return s; }
-    if ((s = tritd_problem_init(p, o, A0, B0, C0)) != TRITD_OK) { tritd_trim(c); return s; }
+    if ((s = tritd_problem_set_D_host(p, D_host)) != TRITD_OK) return poison(s);
+    if (mask_host && (s = tritd_problem_set_mask_host(p, mask_host)) != TRITD_OK) return poison(s);
+    if ((s = tritd_problem_init(p, o, A0, B0, C0)) != TRITD_OK) return poison(s);
     const double t_h2d = now_ms() - t0;
 
     cudaEvent_t e0, e1;
@@ -1124,18 +1287,33 @@ extern "C" int tritd_admm_f64(tritd_ctx* c, const double* D_host, int64_t n1, in
     float it_ms = 0.f;
     cudaEventElapsedTime(&it_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (s != TRITD_OK) { tritd_trim(c); return s; }
+    if (s != TRITD_OK) return poison(s);
 
     t0 = now_ms();
     s = tritd_problem_get(p, A, B, C, O, L, errHist, nullptr, nullptr, &k);
+    if (s == TRITD_OK && E) s = tritd_problem_get_E(p, E);
     const double t_d2h = now_ms() - t0;
-    if (s != TRITD_OK) { tritd_trim(c); return s; }
+    if (s != TRITD_OK) return poison(s);
     if (iters_out) *iters_out = k;
     if (tm) {
         tm->h2d_ms = t_h2d; tm->iterate_ms = it_ms; tm->d2h_ms = t_d2h; tm->total_ms = now_ms() - t_begin;
         tm->iters = k; tm->launches = (int32_t)(c->launches - launches0);
     }
     return TRITD_OK;
+}
+
+extern "C" int tritd_admm_f64(tritd_ctx* c, const double* D_host, int64_t n1, int64_t n2, int64_t n3, int r,
+                              const tritd_opts* o, const double* A0, const double* B0, const double* C0, double* A,
+                              double* B, double* C, double* O, double* L, double* errHist, int32_t* iters_out,
+                              tritd_timing* tm) {
+    return admm_impl(c, D_host, nullptr, n1, n2, n3, r, o, A0, B0, C0, A, B, C, O, nullptr, L, errHist, iters_out, tm);
+}
+
+extern "C" int tritd_admm_ex_f64(tritd_ctx* c, const double* D_host, const unsigned char* mask_or_null, int64_t n1, int64_t n2,
+                                 int64_t n3, int r, const tritd_opts* o, const double* A0, const double* B0, const double* C0,
+                                 double* A, double* B, double* C, double* O, double* E_or_null, double* L_or_null,
+                                 double* errHist, int32_t* iters_out, tritd_timing* tm) {
+    return admm_impl(c, D_host, mask_or_null, n1, n2, n3, r, o, A0, B0, C0, A, B, C, O, E_or_null, L_or_null, errHist, iters_out, tm);
 }
 
 // ---------------------------------------------------------------------------
@@ -1206,34 +1384,68 @@ extern "C" int tritd_als_f64(tritd_ctx* c, const double* X_host, int64_t n1, int
             if (cudaMemcpy(eh.data(), p->errHist, sizeof(double) * done, cudaMemcpyDeviceToHost) != cudaSuccess)
                 return bail(fail(TRITD_ERR_CUDA, "errHist copy failed"));
             for (int k = printed + 1; k <= done; ++k)
-                if (k % 5 == 0) printf("Iteration %d, relative error = %.4e\n", k, eh[k - 1]);
+                if (k % 5 == 0) emit("Iteration %d, relative error = %.4e\n", k, eh[k - 1]);
             printed = done;
-            fflush(stdout);
         }
         if (p->st_host->stop) break;
     }
-    if (p->st_host->status != 0) return bail(fail(TRITD_ERR_NUMERIC, "ridge system not positive definite (ALS iteration %d)", done));
+    if (p->st_host->status != 0) return bail(fail(TRITD_ERR_NUMERIC, "ridge system contains NaN / Inf (ALS iteration %d)", done));
     s = tritd_problem_get(p, A, B, C, nullptr, nullptr, errHist, nullptr, nullptr, nullptr);
     if (iters_out) *iters_out = done;
     tritd_problem_destroy(p);
     return s;
 }
 
-extern "C" int tritd_triple_product_f64(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1,
-                                        int64_t n2, int64_t n3, int r, double* Xhat) {
+// Reconstruction L = triple_product(A,B,C) from the factors resident in `p`, written to `dst` (device) with leading
+// dimension `ld` (even; n1 itself when n1 is even, so a dense caller buffer is written in place).
+static int reconstruct_to(tritd_problem* p, double* dst, int ld) {
+    tritd_ctx* c = p->ctx;
+    FusedArgs a;
+    a.D = nullptr; a.O = dst;
+    a.A1 = p->A1; a.B2 = p->B2; a.C3 = p->C3; a.st = p->st; a.norm_part = p->norm_part;
+    a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.ld1 = ld; a.RS = p->RS;
+    a.n_it = p->n_it; a.n_jc = p->n_jc; a.gi = p->gi;
+#define CALL(NT_, KS_) k_fused<KS_, 1><<<p->gridF, 256, 0, c->stream>>>(a);
+    TRITD_DISPATCH_R(p->r, CALL)
+#undef CALL
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+// dense (ld = n1) when the 16-byte vector stores of k_fused stay aligned, else padded to even
+static int dense_ld(int n1) { return (n1 + 1) & ~1; }
+
+static int triple_product_common(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1, int64_t n2,
+                                 int64_t n3, int r, double* Xhat, bool out_on_device) {
     if (!c || !A || !B || !C || !Xhat) return fail(TRITD_ERR_INVALID, "NULL argument");
     ST_TRY(check_r(r));
     tritd_problem* p = nullptr;
-    ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
+    ST_TRY(problem_create(c, n1, n2, n3, r, kLevelFactors, &p));          // factors + small state only
+    auto done = [&](int code) { cudaStreamSynchronize(c->stream); tritd_problem_destroy(p); return code; };
     int s = upload_factors(p, A, B, C);
-    double* Lbuf = nullptr;
-    if (s == TRITD_OK) s = reconstruct_L(p, &Lbuf);
-    if (s == TRITD_OK) s = copy_out(p, Xhat, Lbuf);
-    cudaStreamSynchronize(c->stream);
-    if (Lbuf) cudaFree(Lbuf);
-    if (s == TRITD_OK && cudaGetLastError() != cudaSuccess) s = fail(TRITD_ERR_CUDA, "triple_product kernel failed");
-    tritd_problem_destroy(p);
-    return s;
+    if (s != TRITD_OK) return done(s);
+    const int ld = dense_ld(p->n1);
+    const size_t ncols = (size_t)p->n2 * p->n3, N = (size_t)p->n1 * ncols;
+    if (out_on_device && ld == p->n1) return done(reconstruct_to(p, Xhat, ld));      // straight into the caller's buffer
+    DevBuf tmp;
+    if ((s = tmp.alloc((size_t)ld * ncols)) != TRITD_OK) return done(s);
+    if ((s = reconstruct_to(p, tmp.p, ld)) != TRITD_OK) return done(s);
+    cudaError_t e;
+    if (ld == p->n1) e = cudaMemcpyAsync(Xhat, tmp.p, N * 8, cudaMemcpyDefault, c->stream);
+    else e = cudaMemcpy2DAsync(Xhat, (size_t)p->n1 * 8, tmp.p, (size_t)ld * 8, (size_t)p->n1 * 8, ncols, cudaMemcpyDefault, c->stream);
+    if (e != cudaSuccess) return done(fail(TRITD_ERR_CUDA, "triple_product copy: %s", cudaGetErrorString(e)));
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return done(fail(TRITD_ERR_CUDA, "triple_product failed: %s", cudaGetErrorString(cudaGetLastError())));
+    return done(TRITD_OK);
+}
+
+extern "C" int tritd_triple_product_f64(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1,
+                                        int64_t n2, int64_t n3, int r, double* Xhat) {
+    return triple_product_common(c, A, B, C, n1, n2, n3, r, Xhat, false);
+}
+extern "C" int tritd_triple_product_dev_f64(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1,
+                                            int64_t n2, int64_t n3, int r, double* Xhat_dev) {
+    return triple_product_common(c, A, B, C, n1, n2, n3, r, Xhat_dev, true);
 }
 
 // Design matrices / triple product of the original (Qi) triple decomposition -- origin_triple_tensor/buildF.m,
@@ -1288,27 +1500,26 @@ extern "C" int tritd_triple_product_qi_f64(tritd_ctx* c, const double* A, const 
 
 // [rmse, nrmse] = evaluate(Xhat, gt, mask) with Xhat = triple_product(A,B,C) formed on the device
 // (traffic_triple_comparison.m:194-202; the drivers' RRE).  gt is a dense n1 x n2 x n3 tensor (entries outside the
-// mask are ignored), mask dense bytes or NULL (all true): the reconstruction never crosses PCIe.
-extern "C" int tritd_evaluate_f64(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1, int64_t n2,
-                                  int64_t n3, int r, const double* gt_host, const unsigned char* mask_host, double* rmse,
-                                  double* nrmse) {
-    if (!c || !A || !B || !C || !gt_host) return fail(TRITD_ERR_INVALID, "NULL argument");
-    ST_TRY(check_r(r));
-    tritd_problem* p = nullptr;
-    ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
-    int s = upload_factors(p, A, B, C);
-    double* Lbuf = nullptr;
+// mask are ignored), mask dense bytes or NULL (all true): the reconstruction never crosses PCIe.  `p` supplies the
+// factors (and the reduction scratch): a kLevelFactors problem for the standalone call, the solver's own problem for
+// tritd_problem_evaluate.  Device memory used: the reconstruction, gt and the mask -- nothing else.
+static int evaluate_with(tritd_problem* p, const double* gt_host, const unsigned char* mask_host, double* rmse, double* nrmse) {
+    tritd_ctx* c = p->ctx;
+    const int ld = dense_ld(p->n1);
+    const size_t ncols = (size_t)p->n2 * p->n3, N = (size_t)p->n1 * ncols;
+    DevBuf L, gt;
+    ST_TRY(L.alloc((size_t)ld * ncols)); ST_TRY(gt.alloc(N));
     unsigned char* mdev = nullptr;
-    const size_t N = (size_t)n1 * n2 * n3;
-    double sums[2] = {0.0, 0.0};
-    if (s == TRITD_OK) s = reconstruct_L(p, &Lbuf);
-    if (s == TRITD_OK) s = copy_in(p, p->D, gt_host);
+    int s = reconstruct_to(p, L.p, ld);
+    if (s == TRITD_OK && cudaMemcpyAsync(gt.p, gt_host, N * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+        s = fail(TRITD_ERR_CUDA, "gt copy failed");
     if (s == TRITD_OK && mask_host) {
         if (cudaMalloc((void**)&mdev, N) != cudaSuccess) s = fail(TRITD_ERR_CUDA, "cudaMalloc(mask) failed");
         else if (cudaMemcpyAsync(mdev, mask_host, N, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) s = fail(TRITD_ERR_CUDA, "mask copy failed");
     }
+    double sums[2] = {0.0, 0.0};
     if (s == TRITD_OK) {
-        k_evaluate<<<1024, 256, 0, c->stream>>>(Lbuf, p->D, mdev, p->n1, p->ld1, (size_t)p->n2 * p->n3, p->norm_part);
+        k_evaluate<<<1024, 256, 0, c->stream>>>(L.p, gt.p, mdev, p->n1, ld, p->n1, ncols, p->norm_part);
         k_sum_pairs<<<1, 256, 0, c->stream>>>(p->norm_part, 1024, p->norms, nullptr);
         c->launches += 2;
         if (cudaMemcpyAsync(sums, p->norms, 16, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
@@ -1316,77 +1527,145 @@ extern "C" int tritd_evaluate_f64(tritd_ctx* c, const double* A, const double* B
             s = fail(TRITD_ERR_CUDA, "evaluate failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     cudaStreamSynchronize(c->stream);
-    if (Lbuf) cudaFree(Lbuf);
     if (mdev) cudaFree(mdev);
-    tritd_problem_destroy(p);
     if (s != TRITD_OK) return s;
     if (rmse) *rmse = sqrt(sums[0]);
     if (nrmse) *nrmse = sqrt(sums[0]) / sqrt(sums[1]);
     return TRITD_OK;
 }
 
-extern "C" int tritd_unfold_f64(tritd_ctx* c, const double* X, int64_t n1, int64_t n2, int64_t n3, int mode, double* Xn) {
+extern "C" int tritd_evaluate_f64(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1, int64_t n2,
+                                  int64_t n3, int r, const double* gt_host, const unsigned char* mask_host, double* rmse,
+                                  double* nrmse) {
+    if (!c || !A || !B || !C || !gt_host) return fail(TRITD_ERR_INVALID, "NULL argument");
+    ST_TRY(check_r(r));
+    tritd_problem* p = nullptr;
+    ST_TRY(problem_create(c, n1, n2, n3, r, kLevelFactors, &p));
+    int s = upload_factors(p, A, B, C);
+    if (s == TRITD_OK) s = evaluate_with(p, gt_host, mask_host, rmse, nrmse);
+    tritd_problem_destroy(p);
+    return s;
+}
+
+// the same with the factors the solver holds on the device (after tritd_problem_iterate): nothing but gt crosses PCIe
+extern "C" int tritd_problem_evaluate(tritd_problem* p, const double* gt_host, const unsigned char* mask_host, double* rmse,
+                                      double* nrmse) {
+    if (!p || !gt_host || !p->initialized) return fail(TRITD_ERR_INVALID, "NULL argument / not initialised");
+    CU_TRY(cudaSetDevice(p->ctx->device));
+    return evaluate_with(p, gt_host, mask_host, rmse, nrmse);
+}
+
+// ---- unfold / buildF / buildG / buildH / soft_threshold: device cores + host wrappers --------------------------
+static int unfold_dev(tritd_ctx* c, const double* X, int64_t n1, int64_t n2, int64_t n3, int mode, double* Xn) {
+    const size_t N = (size_t)n1 * n2 * n3;
+    if (mode == 1) {                     // reshape only (unfold.m:6)
+        if (Xn != X) CU_TRY(cudaMemcpyAsync(Xn, X, N * 8, cudaMemcpyDeviceToDevice, c->stream));
+        return TRITD_OK;
+    }
+    long rows, cols, batch;
+    if (mode == 2) { rows = n1; cols = n2; batch = n3; } else { rows = n1 * n2; cols = n3; batch = 1; }
+    if (batch > 65535 || (cols + 31) / 32 > 65535) return fail(TRITD_ERR_INVALID, "unfold: dimension too large");
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32), (unsigned)batch);
+    const bool vec = rows % 2 == 0 && cols % 2 == 0 && ((uintptr_t)X % 16 == 0) && ((uintptr_t)Xn % 16 == 0);
+    if (vec) k_transpose_v2<<<grid, 256, 0, c->stream>>>(X, Xn, rows, cols);
+    else k_transpose<<<grid, 256, 0, c->stream>>>(X, Xn, rows, cols);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+static int check_unfold_args(tritd_ctx* c, const double* X, int64_t n1, int64_t n2, int64_t n3, int mode, double* Xn) {
     if (!c || !X || !Xn) return fail(TRITD_ERR_INVALID, "NULL argument");
     if (n1 < 1 || n2 < 1 || n3 < 1) return fail(TRITD_ERR_INVALID, "bad size");
     if (mode < 1 || mode > 3) return fail(TRITD_ERR_INVALID, "Mode must be 1, 2, or 3.");
     CU_TRY(cudaSetDevice(c->device));
+    return TRITD_OK;
+}
+
+extern "C" int tritd_unfold_dev_f64(tritd_ctx* c, const double* X_dev, int64_t n1, int64_t n2, int64_t n3, int mode, double* Xn_dev) {
+    ST_TRY(check_unfold_args(c, X_dev, n1, n2, n3, mode, Xn_dev));
+    if (mode != 1 && X_dev == Xn_dev) return fail(TRITD_ERR_INVALID, "unfold: in-place transposition is not supported");
+    return unfold_dev(c, X_dev, n1, n2, n3, mode, Xn_dev);
+}
+
+extern "C" int tritd_unfold_f64(tritd_ctx* c, const double* X, int64_t n1, int64_t n2, int64_t n3, int mode, double* Xn) {
+    ST_TRY(check_unfold_args(c, X, n1, n2, n3, mode, Xn));
     const size_t N = (size_t)n1 * n2 * n3;
     if (mode == 1) { if (Xn != X) memcpy(Xn, X, N * 8); return TRITD_OK; }   // reshape only (unfold.m:6)
     DevBuf in, out;
     ST_TRY(in.alloc(N)); ST_TRY(out.alloc(N));
     CU_TRY(cudaMemcpyAsync(in.p, X, N * 8, cudaMemcpyHostToDevice, c->stream));
-    long rows, cols, batch;
-    if (mode == 2) { rows = n1; cols = n2; batch = n3; } else { rows = n1 * n2; cols = n3; batch = 1; }
-    if (batch > 65535 || (cols + 31) / 32 > 65535) return fail(TRITD_ERR_INVALID, "unfold: dimension too large");
-    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32), (unsigned)batch);
-    k_transpose<<<grid, 256, 0, c->stream>>>(in.p, out.p, rows, cols);
-    CU_TRY(cudaGetLastError());
-    c->launches += 1;
+    ST_TRY(unfold_dev(c, in.p, n1, n2, n3, mode, out.p));
     CU_TRY(cudaMemcpyAsync(Xn, out.p, N * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     return TRITD_OK;
 }
 
-static int khatri_rao_host(tritd_ctx* c, const std::vector<double>& Xa, const std::vector<double>& Xb, long na, long nb,
-                           int R, int RS, double* out_host) {
-    CU_TRY(cudaSetDevice(c->device));
-    DevBuf a, b, o;
-    const size_t total = (size_t)R * na * nb;
-    ST_TRY(a.alloc(Xa.size())); ST_TRY(b.alloc(Xb.size())); ST_TRY(o.alloc(total));
-    CU_TRY(cudaMemcpyAsync(a.p, Xa.data(), Xa.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(cudaMemcpyAsync(b.p, Xb.data(), Xb.size() * 8, cudaMemcpyHostToDevice, c->stream));
-    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)c->num_sms * 16);
-    k_khatri_rao_t<<<grid, 256, 0, c->stream>>>(a.p, b.p, o.p, na, nb, R, RS);
+// which: 0 = F(B,C), 1 = G(A,C), 2 = H(A,B); U, V are the MATLAB 3-D factor arrays on the device
+static int design_dev(tritd_ctx* c, int which, const double* U, const double* V, int64_t na, int64_t nb, int r, double* out) {
+    const int R = r * r;
+    if ((size_t)R * (size_t)na >= ((size_t)1 << 31)) return fail(TRITD_ERR_INVALID, "design matrix: mode too large");
+    dim3 grid((unsigned)(((size_t)R * na + 255) / 256), (unsigned)std::min<int64_t>(nb, 4096));
+    k_build_design<<<grid, 256, 0, c->stream>>>(U, V, out, (int)na, (int)nb, r, which);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
-    CU_TRY(cudaMemcpyAsync(out_host, o.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
+    return TRITD_OK;
+}
+
+extern "C" int tritd_build_design_dev_f64(tritd_ctx* c, int which, const double* U_dev, const double* V_dev, int64_t na, int64_t nb,
+                                          int r, double* out_dev) {
+    if (!c || !U_dev || !V_dev || !out_dev || na < 1 || nb < 1 || which < 0 || which > 2) return fail(TRITD_ERR_INVALID, "bad argument");
+    ST_TRY(check_r(r));
+    CU_TRY(cudaSetDevice(c->device));
+    return design_dev(c, which, U_dev, V_dev, na, nb, r, out_dev);
+}
+
+static int design_host(tritd_ctx* c, int which, const double* U, const double* V, int64_t na, int64_t nb, int r, double* out) {
+    if (!c || !U || !V || !out || na < 1 || nb < 1) return fail(TRITD_ERR_INVALID, "bad argument");
+    ST_TRY(check_r(r));
+    CU_TRY(cudaSetDevice(c->device));
+    const size_t R = (size_t)r * r, total = R * na * nb;
+    DevBuf u, v, o;
+    ST_TRY(u.alloc(R * na)); ST_TRY(v.alloc(R * nb)); ST_TRY(o.alloc(total));
+    CU_TRY(cudaMemcpyAsync(u.p, U, R * na * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(v.p, V, R * nb * 8, cudaMemcpyHostToDevice, c->stream));
+    ST_TRY(design_dev(c, which, u.p, v.p, na, nb, r, o.p));
+    CU_TRY(cudaMemcpyAsync(out, o.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     return TRITD_OK;
 }
 
 extern "C" int tritd_buildF_f64(tritd_ctx* c, const double* B, const double* C, int64_t n2, int64_t n3, int r, double* F) {
-    if (!c || !B || !C || !F || n2 < 1 || n3 < 1) return fail(TRITD_ERR_INVALID, "bad argument");
-    ST_TRY(check_r(r));
-    const int R = r * r, RS = (R + 7) / 8 * 8;
-    std::vector<double> b2, c3;
-    pack_B(B, (int)n2, r, RS, b2); pack_C(C, (int)n3, R, RS, c3);
-    return khatri_rao_host(c, b2, c3, n2, n3, R, RS, F);
+    return design_host(c, 0, B, C, n2, n3, r, F);
 }
 extern "C" int tritd_buildG_f64(tritd_ctx* c, const double* A, const double* C, int64_t n1, int64_t n3, int r, double* G) {
-    if (!c || !A || !C || !G || n1 < 1 || n3 < 1) return fail(TRITD_ERR_INVALID, "bad argument");
-    ST_TRY(check_r(r));
-    const int R = r * r, RS = (R + 7) / 8 * 8;
-    std::vector<double> a1, c3;
-    pack_A(A, (int)n1, R, RS, a1); pack_C(C, (int)n3, R, RS, c3);
-    return khatri_rao_host(c, a1, c3, n1, n3, R, RS, G);
+    return design_host(c, 1, A, C, n1, n3, r, G);
 }
 extern "C" int tritd_buildH_f64(tritd_ctx* c, const double* A, const double* B, int64_t n1, int64_t n2, int r, double* H) {
-    if (!c || !A || !B || !H || n1 < 1 || n2 < 1) return fail(TRITD_ERR_INVALID, "bad argument");
-    ST_TRY(check_r(r));
-    const int R = r * r, RS = (R + 7) / 8 * 8;
-    std::vector<double> a1, b2;
-    pack_A(A, (int)n1, R, RS, a1); pack_B(B, (int)n2, r, RS, b2);
-    return khatri_rao_host(c, a1, b2, n1, n2, R, RS, H);
+    return design_host(c, 2, A, B, n1, n2, r, H);
+}
+
+static int soft_threshold_dev(tritd_ctx* c, const double* X, int64_t n, double lam, double* out) {
+    const size_t n2 = (size_t)n / 2;
+    const bool vec = ((uintptr_t)X % 16 == 0) && ((uintptr_t)out % 16 == 0) && n2 > 0;
+    if (vec) {
+        const unsigned grid = (unsigned)std::min<size_t>((n2 + 255) / 256, (size_t)c->num_sms * 16);
+        k_soft_threshold_v2<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const double2*>(X), reinterpret_cast<double2*>(out), n2, lam);
+        if (n & 1) k_soft_threshold<<<1, 32, 0, c->stream>>>(X + 2 * n2, out + 2 * n2, 1, lam);
+    } else {
+        const unsigned grid = (unsigned)std::min<size_t>(((size_t)n + 255) / 256, (size_t)c->num_sms * 16);
+        k_soft_threshold<<<grid, 256, 0, c->stream>>>(X, out, (size_t)n, lam);
+    }
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
+
+extern "C" int tritd_soft_threshold_dev_f64(tritd_ctx* c, const double* X_dev, int64_t n, double lam, double* out_dev) {
+    if (!c || !X_dev || !out_dev || n < 0) return fail(TRITD_ERR_INVALID, "bad argument");
+    if (n == 0) return TRITD_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    return soft_threshold_dev(c, X_dev, n, lam, out_dev);
 }
 
 extern "C" int tritd_soft_threshold_f64(tritd_ctx* c, const double* X, int64_t n, double lam, double* out) {
@@ -1396,22 +1675,53 @@ extern "C" int tritd_soft_threshold_f64(tritd_ctx* c, const double* X, int64_t n
     DevBuf in, o;
     ST_TRY(in.alloc((size_t)n)); ST_TRY(o.alloc((size_t)n));
     CU_TRY(cudaMemcpyAsync(in.p, X, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-    const unsigned grid = (unsigned)std::min<size_t>(((size_t)n + 255) / 256, (size_t)c->num_sms * 16);
-    k_soft_threshold<<<grid, 256, 0, c->stream>>>(in.p, o.p, (size_t)n, lam);
-    CU_TRY(cudaGetLastError());
-    c->launches += 1;
+    ST_TRY(soft_threshold_dev(c, in.p, n, lam, o.p));
     CU_TRY(cudaMemcpyAsync(out, o.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     return TRITD_OK;
 }
 
+// Measured FP64 tensor-core (DMMA.8x8x4) peak of this GPU: the denominator of the "FP64-TC roofline %" north_star asks
+// for (MEASURED_PEAKS.json holds only HBM and bf16 peaks).  One CTA of 16 warps per SM, 8 independent accumulator
+// chains per warp, `ms_budget` milliseconds of back-to-back launches after a warm-up.
+extern "C" int tritd_measure_dmma_peak(tritd_ctx* c, double ms_budget, double* tflops) {
+    if (!c || !tflops) return fail(TRITD_ERR_INVALID, "NULL argument");
+    CU_TRY(cudaSetDevice(c->device));
+    DevBuf out;
+    ST_TRY(out.alloc((size_t)c->num_sms * 512));
+    const int iters = 4000;
+    cudaEvent_t e0, e1;
+    CU_TRY(cudaEventCreate(&e0)); CU_TRY(cudaEventCreate(&e1));
+    auto run = [&](int reps, float* ms) -> int {
+        CU_TRY(cudaEventRecord(e0, c->stream));
+        for (int q = 0; q < reps; ++q) k_dmma_peak<<<c->num_sms, 512, 0, c->stream>>>(out.p, iters);
+        CU_TRY(cudaEventRecord(e1, c->stream));
+        CU_TRY(cudaEventSynchronize(e1));
+        CU_TRY(cudaEventElapsedTime(ms, e0, e1));
+        c->launches += reps;
+        return TRITD_OK;
+    };
+    float ms = 0.f;
+    int s = run(3, &ms);                                          // warm-up + calibration
+    if (s == TRITD_OK) {
+        const int reps = std::max(3, (int)(ms_budget / std::max(ms / 3.0f, 1e-3f)));
+        s = run(reps, &ms);
+        if (s == TRITD_OK) *tflops = (double)reps * c->num_sms * 16.0 * iters * 8.0 * 512.0 / (ms * 1e-3) * 1e-12;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return s;
+}
+
+// The three contractions of one sweep at fixed factors, through the SOLVER's own kernels: mode 1 = k_mttkrp1 (+ its
+// fixed-order reduction), modes 2 / 3 = k_ppass followed by k_upd's strided-sum sources over t / over j (the very
+// reductions update_B / update_C run; apply = 0 stops before the ridge solve).
 extern "C" int tritd_mttkrp_f64(tritd_ctx* c, const double* X, const double* A, const double* B, const double* C,
                                 int64_t n1, int64_t n2, int64_t n3, int r, int mode, double* rhs) {
     if (!c || !X || !A || !B || !C || !rhs) return fail(TRITD_ERR_INVALID, "NULL argument");
     if (mode < 1 || mode > 3) return fail(TRITD_ERR_INVALID, "Mode must be 1, 2, or 3.");
     ST_TRY(check_r(r));
     tritd_problem* p = nullptr;
-    ST_TRY(tritd_problem_create(c, n1, n2, n3, r, &p));
+    ST_TRY(problem_create(c, n1, n2, n3, r, kLevelContract, &p));
     cudaStream_t st = c->stream;
     auto body = [&]() -> int {
         ST_TRY(copy_in(p, p->T, X));
@@ -1429,18 +1739,56 @@ extern "C" int tritd_mttkrp_f64(tritd_ctx* c, const double* X, const double* A, 
             CU_TRY(cudaMemcpyAsync(p->A1T, a1t.data(), a1t.size() * 8, cudaMemcpyHostToDevice, st));
             CU_TRY(cudaStreamSynchronize(st));
             ST_TRY(launch_ppass(p, p->mapT));
-            if (mode == 2) {
-                k_rhsB<<<p->n2, 256, 0, st>>>(p->P, p->C3, p->rhsB, p->n2, p->n3, p->RS, &p->st->stop);
-                CU_TRY(cudaMemcpyAsync(h.data(), p->rhsB, h.size() * 8, cudaMemcpyDeviceToHost, st));
-            } else {
-                k_rhsC<<<p->n3, 256, 0, st>>>(p->P, p->B2, p->rhsC, p->n2, p->n3, p->RS, &p->st->stop);
-                CU_TRY(cudaMemcpyAsync(h.data(), p->rhsC, h.size() * 8, cudaMemcpyDeviceToHost, st));
-            }
-            CU_TRY(cudaGetLastError());
-            c->launches += 1;
+            double* out = mode == 2 ? p->rhsB : p->rhsC;
+            ST_TRY(launch_upd(p, mode - 1, mode == 2 ? kSrcPB : kSrcPC, false, nullptr, out, nullptr, nullptr, 0.0, nullptr, nullptr, n, nullptr));
+            CU_TRY(cudaMemcpyAsync(h.data(), out, h.size() * 8, cudaMemcpyDeviceToHost, st));
         }
         CU_TRY(cudaStreamSynchronize(st));
         for (int k = 0; k < p->R; ++k) for (int i = 0; i < n; ++i) rhs[(size_t)k * n + i] = h[(size_t)i * p->RS + k];
+        return TRITD_OK;
+    };
+    int s = body();
+    tritd_problem_destroy(p);
+    return s;
+}
+
+// One factor update in isolation (update_A/B/C after the contraction, :77-78 / :86 / :93): X = RHS * pinv(S1 o S2 +
+// alpha*I) through k_upd exactly as the solver launches it (direct RHS source): also returns the pseudo-inverse and
+// X'X, plus info[0] = 1 when the truncating pinv path ran and info[1] = singular values it zeroed.
+extern "C" int tritd_factor_update_f64(tritd_ctx* c, const double* rhs, int64_t n, int r, const double* S1, const double* S2,
+                                       double alpha, double* X, double* Ginv_or_null, double* XtX_or_null, int32_t* info_or_null) {
+    if (!c || !rhs || !S1 || !S2 || !X || n < 1) return fail(TRITD_ERR_INVALID, "bad argument");
+    ST_TRY(check_r(r));
+    tritd_problem* p = nullptr;
+    // the update runs over "mode 1" of an n x 1 x 1 problem: only the factor-sized state is used
+    ST_TRY(problem_create(c, n, 1, 1, r, kLevelFactors, &p));
+    cudaStream_t st = c->stream;
+    const int R = p->R, RS = p->RS;
+    auto body = [&]() -> int {
+        std::vector<double> h((size_t)n * RS, 0.0), g((size_t)RS * RS, 0.0);
+        for (int k = 0; k < R; ++k) for (int64_t i = 0; i < n; ++i) h[(size_t)i * RS + k] = rhs[(size_t)k * n + i];
+        CU_TRY(cudaMemcpyAsync(p->bufA, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        double* S2d = p->bufA + (size_t)p->n1 * RS;
+        for (int a = 0; a < R; ++a) for (int b = 0; b < R; ++b) g[(size_t)a * RS + b] = S1[(size_t)b * R + a];
+        CU_TRY(cudaMemcpyAsync(p->SB, g.data(), g.size() * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        for (int a = 0; a < R; ++a) for (int b = 0; b < R; ++b) g[(size_t)a * RS + b] = S2[(size_t)b * R + a];
+        CU_TRY(cudaMemcpyAsync(S2d, g.data(), g.size() * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        ST_TRY(launch_upd(p, 0, kSrcDirect, true, p->bufA, nullptr, p->SB, S2d, alpha, p->A1, p->A1T, (int)n, p->SA));
+        ST_TRY(fetch_state(p));
+        CU_TRY(cudaMemcpy(h.data(), p->A1, h.size() * 8, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < R; ++k) for (int64_t i = 0; i < n; ++i) X[(size_t)k * n + i] = h[(size_t)i * RS + k];
+        if (Ginv_or_null) {
+            CU_TRY(cudaMemcpy(g.data(), p->Minv, g.size() * 8, cudaMemcpyDeviceToHost));
+            for (int a = 0; a < R; ++a) for (int b = 0; b < R; ++b) Ginv_or_null[(size_t)b * R + a] = g[(size_t)a * RS + b];
+        }
+        if (XtX_or_null) {
+            CU_TRY(cudaMemcpy(g.data(), p->SA, g.size() * 8, cudaMemcpyDeviceToHost));
+            for (int a = 0; a < R; ++a) for (int b = 0; b < R; ++b) XtX_or_null[(size_t)b * R + a] = g[(size_t)a * RS + b];
+        }
+        if (info_or_null) { info_or_null[0] = p->st_host->pinv_fallbacks; info_or_null[1] = p->st_host->pinv_truncated; }
         return TRITD_OK;
     };
     int s = body();

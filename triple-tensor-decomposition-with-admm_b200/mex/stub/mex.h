@@ -16,6 +16,11 @@ int mxIsComplex(const mxArray*);
 int mxIsSparse(const mxArray*);
 int mxIsStruct(const mxArray*);
 int mxIsEmpty(const mxArray*);
+int mxIsLogical(const mxArray*);
+typedef unsigned char mxLogical;
+mxLogical* mxGetLogicals(const mxArray*);
+mxArray* mxCreateStructMatrix(mwSize, mwSize, int, const char**);
+void mxSetField(mxArray*, size_t, const char*, mxArray*);
 mwSize mxGetNumberOfDimensions(const mxArray*);
 const mwSize* mxGetDimensions(const mxArray*);
 size_t mxGetNumberOfElements(const mxArray*);

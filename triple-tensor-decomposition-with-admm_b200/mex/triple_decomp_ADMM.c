@@ -6,8 +6,10 @@
  * validates arguments, draws the initial factors with MATLAB's own randn in the reference's
  * order (:23 -- A, B, C -- so rng(0) in the caller gives the reference's factors) and moves
  * mxArrays in and out.  Optional extension fields of opts: A0, B0, C0 (injected
- * initial factors), device (CUDA ordinal).  A sixth output, when requested, is
- * L = triple_product(A,B,C).
+ * initial factors), device (CUDA ordinal), mask (logical n1 x n2 x n3, true = observed: the completion
+ * variant, see triple_ADMM_masked.c).  A sixth output, when requested, is L = triple_product(A,B,C), a seventh is
+ * E ("O,E : sparse components (clone E)", triple_decomp_ADMM.m:12).  The progress line of opts.disp (:60-62) is
+ * printed through mexPrintf.
  *
  * Build (on a machine with MATLAB + CUDA):
  *   mex -I../../include triple_decomp_ADMM.c -L../tritd -ltritd
@@ -24,10 +26,16 @@ static void at_exit(void) {
     if (g_ctx) { tritd_destroy(g_ctx); g_ctx = NULL; }
 }
 
+static void to_matlab_console(const char* line, void* user) {
+    (void)user;
+    mexPrintf("%s", line);
+}
+
+/* a required scalar field of opts; logical is accepted (opts.disp = true) */
 static double req_field(const mxArray* opts, const char* name) {
     const mxArray* f = mxGetField(opts, 0, name);
     if (!f) mexErrMsgIdAndTxt("MATLAB:nonExistentField", "Unrecognized field name \"%s\".", name);
-    if (!mxIsDouble(f) && mxGetNumberOfElements(f) != 1)
+    if (!(mxIsDouble(f) || mxIsLogical(f)) || mxIsComplex(f) || mxIsSparse(f) || mxGetNumberOfElements(f) != 1)
         mexErrMsgIdAndTxt("tritd:opts", "opts.%s must be a real scalar.", name);
     return mxGetScalar(f);
 }
@@ -52,7 +60,7 @@ static mxArray* randn3(mwSize a, mwSize b, mwSize c) {
 
 void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (nrhs != 3) mexErrMsgIdAndTxt("tritd:nargin", "Usage: [A,B,C,O,errHist] = triple_decomp_ADMM(D, r, opts)");
-    if (nlhs > 6) mexErrMsgIdAndTxt("MATLAB:TooManyOutputs", "Too many output arguments.");
+    if (nlhs > 7) mexErrMsgIdAndTxt("MATLAB:TooManyOutputs", "Too many output arguments.");
     const mxArray* Dm = prhs[0];
     if (!mxIsDouble(Dm) || mxIsComplex(Dm) || mxIsSparse(Dm)) mexErrMsgIdAndTxt("tritd:D", "D must be a full real double array.");
     const mwSize nd = mxGetNumberOfDimensions(Dm);
@@ -92,6 +100,18 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         mexLock();
         mexAtExit(at_exit);
     }
+    tritd_set_print(to_matlab_console, NULL);
+
+    /* optional completion mask: logical, size of D, true = observed */
+    const unsigned char* mask = NULL;
+    {
+        const mxArray* mk = mxGetField(om, 0, "mask");
+        if (mk && !mxIsEmpty(mk)) {
+            if (!mxIsLogical(mk) || mxGetNumberOfElements(mk) != (size_t)n1 * n2 * n3)
+                mexErrMsgIdAndTxt("tritd:opts", "opts.mask must be a logical array of the size of D.");
+            mask = (const unsigned char*)mxGetLogicals(mk);
+        }
+    }
 
     const mwSize dA[3] = {n1, (mwSize)r, (mwSize)r}, dB[3] = {(mwSize)r, n2, (mwSize)r}, dC[3] = {(mwSize)r, (mwSize)r, n3};
     const mwSize dO[3] = {n1, n2, n3};
@@ -100,14 +120,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     mxArray* Cm = mxCreateNumericArray(3, dC, mxDOUBLE_CLASS, mxREAL);
     mxArray* Om = nlhs >= 4 ? mxCreateNumericArray(3, dO, mxDOUBLE_CLASS, mxREAL) : NULL;
     mxArray* Lm = nlhs >= 6 ? mxCreateNumericArray(3, dO, mxDOUBLE_CLASS, mxREAL) : NULL;
+    mxArray* Em = nlhs >= 7 ? mxCreateNumericArray(3, dO, mxDOUBLE_CLASS, mxREAL) : NULL;
     double* eh = (double*)mxMalloc(sizeof(double) * (size_t)(o.maxIter > 0 ? o.maxIter : 1));
     int32_t iters = 0;
 
-    /* inputs are MATLAB-owned and only read; the library prints the reference's progress line
-     * ("Iter %d, errL=%.2e, errO=%.2e", :60-62) itself when opts.disp is set */
-    const int st = tritd_admm_f64(g_ctx, mxGetPr(Dm), (int64_t)n1, (int64_t)n2, (int64_t)n3, r, &o, A0, B0, C0,
-                                  mxGetPr(Am), mxGetPr(Bm), mxGetPr(Cm), Om ? mxGetPr(Om) : NULL,
-                                  Lm ? mxGetPr(Lm) : NULL, eh, &iters, NULL);
+    /* inputs are MATLAB-owned and only read; the library emits the reference's progress line
+     * ("Iter %d, errL=%.2e, errO=%.2e", :60-62) through the print sink when opts.disp is set */
+    const int st = tritd_admm_ex_f64(g_ctx, mxGetPr(Dm), mask, (int64_t)n1, (int64_t)n2, (int64_t)n3, r, &o, A0, B0, C0,
+                                     mxGetPr(Am), mxGetPr(Bm), mxGetPr(Cm), Om ? mxGetPr(Om) : NULL,
+                                     Em ? mxGetPr(Em) : NULL, Lm ? mxGetPr(Lm) : NULL, eh, &iters, NULL);
     if (A0m) mxDestroyArray(A0m);
     if (B0m) mxDestroyArray(B0m);
     if (C0m) mxDestroyArray(C0m);
@@ -125,5 +146,6 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         memcpy(mxGetPr(plhs[4]), eh, sizeof(double) * (size_t)iters);
     }
     if (nlhs >= 6) plhs[5] = Lm;
+    if (nlhs >= 7) plhs[6] = Em;
     mxFree(eh);
 }

@@ -21,10 +21,15 @@ static void at_exit(void) {
     if (g_ctx) { tritd_destroy(g_ctx); g_ctx = NULL; }
 }
 
+static void to_matlab_console(const char* line, void* user) {
+    (void)user;
+    mexPrintf("%s", line);
+}
+
 static double req_field(const mxArray* opts, const char* name) {
     const mxArray* f = mxGetField(opts, 0, name);
     if (!f) mexErrMsgIdAndTxt("MATLAB:nonExistentField", "Unrecognized field name \"%s\".", name);
-    if (!mxIsDouble(f) && mxGetNumberOfElements(f) != 1)
+    if (!(mxIsDouble(f) || mxIsLogical(f)) || mxIsComplex(f) || mxIsSparse(f) || mxGetNumberOfElements(f) != 1)
         mexErrMsgIdAndTxt("tritd:opts", "opts.%s must be a real scalar.", name);
     return mxGetScalar(f);
 }
@@ -83,6 +88,7 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         mexLock();
         mexAtExit(at_exit);
     }
+    tritd_set_print(to_matlab_console, NULL);
 
     const mwSize dA[3] = {n1, (mwSize)r, (mwSize)r}, dB[3] = {(mwSize)r, n2, (mwSize)r}, dC[3] = {(mwSize)r, (mwSize)r, n3};
     mxArray* Am = mxCreateNumericArray(3, dA, mxDOUBLE_CLASS, mxREAL);

@@ -66,6 +66,9 @@ SYMBOLS = {
     "tritd_slab_bounds": (C.c_int, [_i64, C.c_int, C.c_int, C.POINTER(_i64), C.POINTER(_i64)]),
     "tritd_admm_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int, C.POINTER(tritd_opts), _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), C.POINTER(tritd_timing)]),
+    "tritd_admm_ex_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, C.c_int, C.POINTER(tritd_opts), _vp, _vp, _vp,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), C.POINTER(tritd_timing)]),
+    "tritd_set_print": (None, [_vp, _vp]),
     "tritd_trim": (C.c_int, [_vp]),
     "tritd_evaluate_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, C.c_int, _vp, _vp, C.POINTER(C.c_double),
                                      C.POINTER(C.c_double)]),
@@ -77,6 +80,12 @@ SYMBOLS = {
     "tritd_problem_destroy": (None, [_vp]),
     "tritd_problem_set_D_host": (C.c_int, [_vp, _vp]),
     "tritd_problem_set_D_dev": (C.c_int, [_vp, _vp]),
+    "tritd_problem_set_mask_host": (C.c_int, [_vp, _vp]),
+    "tritd_problem_set_mask_dev": (C.c_int, [_vp, _vp]),
+    "tritd_problem_get_E": (C.c_int, [_vp, _vp]),
+    "tritd_problem_get_E_dev": (C.c_int, [_vp, _vp]),
+    "tritd_problem_evaluate": (C.c_int, [_vp, _vp, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "tritd_problem_pinv_stats": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "tritd_problem_init": (C.c_int, [_vp, C.POINTER(tritd_opts), _vp, _vp, _vp]),
     "tritd_problem_iterate": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_int32)]),
     "tritd_problem_enqueue": (C.c_int, [_vp, C.c_int32]),
@@ -85,10 +94,16 @@ SYMBOLS = {
     "tritd_problem_get_O_dev": (C.c_int, [_vp, _vp]),
     "tritd_problem_get_L_dev": (C.c_int, [_vp, _vp]),
     "tritd_launch_count": (C.c_int64, [_vp]),
+    "tritd_measure_dmma_peak": (C.c_int, [_vp, C.c_double, C.POINTER(C.c_double)]),
     "tritd_problem_set_profiling": (C.c_int, [_vp, C.c_int]),
     "tritd_problem_phase_ms": (C.c_int, [_vp, _vp, C.POINTER(C.c_int32)]),
     "tritd_triple_product_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, C.c_int, _vp]),
+    "tritd_triple_product_dev_f64": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, C.c_int, _vp]),
     "tritd_unfold_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int, _vp]),
+    "tritd_unfold_dev_f64": (C.c_int, [_vp, _vp, _i64, _i64, _i64, C.c_int, _vp]),
+    "tritd_build_design_dev_f64": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _i64, C.c_int, _vp]),
+    "tritd_soft_threshold_dev_f64": (C.c_int, [_vp, _vp, _i64, C.c_double, _vp]),
+    "tritd_factor_update_f64": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp]),
     "tritd_buildF_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_int, _vp]),
     "tritd_buildG_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_int, _vp]),
     "tritd_buildH_f64": (C.c_int, [_vp, _vp, _vp, _i64, _i64, C.c_int, _vp]),
@@ -172,6 +187,12 @@ class Context:
     def launches(self) -> int:
         return int(load_library().tritd_launch_count(self._h))
 
+    def measure_dmma_peak(self, ms_budget=50.0) -> float:
+        """measured FP64 tensor-core (DMMA) peak of this GPU, TFLOP/s"""
+        t = C.c_double()
+        _check(load_library().tritd_measure_dmma_peak(self._h, float(ms_budget), C.byref(t)))
+        return t.value
+
     def trim(self):
         """Release the device state tritd_admm_f64 caches between equally shaped calls."""
         _check(load_library().tritd_trim(self._h))
@@ -222,6 +243,35 @@ class Problem:
 
     def set_D_dev(self, dev_ptr):
         _check(load_library().tritd_problem_set_D_dev(self._h, _vp(dev_ptr)))
+
+    def set_mask(self, mask):
+        """completion variant: boolean tensor of D's shape, True = observed (call after set_D, before init)"""
+        m = np.asfortranarray(np.asarray(mask).astype(bool), dtype=np.uint8)
+        if m.shape != self.shape:
+            raise ValueError("mask must have the shape of D")
+        _check(load_library().tritd_problem_set_mask_host(self._h, m.ctypes.data_as(_vp)))
+
+    def get_E(self):
+        E = np.zeros(self.shape, order="F")
+        _check(load_library().tritd_problem_get_E(self._h, _ptr(E)))
+        return E
+
+    def evaluate(self, gt, mask=None):
+        """[rmse, nrmse] = evaluate(triple_product(A,B,C), gt, mask) with the resident factors"""
+        gt = _f64(gt, self.shape)
+        m = None
+        if mask is not None:
+            m = np.asfortranarray(np.asarray(mask).astype(bool), dtype=np.uint8)
+        rmse, nrmse = C.c_double(), C.c_double()
+        _check(load_library().tritd_problem_evaluate(self._h, _ptr(gt), m.ctypes.data_as(_vp) if m is not None else None,
+                                                     C.byref(rmse), C.byref(nrmse)))
+        return rmse.value, nrmse.value
+
+    def pinv_stats(self):
+        """(ridge solves that took the truncating pinv path, singular values they zeroed)"""
+        a, b = C.c_int32(), C.c_int32()
+        _check(load_library().tritd_problem_pinv_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def init(self, opts, A0, B0, C0):
         n1, n2, n3 = self.shape
@@ -288,14 +338,16 @@ class Problem:
 # the reference's functions
 # --------------------------------------------------------------------------
 def triple_decomp_ADMM(D, r, opts, A0=None, B0=None, C0=None, rng=None, ctx=None, return_info=False, want_L=False,
-                       out_O=None):
+                       out_O=None, mask=None, want_E=False):
     """[A,B,C,O,errHist] = triple_decomp_ADMM(D, r, opts)   (triple_decomp_ADMM.m:1-70).
 
     The reference draws A,B,C with randn at :23 (order A, B, C).  Here the same
     order is drawn from ``rng`` (numpy Generator; default_rng(0) if omitted)
     unless ``A0,B0,C0`` (or ``opts['A0']`` ...) inject them -- the library itself
     never draws random numbers.  ``out_O`` may be a preallocated Fortran-ordered float64 array (e.g. a view of pinned
-    memory) to receive O."""
+    memory) to receive O.  Extensions (SURVEY 8f rank 2, default path untouched): ``want_E`` adds E to ``info``;
+    ``mask`` (boolean, True = observed; also ``opts['mask']``) selects the completion variant, see
+    :func:`triple_ADMM_masked`."""
     D = np.asarray(D)
     if D.ndim == 2:                       # MATLAB hands an n1 x n2 x 1 tensor over as 2-D
         D = D[:, :, None]
@@ -323,18 +375,73 @@ def triple_decomp_ADMM(D, r, opts, A0=None, B0=None, C0=None, rng=None, ctx=None
     else:
         O = np.zeros((n1, n2, n3), order="F")
     L = np.zeros((n1, n2, n3), order="F") if want_L else None
+    E = np.zeros((n1, n2, n3), order="F") if want_E else None
+    mask = opts.get("mask", mask)
+    m = None
+    if mask is not None:
+        m = np.asfortranarray(np.asarray(mask).astype(bool), dtype=np.uint8)
+        if m.ndim == 2:
+            m = m[:, :, None]
+        if m.shape != (n1, n2, n3):
+            raise ValueError("mask must have the shape of D")
     errHist = np.zeros(o.maxIter)
     k = C.c_int32()
     tm = tritd_timing()
-    _check(load_library().tritd_admm_f64(ctx._h, _ptr(D), n1, n2, n3, r, C.byref(o), _ptr(A0), _ptr(B0), _ptr(C0),
-                                         _ptr(A), _ptr(B), _ptr(Cc), _ptr(O), _ptr(L), _ptr(errHist), C.byref(k),
-                                         C.byref(tm)))
+    if m is None and E is None:          # the reference's own call: the 3-in / 5-out entry point
+        _check(load_library().tritd_admm_f64(ctx._h, _ptr(D), n1, n2, n3, r, C.byref(o), _ptr(A0), _ptr(B0), _ptr(C0),
+                                             _ptr(A), _ptr(B), _ptr(Cc), _ptr(O), _ptr(L), _ptr(errHist), C.byref(k),
+                                             C.byref(tm)))
+    else:
+        _check(load_library().tritd_admm_ex_f64(ctx._h, _ptr(D), m.ctypes.data_as(_vp) if m is not None else None, n1, n2, n3,
+                                                r, C.byref(o), _ptr(A0), _ptr(B0), _ptr(C0), _ptr(A), _ptr(B), _ptr(Cc),
+                                                _ptr(O), _ptr(E), _ptr(L), _ptr(errHist), C.byref(k), C.byref(tm)))
     errHist = errHist[:k.value].copy()
     if return_info:
         info = dict(iters=k.value, h2d_ms=tm.h2d_ms, iterate_ms=tm.iterate_ms, d2h_ms=tm.d2h_ms, total_ms=tm.total_ms,
-                    launches=tm.launches, L=L)
+                    launches=tm.launches, L=L, E=E)
         return A, B, Cc, O, errHist, info
     return A, B, Cc, O, errHist
+
+
+def triple_ADMM_masked(Y, mask, r, opts, A0=None, B0=None, C0=None, rng=None, ctx=None):
+    """[A,B,C,O,E,Out] = triple_ADMM_masked(Y, mask, r, opts) -- the completion variant the reference's drivers name
+    in a comment (traffic_triple_comparison.m:53, video_triple_comparison.m:52: ``triple_ADMM_masked(Y, ~mask_missing,
+    r, opts)``, ``errHist = Out.errHist``) but do not ship.  ``mask`` True = observed.  Semantics: DESIGN.md 4.6."""
+    A, B, Cc, O, eh, info = triple_decomp_ADMM(Y, r, opts, A0, B0, C0, rng=rng, ctx=ctx, return_info=True, mask=mask,
+                                                want_E=True)
+    return A, B, Cc, O, info["E"], dict(errHist=eh, iters=info["iters"])
+
+
+_print_cb = None
+
+
+def set_print(fn):
+    """Route the progress lines through ``fn(str)`` (None: back to stdout) -- what a MEX gateway does with mexPrintf."""
+    global _print_cb
+    lib = load_library()
+    if fn is None:
+        _print_cb = None
+        lib.tritd_set_print(None, None)
+        return
+    _print_cb = C.CFUNCTYPE(None, C.c_char_p, _vp)(lambda line, user: fn(line.decode()))
+    lib.tritd_set_print(C.cast(_print_cb, _vp), None)
+
+
+def factor_update(rhs, S1, S2, alpha, ctx=None):
+    """X = rhs * pinv(S1 .* S2 + alpha*eye) through the solver's update kernel (update_A/B/C, :77-78/:86/:93).
+    -> X, pinv, X'X, (took the truncating path?, singular values zeroed)"""
+    rhs = _f64(rhs)
+    n, R = rhs.shape
+    r = int(round(R ** 0.5))
+    if r * r != R:
+        raise ValueError("rhs must have r^2 columns")
+    S1 = _f64(S1, (R, R)); S2 = _f64(S2, (R, R))
+    X = np.zeros((n, R), order="F"); Gi = np.zeros((R, R), order="F"); XtX = np.zeros((R, R), order="F")
+    info = (C.c_int32 * 2)()
+    ctx = ctx or default_context()
+    _check(load_library().tritd_factor_update_f64(ctx._h, _ptr(rhs), n, r, _ptr(S1), _ptr(S2), float(alpha), _ptr(X), _ptr(Gi),
+                                                  _ptr(XtX), info))
+    return X, Gi, XtX, (int(info[0]), int(info[1]))
 
 
 def triple_decomp_ALS(X, r, opts, A0=None, B0=None, C0=None, rng=None, ctx=None, disp=None):
