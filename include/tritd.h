@@ -28,7 +28,8 @@
  *    serialised by the caller.
  *
  * Multi-GPU: the tensor is sharded along its slowest mode (t, mode 3) into
- * contiguous slabs, one per rank (tritd_slab_bounds).  A context created
+ * contiguous slabs, one per rank (tritd_slab_bounds).  Either one process drives all GPUs
+ * (tritd_create_devices: full tensors in and out, the MEX gateway's mode) or: a context created
  * with tritd_create_rank() is one rank of an NCCL communicator (one process
  * per GPU; the 128-byte unique id is exchanged by the caller, e.g. through
  * torch.distributed); every rank then passes only ITS slab of D / C0 and
@@ -96,6 +97,14 @@ int tritd_create(int device, tritd_ctx** out);
  * on rank 0 and distributed by the caller. */
 int tritd_nccl_unique_id(void* id_out);
 int tritd_create_rank(int device, int rank, int nranks, const void* nccl_id, tritd_ctx** out);
+
+/* Single-PROCESS multi-GPU context over `ndev` (1..8) distinct devices with mutual peer access -- what a MEX gateway
+ * needs, MATLAB being one process (traffic_triple_comparison.m:55).  tritd_admm_f64 / tritd_admm_ex_f64 on such a
+ * context take and return FULL tensors: device g owns the mode-3 slab tritd_slab_bounds(n3, ndev, g) (n3 >= ndev), the
+ * per-iteration partials travel through the same NVLink peer mailboxes as with tritd_create_rank (mapped by peer
+ * access: no IPC, no NCCL), A and B are taken from device 0.  The staged tritd_problem_* solver API needs a
+ * single-device context; the standalone helpers run on the first device. */
+int tritd_create_devices(const int* devices, int ndev, tritd_ctx** out);
 
 void tritd_destroy(tritd_ctx* ctx);
 const char* tritd_last_error(void);

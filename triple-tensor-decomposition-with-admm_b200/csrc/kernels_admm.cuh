@@ -43,12 +43,14 @@ struct AdmmArgs {
     const unsigned* nflags;            // own mailbox: flag row of this exchange
     int rank, nranks;
     unsigned xbase;
-    double* partM;                     // [grid][128][RS]: this CTA's partial of the next X1*F'
+    double* partM;                     // [i-tile][part_slots][128][RS]: this CTA's partial of the next X1*F' at (its tile, its index in the tile)
+    long long* dbg;                    // optional [grid][2] globaltimer stamps: CTA start / end (diagnostics, TRITD_DEBUG_STAMPS)
+    int part_slots;                    // slots per tile (= the largest number of CTAs any tile has)
     const int* cta_tab;                // [grid][3]: i-tile, index within the tile's CTAs, CTAs of that tile
     int n1, n2, n3, RS;
+    int n1s;                           // rows covered by 16-row strips (n1, or the padded leading dimension)
     int n_jc;                          // j-chunks (32 columns)
     int tile_h;                        // rows per i-tile: 16 * (consumer warps used), <= 128
-    int refill_mode;                   // producer scheme: 0 deferred refill (one stage late), 1 immediate, 2 immediate with two producers
 };
 
 // JGP: column groups per stage asked for (1 or 2).  Two-group stages give every warp two independent dependency
@@ -139,7 +141,8 @@ constexpr int kAdmmThreads = 384;
 // MASKED: the opt-in completion variant (tritd_admm_masked_f64): unobserved entries are stored as NaN
 // in D; there O = E = Y_L = Y_O = 0, the residuals do not count and the next target is T' = L (imputation).
 template <int KS, int NT, bool MASKED, int JGP = 2>
-__global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant__ AdmmMaps maps, const AdmmArgs a) {
+__global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant__ AdmmMaps maps_full, const __grid_constant__ AdmmMaps maps_last,
+                                                          const AdmmArgs a) {
     using Cfg = AdmmCfg<KS, NT, JGP>;
     constexpr int PL = Cfg::PL, NB = Cfg::NB, S = Cfg::S, JG = Cfg::JG, kBoxD = Cfg::kBoxD;
     constexpr int kStageD = Cfg::kStageBytes / 8;
@@ -156,97 +159,58 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int it = a.cta_tab[3 * blockIdx.x], x = a.cta_tab[3 * blockIdx.x + 1], gi = a.cta_tab[3 * blockIdx.x + 2];
-    const long V = (long)a.n_jc * a.n3;
-    const long v0 = V * x / gi, v1 = V * (x + 1) / gi;
-    const long nq = (v1 - v0) * SPU;
-    const int nw = a.tile_h >> 4;                                    // consumer warps per tile (= TMA box depth in i_hi)
-    const int nact = min(nw, (a.n1 - it * a.tile_h + 15) >> 4);      // ... of which have rows inside the tensor
-    const int jc0 = (int)(v0 / a.n3), t0 = (int)(v0 - (long)jc0 * a.n3);
+    // The CTAs of an i-tile split its stages (a stage = 8*JG columns of one slice; SPU stages = one unit of 32 columns)
+    // evenly: a contiguous range of stage indices q in [q0, q1), unit = q / SPU, column group = q % SPU.
+    const long Q = (long)a.n_jc * a.n3 * SPU;
+    const long q0 = Q * x / gi, q1 = Q * (x + 1) / gi;
+    const long nq = q1 - q0;
+    const int nwf = a.tile_h >> 4;                                   // 16-row strips (= consumer warps) of a full i-tile
+    const int nact = min(nwf, (a.n1s - it * a.tile_h + 15) >> 4);     // ... of THIS tile (the last tile may have fewer)
+    // TMA box depth in i_hi = strips of this tile: the last tile has its own tensor maps, so that no box ever
+    // reaches past the tensor in i (boxes clipped by the out-of-bounds logic measured ~7 % slower)
+    const int nw = nact;
+    const AdmmMaps& maps = nact < nwf ? maps_last : maps_full;
+    const int i_hi0 = it * nwf;                                      // first strip of this tile
+    const long u0 = q0 / SPU;
+    const int jc0 = (int)(u0 / a.n3), t0 = (int)(u0 - (long)jc0 * a.n3), sg0 = (int)(q0 - u0 * SPU);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], nact); }
         mbar_fence_init();
+        if (a.dbg) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.dbg[2 * blockIdx.x] = t_; }
     }
     __syncthreads();
 
     if (warp >= 8) {
         // ---------------- TMA warpgroup: loads, stores, slot recycling ----------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        if (a.refill_mode != 0) {
-            // Producers: lane 0 of warp 8 (and of warp 9 when refill_mode == 2, alternating stages).  Stage q lives in
-            // slot q % S.  Once the consumers are done with stage q its four boxes go back with one TMA store each;
-            // as soon as those stores have READ shared memory the slot is refilled with stage q + S -- the slot never
-            // idles waiting for the next stage's completion.
-            const int np = a.refill_mode == 2 ? 2 : 1, me = warp - 8;
-            if (me < np && lane == 0 && nq > 0) {
-                tma_prefetch_desc(&maps.D); tma_prefetch_desc(&maps.YL); tma_prefetch_desc(&maps.E);
-                tma_prefetch_desc(&maps.YO); tma_prefetch_desc(&maps.T);
-                auto coords = [&](long q, int& j0, int& tt) {
-                    const long u = v0 + q / SPU;
-                    const int jg = (int)(q - (q / SPU) * SPU);
-                    const int jc = (int)(u / a.n3);
-                    tt = (int)(u - (long)jc * a.n3);
-                    j0 = jc * 32 + jg * (8 * JG);
-                };
-                auto issue_load = [&](long q) {
-                    const int sl = (int)(q % S);
-                    double* st = ring + (size_t)sl * kStageD;
-                    int j0, tt;
-                    coords(q, j0, tt);
-                    mbar_expect_tx(&full[sl], 4 * nw * JG * 1024 + NT * 8 * 8);
-                    tma_load_4d(st, &maps.D, &full[sl], 0, j0, it * nw, tt);
-                    tma_load_4d(st + kBoxD, &maps.YL, &full[sl], 0, j0, it * nw, tt);
-                    tma_load_4d(st + 2 * kBoxD, &maps.E, &full[sl], 0, j0, it * nw, tt);
-                    tma_load_4d(st + 3 * kBoxD, &maps.YO, &full[sl], 0, j0, it * nw, tt);
-                    bulk_load_1d(st + NB * kBoxD, a.C3 + (size_t)tt * a.RS, NT * 8 * 8, &full[sl]);   // C3 row of slice t
-                };
-                if (me == 0) for (long q = 0; q < S && q < nq; ++q) issue_load(q);
-                for (long q = me; q < nq; q += np) {
-                    const int sl = (int)(q % S);
-                    mbar_wait(&done[sl], (uint32_t)((q / S) & 1));
-                    double* st = ring + (size_t)sl * kStageD;
-                    int j0, tt;
-                    coords(q, j0, tt);
-                    tma_store_4d(&maps.T, st, 0, j0, it * nw, tt);
-                    tma_store_4d(&maps.YL, st + kBoxD, 0, j0, it * nw, tt);
-                    tma_store_4d(&maps.E, st + 2 * kBoxD, 0, j0, it * nw, tt);
-                    tma_store_4d(&maps.YO, st + 3 * kBoxD, 0, j0, it * nw, tt);
-                    tma_store_commit();
-                    if (q + S < nq) {
-                        tma_store_wait_read<0>();
-                        issue_load(q + S);
-                    }
-                }
-                tma_store_wait_all<0>();
-            }
-        } else
         if (warp == 8 && lane == 0 && nq > 0) {
             tma_prefetch_desc(&maps.D); tma_prefetch_desc(&maps.YL); tma_prefetch_desc(&maps.E);
             tma_prefetch_desc(&maps.YO); tma_prefetch_desc(&maps.T);
-            int ljc = jc0, lt = t0, ljg = 0, ls = 0;                 // load cursor
+            int ljc = jc0, lt = t0, ljg = sg0, ls = 0;               // load cursor
             auto issue_load = [&]() {
                 double* st = ring + (size_t)ls * kStageD;
                 const int j0 = ljc * 32 + ljg * (8 * JG);
                 mbar_expect_tx(&full[ls], 4 * nw * JG * 1024 + NT * 8 * 8);
-                tma_load_4d(st, &maps.D, &full[ls], 0, j0, it * nw, lt);
-                tma_load_4d(st + kBoxD, &maps.YL, &full[ls], 0, j0, it * nw, lt);
-                tma_load_4d(st + 2 * kBoxD, &maps.E, &full[ls], 0, j0, it * nw, lt);
-                tma_load_4d(st + 3 * kBoxD, &maps.YO, &full[ls], 0, j0, it * nw, lt);
+                tma_load_4d(st, &maps.D, &full[ls], 0, j0, i_hi0, lt);
+                tma_load_4d(st + kBoxD, &maps.YL, &full[ls], 0, j0, i_hi0, lt);
+                tma_load_4d(st + 2 * kBoxD, &maps.E, &full[ls], 0, j0, i_hi0, lt);
+                tma_load_4d(st + 3 * kBoxD, &maps.YO, &full[ls], 0, j0, i_hi0, lt);
                 bulk_load_1d(st + NB * kBoxD, a.C3 + (size_t)lt * a.RS, NT * 8 * 8, &full[ls]);   // C3 row of slice t
                 if (++ljg == SPU) { ljg = 0; if (++lt == a.n3) { lt = 0; ++ljc; } }
                 if (++ls == S) ls = 0;
             };
             long loaded = 0;
             for (; loaded < S && loaded < nq; ++loaded) issue_load();
-            int sjc = jc0, stt = t0, sjg = 0, ss = 0; uint32_t sph = 0;   // store cursor
+            int sjc = jc0, stt = t0, sjg = sg0, ss = 0; uint32_t sph = 0;   // store cursor
             for (long q = 0; q < nq; ++q) {
                 mbar_wait(&done[ss], sph);
                 double* st = ring + (size_t)ss * kStageD;
                 const int j0 = sjc * 32 + sjg * (8 * JG);
-                tma_store_4d(&maps.T, st, 0, j0, it * nw, stt);
-                tma_store_4d(&maps.YL, st + kBoxD, 0, j0, it * nw, stt);
-                tma_store_4d(&maps.E, st + 2 * kBoxD, 0, j0, it * nw, stt);
-                tma_store_4d(&maps.YO, st + 3 * kBoxD, 0, j0, it * nw, stt);
+                tma_store_4d(&maps.T, st, 0, j0, i_hi0, stt);
+                tma_store_4d(&maps.YL, st + kBoxD, 0, j0, i_hi0, stt);
+                tma_store_4d(&maps.E, st + 2 * kBoxD, 0, j0, i_hi0, stt);
+                tma_store_4d(&maps.YO, st + 3 * kBoxD, 0, j0, i_hi0, stt);
                 tma_store_commit();
                 if (++sjg == SPU) { sjg = 0; if (++stt == a.n3) { stt = 0; ++sjc; } }
                 if (++ss == S) { ss = 0; sph ^= 1; }
@@ -291,7 +255,8 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         int jc = jc0, t = t0, cur_jc = -1;
         const int nthr = nact * 32;
 
-        for (long u = v0; u < v1; ++u) {
+        const long u_end = nq > 0 ? (q1 - 1) / SPU + 1 : u0;
+        for (long u = u0; u < u_end; ++u) {
             if (jc != cur_jc) {                    // uniform over the consumers: all walk the same sequence
                 asm volatile("bar.sync 1, %0;" ::"r"(nthr));
                 if (!Cfg::kShareB)
@@ -310,10 +275,12 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
             }
 #pragma unroll
             for (int sg = 0; sg < SPU; ++sg) {
+                const long qa = u * SPU + sg;                // (the first and the last unit of a CTA may be partial)
+                if (qa < q0 || qa >= q1) continue;
                 double* st = ring + (size_t)slot * kStageD;
                 mbar_wait(&full[slot], ph);
                 const double* c3row = st + NB * kBoxD;       // C3(t, :), landed with this stage
-                if (kFoldA && sg == 0) {
+                if (kFoldA && (sg == 0 || qa == q0)) {
 #pragma unroll
                     for (int s = 0; s < KS; ++s) {
                         const double c3 = c3row[4 * s + tig];
@@ -378,7 +345,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
             }
             if (++t == a.n3) { t = 0; ++jc; }
         }
-        double* p = a.partM + (size_t)blockIdx.x * 128 * a.RS;
+        double* p = a.partM + ((size_t)it * a.part_slots + x) * 128 * a.RS;
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -390,7 +357,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         if (lane == 0) { red[warp] = sL; red[8 + warp] = sO; }
       } else {
         // consumer warp whose 16 rows lie entirely outside the tensor: contributes zeros
-        double* p = a.partM + (size_t)blockIdx.x * 128 * a.RS;
+        double* p = a.partM + ((size_t)it * a.part_slots + x) * 128 * a.RS;
         for (int e = lane; e < 16 * a.RS; e += 32) p[(size_t)warp * 16 * a.RS + e] = 0.0;
         if (lane == 0) { red[warp] = 0.0; red[8 + warp] = 0.0; }
       }
@@ -401,6 +368,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         double sl = 0.0, so = 0.0;
         for (int w = 0; w < 8; ++w) { sl += red[w]; so += red[8 + w]; }
         a.norm_part[2 * blockIdx.x] = sl; a.norm_part[2 * blockIdx.x + 1] = so;
+        if (a.dbg) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.dbg[2 * blockIdx.x + 1] = t_; }
         __threadfence();
         s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     }

@@ -39,6 +39,7 @@ struct UpdArgs {
     long tile_stride, row_stride;
     int tile_h;               // rows per tile of the source (INT_MAX when rows are simply row_stride apart)
     int count;                // items per row
+    const int* tile_cnt;      // optional: items per row for the rows of source tile q (else `count` for all rows)
     int wpr;                  // warps that share a row: 1 (8 rows per CTA) or 8 (1 row per CTA)
     const double *S1, *S2;    // [RS][RS] small Grams of the two other factors; S2 may be a stack of ns2 matrices
     int ns2;                  // (the per-rank partials of C3'C3 in the exchange mailbox), summed in order
@@ -446,14 +447,15 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
             const int it = row / a.tile_h, il = row - it * a.tile_h;
             const double* vb = a.v + it * a.tile_stride + il * a.row_stride + lane;
             const double* wb = a.w + lane;
+            const int count = a.tile_cnt ? a.tile_cnt[it] : a.count;
             // items m = sub + wpr * (c + CH * round); the loads of a round are issued together, then accumulated;
             // out-of-range items of the last round read item 0 with weight 0
-            for (int m0 = sub; m0 < a.count; m0 += wpr * CH) {
+            for (int m0 = sub; m0 < count; m0 += wpr * CH) {
                 double v[KPL][CH], w[KPL][CH];
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int m = m0 + c * wpr;
-                    const bool ok = m < a.count;
+                    const bool ok = m < count;
                     const long mv = ok ? m * a.stride : 0, mw = ok ? m * a.wstride : 0;
 #pragma unroll
                     for (int q = 0; q < KPL; ++q) {

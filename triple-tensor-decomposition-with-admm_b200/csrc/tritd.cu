@@ -129,6 +129,11 @@ struct tritd_ctx {
     PFN_encodeTiled encode = nullptr;
     tritd_problem* cached = nullptr;     // device state of the last tritd_admm_f64 call, reused when the shape repeats
     bool cache_poisoned = false;         // the last call failed half-way: the cached state must not be reused
+    // single-process multi-GPU (tritd_create_devices): the context the caller holds is a GROUP of one member
+    // context per device (rank g of `nranks` = number of devices, no NCCL communicator, peer access instead of IPC)
+    bool inproc = false;                 // member of a group
+    std::vector<tritd_ctx*> sub;         // group: the members
+    std::vector<tritd_problem*> gcached; // group: cached member problems of the last tritd_admm_f64 call
     unsigned xepoch = 0;                 // peer exchange: first unused epoch (advances identically on every rank)
 };
 
@@ -208,12 +213,50 @@ extern "C" int tritd_create_rank(int device, int rank, int nranks, const void* n
     return TRITD_OK;
 }
 
+// Single-process multi-GPU context (what a MEX gateway needs: one MATLAB process, several GPUs).  The returned
+// context takes and returns FULL tensors through tritd_admm_f64 / tritd_admm_ex_f64; inside, device g owns the mode-3
+// slab tritd_slab_bounds(n3, ndev, g) and the per-iteration partials travel through the same NVLink peer mailboxes
+// as in the one-process-per-GPU mode, mapped by plain peer access (no IPC, no NCCL).
+extern "C" int tritd_create_devices(const int* devices, int ndev, tritd_ctx** out) {
+    if (!out) return fail(TRITD_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!devices || ndev < 1) return fail(TRITD_ERR_INVALID, "no devices given");
+    if (ndev == 1) return tritd_create(devices[0], out);
+    if (ndev > 8) return fail(TRITD_ERR_UNSUPPORTED, "at most 8 devices per context (got %d)", ndev);
+    for (int a = 0; a < ndev; ++a) for (int b = a + 1; b < ndev; ++b)
+        if (devices[a] == devices[b]) return fail(TRITD_ERR_INVALID, "device %d listed twice", devices[a]);
+    tritd_ctx* g = new tritd_ctx();
+    int s = ctx_common_init(g, devices[0]);
+    for (int q = 0; s == TRITD_OK && q < ndev; ++q) {
+        tritd_ctx* m = new tritd_ctx();
+        g->sub.push_back(m);
+        s = ctx_common_init(m, devices[q]);
+        m->rank = q; m->nranks = ndev; m->inproc = true;
+    }
+    for (int a = 0; s == TRITD_OK && a < ndev; ++a) {
+        cudaSetDevice(devices[a]);
+        for (int b = 0; b < ndev; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+            cudaError_t e = can ? cudaDeviceEnablePeerAccess(devices[b], 0) : cudaErrorPeerAccessUnsupported;
+            if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+            if (e != cudaSuccess) { s = fail(TRITD_ERR_UNSUPPORTED, "no peer access from device %d to device %d (%s)", devices[a], devices[b], cudaGetErrorString(e)); break; }
+        }
+    }
+    if (s != TRITD_OK) { tritd_destroy(g); return s; }
+    *out = g;
+    return TRITD_OK;
+}
+
 extern "C" void tritd_problem_destroy(tritd_problem* p);
 extern "C" int tritd_problem_get_E(tritd_problem* p, double* E_host);
 
 extern "C" int tritd_trim(tritd_ctx* c) {
     if (!c) return fail(TRITD_ERR_INVALID, "ctx is NULL");
     if (c->cached) { tritd_problem_destroy(c->cached); c->cached = nullptr; }
+    for (tritd_problem* q : c->gcached) tritd_problem_destroy(q);
+    c->gcached.clear();
     return TRITD_OK;
 }
 
@@ -221,6 +264,8 @@ extern "C" void tritd_destroy(tritd_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     tritd_trim(c);
+    for (tritd_ctx* m : c->sub) tritd_destroy(m);
+    c->sub.clear();
     if (c->comm) g_nccl.CommDestroy(c->comm);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -228,10 +273,16 @@ extern "C" void tritd_destroy(tritd_ctx* c) {
 
 extern "C" const char* tritd_last_error(void) { return g_err; }
 extern "C" const char* tritd_version(void) { return "tritd-b200 0.1 (sm_100a)"; }
-extern "C" int64_t tritd_launch_count(const tritd_ctx* c) { return c ? c->launches : 0; }
+extern "C" int64_t tritd_launch_count(const tritd_ctx* c) {
+    if (!c) return 0;
+    int64_t n = c->launches;
+    for (const tritd_ctx* m : c->sub) n += m->launches;
+    return n;
+}
 
 extern "C" int tritd_set_stream(tritd_ctx* c, void* cuda_stream) {
     if (!c) return fail(TRITD_ERR_INVALID, "ctx is NULL");
+    if (!c->sub.empty() && cuda_stream) return fail(TRITD_ERR_UNSUPPORTED, "a multi-device context runs on its own per-device streams");
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
     return TRITD_OK;
 }
@@ -276,6 +327,7 @@ struct tritd_problem {
     double* ones = nullptr;              // [64] vector of ones: the weights of a plain-sum RHS source
     double* Minv = nullptr;              // [3][RS][RS] inverses of the three ridge systems (written by k_upd's block 0)
     long long* dbg = nullptr;            // optional globaltimer stamps of k_upd (TRITD_DEBUG_STAMPS=1)
+    long long* dbgA = nullptr;           // ... and of k_admm: [gridA][2] CTA start / end
     unsigned* flags = nullptr;           // [3][4] k_upd hand-shake words (A, B, C) + [12] the k_admm completion ticket
     int *tile0 = nullptr, *tile1 = nullptr;   // first / last i-tile of each k_mttkrp1 CTA
     IterState* st = nullptr;
@@ -284,10 +336,12 @@ struct tritd_problem {
     IterState* poll = nullptr;           // pinned [2]: asynchronous copies of the iteration scalars (tritd_problem_iterate)
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     CUtensorMap mapT, mapA1T;
-    alignas(64) AdmmMaps maps;           // [8 j][16 i] boxes of D, Y_L, E, Y_O, T, O for k_admm
+    alignas(64) AdmmMaps maps;           // boxes [strips of a full i-tile][8*JG j][16 i] of D, Y_L, E, Y_O, T, O for k_admm
+    alignas(64) AdmmMaps mapsLast;       // the same with the depth of the last i-tile (no box reaches past the tensor in i)
     double* partF = nullptr;             // [gridA][128][RS] fused mode-1 partials (next iteration's X1*F')
     int* ctaTab = nullptr;               // per k_admm CTA: (i-tile, index among the tile's CTAs, CTAs of that tile)
-    int refill_mode = 0;                 // k_admm producer scheme (AdmmArgs::refill_mode)
+    int* tileCnt = nullptr;              // CTAs (= partials of X1*F') per i-tile
+    int partSlots = 0;                   // the largest of them: partF is [i-tile][partSlots][128][RS]
     int jgp = 2;                         // k_admm: column groups per stage asked for (AdmmCfg::JGP)
     int gridA = 0, tileH = 128, nitA = 1;  // k_admm: rows per i-tile (16 x consumer warps used) and number of i-tiles
     bool rhsA_ready = false;             // partF holds X1*F' of the current T
@@ -327,8 +381,14 @@ static int dalloc(tritd_problem* p, Tp** ptr, size_t count) {
 static int make_map(tritd_ctx* c, CUtensorMap* map, void* base, int rank, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
     cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char* e = getenv("TRITD_L2PROMO")) {
+        const int v = atoi(e);
+        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    }
     CUresult r = c->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(TRITD_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
     return TRITD_OK;
@@ -411,13 +471,14 @@ static int launch_admm(tritd_problem* p) {
     a.peers = p->xchg ? p->peers : nullptr; a.norm_off = (long)(p->offN + 8 * (size_t)c->rank); a.nflag_off = (long)p->offF;
     a.nslots = p->xchg ? p->box + p->offN : nullptr; a.nflags = p->xchg ? reinterpret_cast<const unsigned*>(p->box + p->offF) : nullptr;
     a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase;
-    a.cta_tab = p->ctaTab;
+    a.n1s = p->n1;
+    a.cta_tab = p->ctaTab; a.part_slots = p->partSlots; a.dbg = p->dbgA;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc; a.tile_h = p->tileH;
-    a.refill_mode = p->refill_mode;
 #define CALL(NT_, KS_)                                                                                                       \
-    if (p->masked) k_admm<KS_, NT_, true, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream>>>(p->maps, a);  \
-    else if (p->jgp == 1) k_admm<KS_, NT_, false, 1><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream>>>(p->maps, a); \
-    else k_admm<KS_, NT_, false, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream>>>(p->maps, a);
+    if (p->masked && p->jgp == 1) k_admm<KS_, NT_, true, 1><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream>>>(p->maps, p->mapsLast, a);  \
+    else if (p->masked) k_admm<KS_, NT_, true, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream>>>(p->maps, p->mapsLast, a);  \
+    else if (p->jgp == 1) k_admm<KS_, NT_, false, 1><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream>>>(p->maps, p->mapsLast, a); \
+    else k_admm<KS_, NT_, false, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream>>>(p->maps, p->mapsLast, a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
     CU_TRY(cudaGetLastError());
@@ -443,8 +504,8 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
     switch (src) {
         case kSrcDirect: a.v = rhs_direct; a.stride = 0; a.count = 1; break;
         case kSrcPartF:
-            a.v = p->partF; a.stride = (long)p->nitA * 128 * RS; a.count = p->gridA / p->nitA;
-            a.tile_h = p->tileH; a.tile_stride = 128 * RS; a.wpr = 8;
+            a.v = p->partF; a.stride = 128 * RS; a.count = p->partSlots; a.tile_cnt = p->tileCnt;
+            a.tile_h = p->tileH; a.tile_stride = (long)p->partSlots * 128 * RS; a.wpr = 8;
             break;
         case kSrcPB: a.v = p->P; a.stride = (long)p->n2 * RS; a.count = p->n3; a.w = p->C3; a.wstride = RS; a.wpr = 8; break;
         case kSrcPC: a.v = p->P; a.stride = RS; a.count = p->n2; a.row_stride = (long)p->n2 * RS; a.w = p->B2; a.wstride = RS; a.wpr = 8; break;
@@ -494,12 +555,9 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
     return TRITD_OK;
 }
 
-// Map every rank's mailbox (CUDA IPC handles exchanged through NCCL once per problem).
-static int setup_exchange(tritd_problem* p) {
-    tritd_ctx* c = p->ctx;
-    const int nr = c->nranks;
-    p->xchg = false;
-    if (nr < 2 || nr > 8 || getenv("TRITD_XCHG_NCCL")) return TRITD_OK;       // NCCL all-reduces instead
+// ---- peer exchange set-up ------------------------------------------------------------------------------------
+static void exchange_layout(tritd_problem* p) {
+    const int nr = p->ctx->nranks;
     const size_t RS = p->RS;
     p->slotA = (size_t)p->n1 * RS + RS * RS;
     p->slotB = (size_t)p->n2 * RS;
@@ -509,14 +567,47 @@ static int setup_exchange(tritd_problem* p) {
     p->fsA = ((size_t)p->n1 + 1 + 7) & ~(size_t)7;   // one flag per k_upd CTA (<= n + 1 CTAs), per rank
     p->fsB = ((size_t)p->n2 + 1 + 7) & ~(size_t)7;
     p->box_doubles = p->offF + (8 + (size_t)nr * (p->fsA + p->fsB)) / 2 + 8;
-    int s = dalloc(p, &p->box, p->box_doubles);
-    if (s != TRITD_OK) return s;
-    CU_TRY(cudaMemsetAsync(p->box, 0, p->box_doubles * 8, c->stream));
+}
+
+// the mailbox bases of all ranks are known: upload them, size the one-wave limit of the exchanging grids
+static int exchange_finish(tritd_problem* p, const std::vector<double*>& bases) {
+    tritd_ctx* c = p->ctx;
+    const int nr = c->nranks;
+    int s;
+    if ((s = dalloc(p, &p->peers, (size_t)nr)) != TRITD_OK) return s;
+    CU_TRY(cudaMemcpy(p->peers, bases.data(), sizeof(double*) * nr, cudaMemcpyHostToDevice));
+    int occ = 0;
+    const size_t sm = upd_smem_bytes(p->RS);
+    switch ((p->R + 15) / 16) {
+        case 1: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<1>, kUpdThreads, sm)); break;
+        case 2: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<2>, kUpdThreads, sm)); break;
+        case 3: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<3>, kUpdThreads, sm)); break;
+        default: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<4>, kUpdThreads, sm)); break;
+    }
+    p->upd_wave = std::max(1, occ * c->num_sms);
+    p->xchg = true;
+    return TRITD_OK;
+}
+
+// One process per GPU: map every rank's mailbox (CUDA IPC handles exchanged through NCCL once per problem).  Every
+// rank takes part in both collectives whatever happened locally: a local failure (allocation, IPC disabled in the
+// container, no peer access) only lowers the vote, and then ALL ranks use the NCCL all-reduces.
+static int setup_exchange(tritd_problem* p) {
+    tritd_ctx* c = p->ctx;
+    const int nr = c->nranks;
+    p->xchg = false;
+    if (nr < 2 || nr > 8 || getenv("TRITD_XCHG_NCCL")) return TRITD_OK;       // NCCL all-reduces instead
+    exchange_layout(p);
+    int ok = 1;
+    if (dalloc(p, &p->box, p->box_doubles) != TRITD_OK) { ok = 0; p->box = nullptr; }
+    if (ok && cudaMemsetAsync(p->box, 0, p->box_doubles * 8, c->stream) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     cudaIpcMemHandle_t mine;
-    CU_TRY(cudaIpcGetMemHandle(&mine, p->box));
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaIpcGetMemHandle(&mine, p->box) != cudaSuccess) { cudaGetLastError(); ok = 0; }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     unsigned char* hdev = nullptr;
-    if ((s = dalloc(p, &hdev, (size_t)64 * (nr + 1))) != TRITD_OK) return s;
+    int s;
+    if ((s = dalloc(p, &hdev, (size_t)64 * (nr + 1))) != TRITD_OK) return s;       // (without this scratch no collective is possible)
     CU_TRY(cudaMemcpyAsync(hdev + 64 * nr, &mine, 64, cudaMemcpyHostToDevice, c->stream));
     NCCL_TRY(g_nccl.AllGather(hdev + 64 * nr, hdev, 64, ncclChar, c->comm, c->stream));
     std::vector<cudaIpcMemHandle_t> all(nr);
@@ -524,8 +615,7 @@ static int setup_exchange(tritd_problem* p) {
     CU_TRY(cudaStreamSynchronize(c->stream));
     std::vector<double*> bases(nr, nullptr);
     p->peer_map.assign(nr, nullptr);
-    int ok = 1;
-    for (int r = 0; r < nr; ++r) {
+    for (int r = 0; ok && r < nr; ++r) {
         if (r == c->rank) { bases[r] = p->box; continue; }
         void* q = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess);
@@ -533,8 +623,6 @@ static int setup_exchange(tritd_problem* p) {
         p->peer_map[r] = q;
         bases[r] = (double*)q;
     }
-    // every rank must take the same path: all-reduce(min) of the success flags; if any rank could not map its peers
-    // (no peer access between the GPUs, IPC disabled in the container) all of them use the NCCL all-reduces
     {
         double* flag = reinterpret_cast<double*>(hdev);           // scratch, no longer needed
         const double mine_ok = ok;
@@ -545,24 +633,30 @@ static int setup_exchange(tritd_problem* p) {
         CU_TRY(cudaStreamSynchronize(c->stream));
         if (all_ok < 0.5) {
             for (void*& q : p->peer_map) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
-            if (c->rank == 0) fprintf(stderr, "libtritd: peer mailboxes unavailable (cudaIpcOpenMemHandle failed on some rank); using NCCL all-reduces\n");
+            if (c->rank == 0) fprintf(stderr, "libtritd: peer mailboxes unavailable (allocation / CUDA IPC / peer access failed on some rank); using NCCL all-reduces\n");
             return TRITD_OK;
         }
     }
-    if ((s = dalloc(p, &p->peers, (size_t)nr)) != TRITD_OK) return s;
-    CU_TRY(cudaMemcpy(p->peers, bases.data(), sizeof(double*) * nr, cudaMemcpyHostToDevice));
-    {
-        int occ = 0;
-        const size_t sm = upd_smem_bytes(p->RS);
-        switch ((p->R + 15) / 16) {
-            case 1: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<1>, kUpdThreads, sm)); break;
-            case 2: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<2>, kUpdThreads, sm)); break;
-            case 3: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<3>, kUpdThreads, sm)); break;
-            default: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<4>, kUpdThreads, sm)); break;
-        }
-        p->upd_wave = std::max(1, occ * c->num_sms);
+    return exchange_finish(p, bases);
+}
+
+// Single process, one member problem per device: the mailboxes are plain device allocations reachable through peer
+// access (enabled by tritd_create_devices).
+static int setup_exchange_inproc(std::vector<tritd_problem*>& ps) {
+    const int nr = (int)ps.size();
+    std::vector<double*> bases(nr, nullptr);
+    for (int r = 0; r < nr; ++r) {
+        tritd_problem* p = ps[r];
+        CU_TRY(cudaSetDevice(p->ctx->device));
+        exchange_layout(p);
+        ST_TRY(dalloc(p, &p->box, p->box_doubles));
+        CU_TRY(cudaMemset(p->box, 0, p->box_doubles * 8));
+        bases[r] = p->box;
     }
-    p->xchg = true;
+    for (int r = 0; r < nr; ++r) {
+        CU_TRY(cudaSetDevice(ps[r]->ctx->device));
+        ST_TRY(exchange_finish(ps[r], bases));
+    }
     return TRITD_OK;
 }
 
@@ -595,6 +689,8 @@ extern "C" int tritd_problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_
 static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int r, int level, tritd_problem** out) {
     if (!c || !out) return fail(TRITD_ERR_INVALID, "ctx/out is NULL");
     *out = nullptr;
+    if (!c->sub.empty() && level == kLevelSolver)
+        return fail(TRITD_ERR_UNSUPPORTED, "the staged solver API needs a single-device context; a multi-device context solves through tritd_admm_f64");
     if (n1 < 1 || n2 < 1 || n3 < 1) return fail(TRITD_ERR_INVALID, "tensor size %lld x %lld x %lld", (long long)n1, (long long)n2, (long long)n3);
     if (r < 1) return fail(TRITD_ERR_INVALID, "triple rank r=%d", r);
     if (r > TRITD_MAX_R) return fail(TRITD_ERR_UNSUPPORTED, "r=%d unsupported (1..%d)", r, TRITD_MAX_R);
@@ -608,13 +704,31 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
     p->RS = (p->R + 7) / 8 * 8;
     const RankCfg rc = rank_cfg(r);
     p->NT = rc.NT; p->KS = rc.KS;
-    p->ld1 = (p->n1 + 15) & ~15;      // padded rows exist (and stay zero): TMA views the rows as (16, n1p/16)
+    // Leading dimension: a multiple of 16 rows (padded rows exist and stay zero: TMA views the rows as (16, ld1/16)),
+    // and DRAM-friendly: measured on B200 (profiles/r02_tile_experiments.md), the streaming kernels run 7-10 % faster when
+    // every column starts on a 2 KB boundary (ld1 a multiple of 256 rows... of 128 rows suffices for 128-row tiles)
+    // than on a 128-byte one, with 256-byte alignment (multiples of 32 rows) in between -- the 1 KB column chunks
+    // of an i-tile then never straddle a DRAM interleave block.  So: round up to 128 rows when that costs <= 1/8
+    // extra memory, else to 32 rows.
+    p->ld1 = (p->n1 + 15) & ~15;
+    {
+        const int l128 = (p->n1 + 127) & ~127, l32 = (p->n1 + 31) & ~31;
+        if ((l128 - p->n1) * 8 <= p->n1) p->ld1 = l128;
+        else if ((l32 - p->n1) * 8 <= p->n1) p->ld1 = l32;
+    }
+    if (const char* e = getenv("TRITD_LD1")) p->ld1 = std::max((p->n1 + 15) & ~15, atoi(e) & ~15);
     p->ldt = p->ld1;
     p->Np = (size_t)p->ld1 * p->n2 * p->n3;
     p->n_it = (p->n1 + 127) / 128;
     p->n_jc = (p->n2 + kBoxRows - 1) / kBoxRows;
+    // k_admm stage size: two 8-column groups per stage, except on small slabs (few stages per CTA), where the finer
+    // one-group stages balance the CTAs better and keep more loads in flight during the short kernel
+    {
+        const int nwr_ = (p->n1 + 15) / 16, nit_ = (nwr_ + 7) / 8;
+        const long stages2 = (long)p->n_jc * p->n3 * 2 / std::max(1, c->num_sms / nit_);
+        p->jgp = stages2 < 24 ? 1 : 2;
+    }
     if (const char* e = getenv("TRITD_ADMM_JG")) p->jgp = atoi(e) == 1 ? 1 : 2;
-    if (const char* e = getenv("TRITD_ADMM_REFILL")) p->refill_mode = atoi(e);
 
     int s = TRITD_OK;
     auto bail = [&](int code) { tritd_problem_destroy(p); return code; };
@@ -668,16 +782,19 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
         }
         cudaMemset(p->flags, 0, (16 + 3 * 64) * 4);
         // k_admm: one CTA per SM.  The i-tiles are as even as 16-row warp strips allow (240 rows -> 128 + 112,
-        // 130 rows -> 80 + 50) and every tile gets the same number of CTAs: a stage costs the same whether
-        // 7 or 8 warps work on it, so equal stage counts finish together.
+        // 130 rows -> 80 + 50) and every tile gets the same number of CTAs.  (Handing a shallower last tile fewer
+        // CTAs in proportion to its measured stage time was tried and lost: 284 vs 267 us on 240 x 320 x 300,
+        // profiles/r02_tile_experiments.md.)
         const int nwr = (p->n1 + 15) / 16;
         p->nitA = (nwr + 7) / 8;
         p->tileH = 16 * ((nwr + p->nitA - 1) / p->nitA);
-        p->gridA = std::max(c->num_sms / p->nitA, 1) * p->nitA;
-        std::vector<int> per(p->nitA, p->gridA / p->nitA);
+        std::vector<int> per(p->nitA, std::max(c->num_sms / p->nitA, 1));
+        p->gridA = 0; p->partSlots = 0;
+        for (int x : per) { p->gridA += x; p->partSlots = std::max(p->partSlots, x); }
         if (solver) {
-            PALLOC(partF, (size_t)p->gridA * 128 * p->RS);
+            PALLOC(partF, (size_t)p->nitA * p->partSlots * 128 * p->RS);
             PALLOC(ctaTab, 3 * p->gridA);
+            PALLOC(tileCnt, p->nitA);
             std::vector<int> tab(3 * p->gridA);
             // interleave the tiles so neighbouring CTAs (launched together) work on the same columns
             std::vector<int> used(p->nitA, 0);
@@ -687,6 +804,8 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
                 q = (q + 1) % p->nitA;
             }
             cudaMemcpy(p->ctaTab, tab.data(), sizeof(int) * 3 * p->gridA, cudaMemcpyHostToDevice);
+            cudaMemcpy(p->tileCnt, per.data(), sizeof(int) * p->nitA, cudaMemcpyHostToDevice);
+            if (getenv("TRITD_DEBUG_STAMPS")) { PALLOC(dbgA, 2 * p->gridA); cudaMemset(p->dbgA, 0, 16 * p->gridA); }
         }
     }
     PALLOC(norm_part, (size_t)2 * std::max(std::max(p->gridF, c->num_sms), 1024));
@@ -706,7 +825,9 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
     CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                 (int)AdmmCfg<KS_, NT_, 1>::kSmem));                                               \
     CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                (int)AdmmCfg<KS_, NT_, 2>::kSmem));
+                                (int)AdmmCfg<KS_, NT_, 2>::kSmem));                                               \
+    CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                (int)AdmmCfg<KS_, NT_, 1>::kSmem));
             TRITD_DISPATCH_R(r, CALL)
 #undef CALL
             const int usm = (int)upd_smem_bytes(p->RS);
@@ -746,17 +867,22 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
             if ((s = q()) != TRITD_OK) return bail(s);
         }
         cuuint32_t box4[4] = {16, (cuuint32_t)(8 * jgroups), (cuuint32_t)(p->tileH / 16), 1};
-        struct { CUtensorMap* m; double* base; } mm[6] = {{&p->maps.D, p->D}, {&p->maps.YL, p->YL}, {&p->maps.E, p->E},
-                                                         {&p->maps.YO, p->YO}, {&p->maps.T, p->T}, {&p->maps.O, p->O}};
-        for (auto& q : mm)
+        const int strips = (p->n1 + 15) / 16, last_depth = strips - (p->nitA - 1) * (p->tileH / 16);
+        cuuint32_t box4l[4] = {16, (cuuint32_t)(8 * jgroups), (cuuint32_t)last_depth, 1};
+        struct { CUtensorMap* m; CUtensorMap* ml; double* base; } mm[6] = {
+            {&p->maps.D, &p->mapsLast.D, p->D}, {&p->maps.YL, &p->mapsLast.YL, p->YL}, {&p->maps.E, &p->mapsLast.E, p->E},
+            {&p->maps.YO, &p->mapsLast.YO, p->YO}, {&p->maps.T, &p->mapsLast.T, p->T}, {&p->maps.O, &p->mapsLast.O, p->O}};
+        for (auto& q : mm) {
             if (solver && (s = make_map(c, q.m, q.base, 4, dims4, str4, box4)) != TRITD_OK) return bail(s);
+            if (solver && (s = make_map(c, q.ml, q.base, 4, dims4, str4, box4l)) != TRITD_OK) return bail(s);
+        }
         cuuint64_t dims2[2] = {(cuuint64_t)p->n1, (cuuint64_t)p->RS};
         cuuint64_t str2[1] = {(cuuint64_t)p->ldt * 8};
         cuuint32_t box2[2] = {16, (cuuint32_t)p->RS};
         if ((s = make_map(c, &p->mapA1T, p->A1T, 2, dims2, str2, box2)) != TRITD_OK) return bail(s);
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) return bail(fail(TRITD_ERR_CUDA, "sync failed"));
-    if (solver && (s = setup_exchange(p)) != TRITD_OK) return bail(s);
+    if (solver && !c->inproc && (s = setup_exchange(p)) != TRITD_OK) return bail(s);      // (groups: setup_exchange_inproc)
     *out = p;
     return TRITD_OK;
 }
@@ -859,8 +985,10 @@ static int upload_factors(tritd_problem* p, const double* A0, const double* B0, 
     return TRITD_OK;
 }
 
-extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const double* A0, const double* B0,
-                                  const double* C0) {
+// tritd_problem_init in three steps so that a group of member problems (one per device) can run the steps in
+// lock-step with a host-side sum in between: (1) local state + partial ||D||^2, (2) the sum over the ranks,
+// (3) normD, the small Grams, epochs.
+static int problem_init_local(tritd_problem* p, const tritd_opts* o, const double* A0, const double* B0, const double* C0) {
     if (!p || !o || !A0 || !B0 || !C0) return fail(TRITD_ERR_INVALID, "NULL argument");
     if (p->level != kLevelSolver) return fail(TRITD_ERR_INVALID, "not a solver problem");
     if (!p->has_D) return fail(TRITD_ERR_INVALID, "tritd_problem_set_D_* must be called first");
@@ -902,26 +1030,40 @@ extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const d
     p->errL = p->errHist + p->hist_cap; p->errO = p->errHist + 2 * (size_t)p->hist_cap;
     CU_TRY(cudaMemsetAsync(p->errHist, 0, (size_t)3 * p->hist_cap * 8, st));
 
-    // normD = norm(D(:))  (:28), all-reduced over the slabs
+    // partial of normD^2 = sum(D(:).^2)  (:28) over this rank's slab
     k_sumsq_part<<<1024, 256, 0, st>>>(p->D, p->Np, p->norm_part, p->masked ? 1 : 0);
     k_sum_pairs<<<1, 256, 0, st>>>(p->norm_part, 1024, p->norms, nullptr);
     CU_TRY(cudaGetLastError());
-    ST_TRY(allreduce_sum(c, p->norms, 2));
-    k_set_normD<<<1, 32, 0, st>>>(p->st, p->norms);
-    c->launches += 3;
+    c->launches += 2;
+    return TRITD_OK;
+}
 
-    // small Grams of the initial factors: SB = B2'B2, SC (partial over local rows) = C3'C3 -- 
+static int problem_init_finish(tritd_problem* p) {
+    tritd_ctx* c = p->ctx;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    k_set_normD<<<1, 32, 0, st>>>(p->st, p->norms);
+    c->launches += 1;
+    // small Grams of the initial factors: SB = B2'B2, SC (partial over local rows) = C3'C3
     ST_TRY(launch_small_gram(p, p->B2, p->n2, p->SB));
     ST_TRY(launch_small_gram(p, p->C3, p->n3, p->bufA + (size_t)p->n1 * p->RS));
     CU_TRY(cudaStreamSynchronize(st));
     p->xbase = c->xepoch;                 // epochs of this solve: xbase + 1 .. xbase + maxIter (same on every rank)
-    c->xepoch += (unsigned)o->maxIter + 1u;
+    c->xepoch += (unsigned)p->opts.maxIter + 1u;
     p->initialized = true;
     p->rhsA_ready = false;
     p->graph_off = getenv("TRITD_NO_GRAPH") != nullptr;
     if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }     // opts (lambda2) are baked into the graph
     p->printed_k = 0;
     return TRITD_OK;
+}
+
+extern "C" int tritd_problem_init(tritd_problem* p, const tritd_opts* o, const double* A0, const double* B0,
+                                  const double* C0) {
+    if (p && p->ctx->inproc) return fail(TRITD_ERR_UNSUPPORTED, "member problems of a multi-device context are driven by tritd_admm_f64");
+    ST_TRY(problem_init_local(p, o, A0, B0, C0));
+    ST_TRY(allreduce_sum(p->ctx, p->norms, 2));         // ||D||^2 over the slabs (one process per GPU: NCCL)
+    return problem_init_finish(p);
 }
 
 // One ADMM iteration, enqueued on the context's stream (triple_decomp_ADMM.m:31-66).
@@ -993,11 +1135,20 @@ extern "C" int tritd_debug_stamps(tritd_problem* p, long long* out48) {
     return TRITD_OK;
 }
 
+// diagnostics: start / end globaltimer stamps of every k_admm CTA of the last launch + its (tile, index, CTAs of tile)
+extern "C" int tritd_debug_admm_stamps(tritd_problem* p, long long* out, int* tab, int cap) {
+    if (!p || !p->dbgA || cap < p->gridA) return fail(TRITD_ERR_INVALID, "no k_admm stamps (TRITD_DEBUG_STAMPS) or buffer too small");
+    CU_TRY(cudaMemcpy(out, p->dbgA, 16 * (size_t)p->gridA, cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(tab, p->ctaTab, 12 * (size_t)p->gridA, cudaMemcpyDeviceToHost));
+    return p->gridA;
+}
+
 // One iteration: the first one (and profiled ones) as plain launches, every later one as a replay of a CUDA graph
 // captured from the very same enqueue_iteration() -- all iteration state lives in device memory, so the graph
 // needs no parameter updates -- which removes the launch gaps between the ~9 small dependent kernels.
 static int run_iteration(tritd_problem* p) {
     tritd_ctx* c = p->ctx;
+    if (c->inproc) CU_TRY(cudaSetDevice(c->device));      // members of a group are driven by one host thread
     if (p->profiling || !p->rhsA_ready || p->graph_off) return enqueue_iteration(p);
     if (!p->graph) {
         const int64_t l0 = c->launches;
@@ -1083,17 +1234,25 @@ static int print_progress(tritd_problem* p) {
     return TRITD_OK;
 }
 
-extern "C" int tritd_problem_iterate(tritd_problem* p, int32_t max_more, int32_t* iters_total) {
-    if (!p || !p->initialized) return fail(TRITD_ERR_INVALID, "problem not initialised");
+// Drive one problem -- or the member problems of a group (one per device, rank order), which iterate in lock-step:
+// their kernels wait for one another through the peer mailboxes, so every iteration is enqueued on all devices
+// before the host ever blocks.
+// The stopping rule lives on the device (later launches of a stopped solve are no-ops).  The host follows it
+// WITHOUT stalling the GPUs: after every batch of <= 10 iterations (the cadence of the reference's progress line)
+// the iteration scalars of rank 0 are copied to a pinned slot, and the host looks at the slot of the batch BEFORE
+// the one it has just enqueued -- the streams never run dry, and with one process per GPU no rank waits for its
+// host while its peers spin in an exchange.  At most one batch of no-op launches follows a stop.  (All ranks take
+// bitwise identical stopping decisions, so rank 0's scalars stand for all.)
+static int iterate_many(const std::vector<tritd_problem*>& ps, int32_t max_more, int32_t* iters_total) {
+    tritd_problem* p = ps[0];
     tritd_ctx* c = p->ctx;
+    for (tritd_problem* q : ps) {
+        if (!q || !q->initialized) return fail(TRITD_ERR_INVALID, "problem not initialised");
+        CU_TRY(cudaSetDevice(q->ctx->device));
+        ST_TRY(fetch_state(q));
+    }
     CU_TRY(cudaSetDevice(c->device));
-    ST_TRY(fetch_state(p));
     int remaining = std::min<int>(max_more, p->opts.maxIter - p->st_host->k);
-    // The stopping rule lives on the device (later launches of a stopped solve are no-ops).  The host follows it
-    // WITHOUT stalling the GPU: after every batch of <= 10 iterations (the cadence of the reference's progress line)
-    // the iteration scalars are copied to a pinned slot, and the host looks at the slot of the batch BEFORE the one
-    // it has just enqueued -- the stream never runs dry, and with several ranks no rank waits for its host while
-    // its peers spin in an exchange.  At most one batch of no-op launches follows a stop.
     if (!p->poll) {
         CU_TRY(cudaMallocHost((void**)&p->poll, 2 * sizeof(IterState)));
         CU_TRY(cudaEventCreateWithFlags(&p->poll_ev[0], cudaEventDisableTiming));
@@ -1112,8 +1271,10 @@ extern "C" int tritd_problem_iterate(tritd_problem* p, int32_t max_more, int32_t
     };
     while (remaining > 0 && !p->st_host->stop) {
         const int batch = std::min(remaining, 10 - k_enq % 10);
-        for (int i = 0; i < batch; ++i) ST_TRY(run_iteration(p));
+        for (int i = 0; i < batch; ++i)
+            for (tritd_problem* q : ps) ST_TRY(run_iteration(q));
         k_enq += batch; remaining -= batch;
+        CU_TRY(cudaSetDevice(c->device));
         CU_TRY(cudaMemcpyAsync(&p->poll[slot], p->st, sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaEventRecord(p->poll_ev[slot], c->stream));
         pending[slot] = true;
@@ -1121,10 +1282,19 @@ extern "C" int tritd_problem_iterate(tritd_problem* p, int32_t max_more, int32_t
         slot ^= 1;
     }
     for (int q = 0; q < 2; ++q) { const int sl = (slot + q) & 1; if (pending[sl]) ST_TRY(look(sl)); }   // oldest first
-    ST_TRY(fetch_state(p));
+    for (size_t g = ps.size(); g-- > 0;) {                 // rank 0 last: its device is current afterwards
+        CU_TRY(cudaSetDevice(ps[g]->ctx->device));
+        ST_TRY(fetch_state(ps[g]));
+    }
     ST_TRY(print_progress(p));
     if (iters_total) *iters_total = p->st_host->k;
     return TRITD_OK;
+}
+
+extern "C" int tritd_problem_iterate(tritd_problem* p, int32_t max_more, int32_t* iters_total) {
+    if (!p || !p->initialized) return fail(TRITD_ERR_INVALID, "problem not initialised");
+    if (p->ctx->inproc) return fail(TRITD_ERR_UNSUPPORTED, "member problems of a multi-device context are driven by tritd_admm_f64");
+    return iterate_many(std::vector<tritd_problem*>{p}, max_more, iters_total);
 }
 
 // O is not written inside the loop (see k_recover_O): materialise it into p->O on demand.
@@ -1248,10 +1418,16 @@ static int agree_on_cache_hit(tritd_ctx* c, bool local_hit, bool* all_hit) {
     return s;
 }
 
+static int admm_group(tritd_ctx* G, const double* D_host, const unsigned char* mask_host, int64_t n1, int64_t n2, int64_t n3, int r,
+                      const tritd_opts* o, const double* A0, const double* B0, const double* C0, double* A, double* B, double* C,
+                      double* O, double* E, double* L, double* errHist, int32_t* iters_out, tritd_timing* tm);
+
 static int admm_impl(tritd_ctx* c, const double* D_host, const unsigned char* mask_host, int64_t n1, int64_t n2, int64_t n3, int r,
                      const tritd_opts* o, const double* A0, const double* B0, const double* C0, double* A, double* B, double* C,
                      double* O, double* E, double* L, double* errHist, int32_t* iters_out, tritd_timing* tm) {
     if (!c || !D_host || !o || !A0 || !B0 || !C0 || !errHist) return fail(TRITD_ERR_INVALID, "NULL argument");
+    if (!c->sub.empty())
+        return admm_group(c, D_host, mask_host, n1, n2, n3, r, o, A0, B0, C0, A, B, C, O, E, L, errHist, iters_out, tm);
     const double t_begin = now_ms();
     const int64_t launches0 = c->launches;
     // device state (6 N-sized arrays, tensor maps, the captured iteration graph) is kept in the context and
@@ -1298,6 +1474,96 @@ static int admm_impl(tritd_ctx* c, const double* D_host, const unsigned char* ma
     if (tm) {
         tm->h2d_ms = t_h2d; tm->iterate_ms = it_ms; tm->d2h_ms = t_d2h; tm->total_ms = now_ms() - t_begin;
         tm->iters = k; tm->launches = (int32_t)(c->launches - launches0);
+    }
+    return TRITD_OK;
+}
+
+// The one-call solver on a single-process multi-GPU context (tritd_create_devices): FULL tensors in and out; device g
+// owns the mode-3 slab [t0_g, t1_g); A and B come back from device 0 (the replicas are bitwise equal), C / O / E / L
+// slab by slab.
+static int admm_group(tritd_ctx* G, const double* D_host, const unsigned char* mask_host, int64_t n1, int64_t n2, int64_t n3, int r,
+                      const tritd_opts* o, const double* A0, const double* B0, const double* C0, double* A, double* B, double* C,
+                      double* O, double* E, double* L, double* errHist, int32_t* iters_out, tritd_timing* tm) {
+    if (!D_host || !o || !A0 || !B0 || !C0 || !errHist) return fail(TRITD_ERR_INVALID, "NULL argument");
+    const int nd = (int)G->sub.size();
+    if (n1 < 1 || n2 < 1 || n3 < nd) return fail(TRITD_ERR_INVALID, "tensor %lld x %lld x %lld cannot be split into %d mode-3 slabs", (long long)n1, (long long)n2, (long long)n3, nd);
+    const double t_begin = now_ms();
+    const int64_t launches0 = tritd_launch_count(G);
+    std::vector<int64_t> t0(nd), t1(nd);
+    for (int g = 0; g < nd; ++g) ST_TRY(tritd_slab_bounds(n3, nd, g, &t0[g], &t1[g]));
+    std::vector<tritd_problem*>& ps = G->gcached;
+    bool hit = (int)ps.size() == nd && !G->cache_poisoned;
+    for (int g = 0; hit && g < nd; ++g) hit = ps[g]->n1 == n1 && ps[g]->n2 == n2 && ps[g]->n3 == t1[g] - t0[g] && ps[g]->r == r;
+    auto fail_out = [&](int code) { tritd_trim(G); return code; };
+    if (!hit) {
+        tritd_trim(G);
+        G->cache_poisoned = false;
+        for (int g = 0; g < nd; ++g) {
+            tritd_problem* q = nullptr;
+            int s = problem_create(G->sub[g], n1, n2, t1[g] - t0[g], r, kLevelSolver, &q);
+            if (s != TRITD_OK) return fail_out(s);
+            ps.push_back(q);
+        }
+        int s = setup_exchange_inproc(ps);
+        if (s != TRITD_OK) return fail_out(s);
+    }
+    const size_t slice = (size_t)n1 * n2, R = (size_t)r * r;
+    int s;
+    double tq = now_ms();
+    for (int g = 0; g < nd; ++g) {
+        if ((s = tritd_problem_set_D_host(ps[g], D_host + slice * t0[g])) != TRITD_OK) return fail_out(s);
+        if (mask_host && (s = tritd_problem_set_mask_host(ps[g], mask_host + slice * t0[g])) != TRITD_OK) return fail_out(s);
+    }
+    for (int g = 0; g < nd; ++g)
+        if ((s = problem_init_local(ps[g], o, A0, B0, C0 + R * t0[g])) != TRITD_OK) return fail_out(s);
+    {   // ||D||^2: the slabs' partial sums added on the host in rank order, the total handed to every device
+        double tot = 0.0;
+        for (int g = 0; g < nd; ++g) {
+            double part[2];
+            cudaSetDevice(ps[g]->ctx->device);
+            if (cudaMemcpyAsync(part, ps[g]->norms, 16, cudaMemcpyDeviceToHost, ps[g]->ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ps[g]->ctx->stream) != cudaSuccess)
+                return fail_out(fail(TRITD_ERR_CUDA, "normD partial of device %d: %s", ps[g]->ctx->device, cudaGetErrorString(cudaGetLastError())));
+            tot += part[0];
+        }
+        for (int g = 0; g < nd; ++g) {
+            const double both[2] = {tot, 0.0};
+            cudaSetDevice(ps[g]->ctx->device);
+            if (cudaMemcpyAsync(ps[g]->norms, both, 16, cudaMemcpyHostToDevice, ps[g]->ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ps[g]->ctx->stream) != cudaSuccess)
+                return fail_out(fail(TRITD_ERR_CUDA, "normD upload failed"));
+        }
+    }
+    for (int g = 0; g < nd; ++g)
+        if ((s = problem_init_finish(ps[g])) != TRITD_OK) return fail_out(s);
+    const double t_h2d = now_ms() - tq;
+
+    cudaSetDevice(ps[0]->ctx->device);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, ps[0]->ctx->stream);
+    int32_t k = 0;
+    s = iterate_many(ps, o->maxIter, &k);
+    cudaSetDevice(ps[0]->ctx->device);
+    cudaEventRecord(e1, ps[0]->ctx->stream);
+    cudaEventSynchronize(e1);
+    float it_ms = 0.f;
+    cudaEventElapsedTime(&it_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (s != TRITD_OK) return fail_out(s);
+
+    tq = now_ms();
+    for (int g = 0; g < nd && s == TRITD_OK; ++g) {
+        s = tritd_problem_get(ps[g], g == 0 ? A : nullptr, g == 0 ? B : nullptr, C ? C + R * t0[g] : nullptr, O ? O + slice * t0[g] : nullptr,
+                              L ? L + slice * t0[g] : nullptr, g == 0 ? errHist : nullptr, nullptr, nullptr, &k);
+        if (s == TRITD_OK && E) s = tritd_problem_get_E(ps[g], E + slice * t0[g]);
+    }
+    const double t_d2h = now_ms() - tq;
+    if (s != TRITD_OK) return fail_out(s);
+    if (iters_out) *iters_out = k;
+    if (tm) {
+        tm->h2d_ms = t_h2d; tm->iterate_ms = it_ms; tm->d2h_ms = t_d2h; tm->total_ms = now_ms() - t_begin;
+        tm->iters = k; tm->launches = (int32_t)(tritd_launch_count(G) - launches0);
     }
     return TRITD_OK;
 }

@@ -6,7 +6,8 @@
  * validates arguments, draws the initial factors with MATLAB's own randn in the reference's
  * order (:23 -- A, B, C -- so rng(0) in the caller gives the reference's factors) and moves
  * mxArrays in and out.  Optional extension fields of opts: A0, B0, C0 (injected
- * initial factors), device (CUDA ordinal), mask (logical n1 x n2 x n3, true = observed: the completion
+ * initial factors), device (CUDA ordinal) / devices (list of ordinals) / ngpu (use devices 0..ngpu-1: one MATLAB
+ * process drives several GPUs, D sharded along mode 3), mask (logical n1 x n2 x n3, true = observed: the completion
  * variant, see triple_ADMM_masked.c).  A sixth output, when requested, is L = triple_product(A,B,C), a seventh is
  * E ("O,E : sparse components (clone E)", triple_decomp_ADMM.m:12).  The progress line of opts.disp (:60-62) is
  * printed through mexPrintf.
@@ -94,8 +95,24 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (!C0) { C0m = randn3(r, r, n3); C0 = mxGetPr(C0m); }
 
     if (!g_ctx) {
+        /* opts.devices = [0 1 2 3] (CUDA ordinals) or opts.ngpu = 4 (devices 0..3) or opts.device = 2; default: device 0.
+         * Several devices: one MATLAB process drives them all (tritd_create_devices), D is sharded along mode 3. */
+        int devs[8], nd = 0;
+        const mxArray* dl = mxGetField(om, 0, "devices");
+        const mxArray* ng = mxGetField(om, 0, "ngpu");
         const mxArray* dv = mxGetField(om, 0, "device");
-        if (tritd_create(dv ? (int)mxGetScalar(dv) : 0, &g_ctx) != TRITD_OK)
+        if (dl && !mxIsEmpty(dl)) {
+            if (!mxIsDouble(dl) || mxGetNumberOfElements(dl) > 8) mexErrMsgIdAndTxt("tritd:opts", "opts.devices must list at most 8 device ordinals.");
+            for (nd = 0; nd < (int)mxGetNumberOfElements(dl); ++nd) devs[nd] = (int)mxGetPr(dl)[nd];
+        } else if (ng && !mxIsEmpty(ng)) {
+            const int n = (int)mxGetScalar(ng);
+            if (n < 1 || n > 8) mexErrMsgIdAndTxt("tritd:opts", "opts.ngpu must be 1..8.");
+            for (nd = 0; nd < n; ++nd) devs[nd] = nd;
+        } else {
+            devs[0] = dv ? (int)mxGetScalar(dv) : 0;
+            nd = 1;
+        }
+        if (tritd_create_devices(devs, nd, &g_ctx) != TRITD_OK)
             mexErrMsgIdAndTxt("tritd:cuda", "%s", tritd_last_error());
         mexLock();
         mexAtExit(at_exit);

@@ -59,6 +59,7 @@ SYMBOLS = {
     "tritd_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "tritd_nccl_unique_id": (C.c_int, [_vp]),
     "tritd_create_rank": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, C.POINTER(_vp)]),
+    "tritd_create_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_vp)]),
     "tritd_destroy": (None, [_vp]),
     "tritd_last_error": (C.c_char_p, []),
     "tritd_version": (C.c_char_p, []),
@@ -173,6 +174,19 @@ class Context:
             _check(lib.tritd_create_rank(int(device), int(rank), int(nranks), buf, C.byref(h)))
         self._h = h
         self.device, self.rank, self.nranks = device, rank, nranks
+
+    @classmethod
+    def from_devices(cls, devices):
+        """Single-process multi-GPU context (tritd_create_devices): full tensors in and out of triple_decomp_ADMM."""
+        devices = [int(d) for d in devices]
+        self = cls.__new__(cls)
+        h = _vp()
+        arr = (C.c_int * len(devices))(*devices)
+        _check(load_library().tritd_create_devices(arr, len(devices), C.byref(h)))
+        self._h = h
+        self.device, self.rank, self.nranks = devices[0], 0, 1
+        self.devices = devices
+        return self
 
     @staticmethod
     def nccl_unique_id() -> bytes:
