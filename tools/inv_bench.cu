@@ -7,7 +7,16 @@ using namespace tritd;
 template <int PQ> __global__ void k_inv_test(const double* S1, const double* S2, int R, int RS, double* out, long long* cyc) {
     __shared__ double sm[256];
     long long t0 = clock64();
-    bool bad = invert_ridge_system<PQ>(S1, S2, 1e-3, R, RS, out, sm);
+    int bad = invert_ridge_system<PQ>(S1, S2, 1, 0, 1e-3, R, RS, out, sm);
+    long long t1 = clock64();
+    if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = bad; }
+}
+__device__ long long g_tdbg[128];
+template <int NBMAX> __global__ void k_inv_blocked(const double* S1, const double* S2, int R, int RS, double* out, long long* cyc) {
+    extern __shared__ double smb[];
+    long long t0 = clock64();
+    if (threadIdx.x == 0) g_tdbg[127] = t0;
+    int bad = invert_ridge_blocked<NBMAX>(S1, S2, 1, 0, 1e-3, R, RS, out, smb, g_tdbg);
     long long t1 = clock64();
     if (threadIdx.x == 0) { cyc[0] = t1 - t0; cyc[1] = bad; }
 }
@@ -33,6 +42,8 @@ int main() {
     for (int i = 0; i < RS; ++i) for (int j = 0; j < RS; ++j) h[i * RS + j] = (i == j) ? 3.0 : 1.0 / (1 + abs(i - j));
     double *S1, *S2, *out; long long* cyc;
     cudaMalloc(&S1, RS * RS * 8); cudaMalloc(&S2, RS * RS * 8); cudaMalloc(&out, RS * RS * 8); cudaMalloc(&cyc, 64);
+    double* out2; cudaMalloc(&out2, RS * RS * 8);
+    cudaFuncSetAttribute(k_inv_blocked<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaMemcpy(S1, h.data(), RS * RS * 8, cudaMemcpyHostToDevice); cudaMemcpy(S2, h.data(), RS * RS * 8, cudaMemcpyHostToDevice);
     long long c[8];
     for (int rep = 0; rep < 3; ++rep)
@@ -43,6 +54,23 @@ int main() {
         else k_inv_test<4><<<1, 256>>>(S1, S2, R, RS, out, cyc);
         cudaMemcpy(c, cyc, 16, cudaMemcpyDeviceToHost);
         if (rep == 2) printf("R=%d: %lld cycles (%.0f / step) bad=%lld\n", R, c[0], (double)c[0] / R, c[1]);
+        cudaMemset(out2, 0, RS * RS * 8);
+        if (R <= 16) k_inv_blocked<2><<<1, 256, ridge_blocked_smem_doubles(R) * 8>>>(S1, S2, R, RS, out2, cyc);
+        else if (R <= 32) k_inv_blocked<4><<<1, 256, ridge_blocked_smem_doubles(R) * 8>>>(S1, S2, R, RS, out2, cyc);
+        else if (R <= 48) k_inv_blocked<6><<<1, 256, ridge_blocked_smem_doubles(R) * 8>>>(S1, S2, R, RS, out2, cyc);
+        else k_inv_blocked<8><<<1, 256, ridge_blocked_smem_doubles(R) * 8>>>(S1, S2, R, RS, out2, cyc);
+        cudaMemcpy(c, cyc, 16, cudaMemcpyDeviceToHost);
+        if (rep == 2) {
+            std::vector<double> a(RS * RS), b(RS * RS);
+            cudaMemcpy(a.data(), out, RS * RS * 8, cudaMemcpyDeviceToHost); cudaMemcpy(b.data(), out2, RS * RS * 8, cudaMemcpyDeviceToHost);
+            double md = 0, mx = 0;
+            for (int i = 0; i < R; ++i) for (int j = 0; j < R; ++j) { md = fmax(md, fabs(a[i * RS + j] - b[i * RS + j])); mx = fmax(mx, fabs(a[i * RS + j])); }
+            long long td[128]; cudaMemcpyFromSymbol(td, g_tdbg, sizeof(td));
+            printf("   stamps (cycles since start; warp0 / warp1): ");
+            for (int sl = 0; sl < 10; ++sl) printf("[%d] %lld/%lld ", sl, td[sl * 8] - td[127], td[sl * 8 + 1] - td[127]);
+            printf("\n");
+            printf("   blocked: %lld cycles (%.0f / block step) cond=%lld  max|scalar - blocked| = %.3e (max |inv| %.3e)  %s\n", c[0], (double)c[0] / ((R + 7) / 8), c[1], md, mx, cudaGetErrorString(cudaGetLastError()));
+        }
     }
     for (int t : {32, 256, 1024}) {
         k_lat<<<1, t>>>(out, cyc, 1000);

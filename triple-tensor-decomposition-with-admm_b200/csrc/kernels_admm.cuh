@@ -23,6 +23,7 @@
 #include "kernels_contract.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_xchg.cuh"
+#include "kernels_update.cuh"
 
 namespace tritd {
 
@@ -44,6 +45,9 @@ struct AdmmArgs {
     int rank, nranks;
     unsigned xbase;
     double* partM;                     // [i-tile][part_slots][128][RS]: this CTA's partial of the next X1*F' at (its tile, its index in the tile)
+    RidgeJob inv;                      // update A's ridge inverse of the NEXT iteration: CTA 0 computes it before its streaming work
+    int inv_stages;                    // ... and gets this many stages less than its siblings in return
+    int R;                             // r^2
     long long* dbg;                    // optional [grid][2] globaltimer stamps: CTA start / end (diagnostics, TRITD_DEBUG_STAMPS)
     int part_slots;                    // slots per tile (= the largest number of CTAs any tile has)
     const int* cta_tab;                // [grid][3]: i-tile, index within the tile's CTAs, CTAs of that tile
@@ -149,6 +153,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
     constexpr int SPU = 4 / JG;           // stages per unit (32 columns of one slice)
     constexpr bool kFoldA = KS <= 8;      // fold C3[t,:] into the A fragments once per slice (else into B per use)
     if (a.st->stop) return;
+    const int k_start = a.st->k;          // iteration index of this launch (the last CTA advances it at the very end)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);              // [S][NB boxes + C3 row]
     double* B2s = ring + (size_t)S * kStageD;                        // [32 j][PL]      B-operand of L
@@ -161,8 +166,11 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
     const int it = a.cta_tab[3 * blockIdx.x], x = a.cta_tab[3 * blockIdx.x + 1], gi = a.cta_tab[3 * blockIdx.x + 2];
     // The CTAs of an i-tile split its stages (a stage = 8*JG columns of one slice; SPU stages = one unit of 32 columns)
     // evenly: a contiguous range of stage indices q in [q0, q1), unit = q / SPU, column group = q % SPU.
+    // CTA 0 additionally inverts the ridge system of the next update A (below), which takes about as long as
+    // `inv_stages` stages: the split of ITS tile treats that job like stages in front of CTA 0's range.
     const long Q = (long)a.n_jc * a.n3 * SPU;
-    const long q0 = Q * x / gi, q1 = Q * (x + 1) / gi;
+    const long dq = (a.inv.enable && it == a.cta_tab[0]) ? a.inv_stages : 0;
+    const long q0 = max(0L, (Q + dq) * x / gi - dq), q1 = max(0L, (Q + dq) * (x + 1) / gi - dq);
     const long nq = q1 - q0;
     const int nwf = a.tile_h >> 4;                                   // 16-row strips (= consumer warps) of a full i-tile
     const int nact = min(nwf, (a.n1s - it * a.tile_h + 15) >> 4);     // ... of THIS tile (the last tile may have fewer)
@@ -224,6 +232,14 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         }
     } else {
       asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+      if (a.inv.enable && blockIdx.x == 0) {
+        // The ridge system of the NEXT update A (S_B o S_C + lambda2 I, both final since update C) is inverted here, by
+        // the eight consumer warps of CTA 0 before they start on their (correspondingly shorter) range of stages: the
+        // inverse is ready long before update A launches, which then applies it the moment its right-hand sides are
+        // summed.  Scratch: the factor-chunk buffer (not loaded yet).  An ill-conditioned system is left to update A.
+        ridge_job_run<(NT + 1) / 2, 3, false>(a.inv, a.st, k_start + 1, a.R, a.RS, B2s);
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
       if (warp < nact) {
         // ---------------- consumers ----------------
         const int g = lane >> 2, tig = lane & 3;

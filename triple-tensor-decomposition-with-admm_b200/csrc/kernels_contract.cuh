@@ -17,6 +17,7 @@
 // zero padded.
 #pragma once
 #include "common.cuh"
+#include "kernels_update.cuh"
 
 namespace tritd {
 
@@ -212,6 +213,10 @@ struct PpassArgs {
     int n_jb;           // ceil(n2 / 32)
     long n_rb;          // n3 * n_jb
     long units;         // ceil(n_rb / 8) (grid sizing)
+    RidgeJob inv;       // update B's ridge inverse (S_A o S_C + lambda2 I, S_A final since update A): CTA 0, before its row blocks
+    int inv_rb;         // ... and CTA 0 gets this many row blocks less in return
+    IterState* st;
+    int R;
 };
 
 constexpr int kPW = 16;           // k_ppass consumer warps: two per row block (m-tiles 0,1 / 2,3), 4 per scheduler
@@ -231,8 +236,9 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
     const int nkc = (a.n1 + 15) >> 4;
     // each CTA owns a contiguous range of row blocks, balanced to ONE row block (the DMMA pipe is the limit, so
     // time follows the row-block count, not the number of 8-block passes); a pass = 8 consecutive row blocks
-    const long rbA = a.n_rb * blockIdx.x / gridDim.x;
-    const long rbB = a.n_rb * (blockIdx.x + 1) / gridDim.x;
+    const long drb = a.inv.enable ? a.inv_rb : 0;       // CTA 0's ridge-inverse job counts like drb row blocks in front of its range
+    const long rbA = max(0L, (a.n_rb + drb) * blockIdx.x / gridDim.x - drb);
+    const long rbB = max(0L, (a.n_rb + drb) * (blockIdx.x + 1) / gridDim.x - drb);
     const long npass = (rbB - rbA + kCW - 1) / kCW;
 
     if (threadIdx.x == 0) {
@@ -266,6 +272,11 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
         return;
     }
 
+    if (a.inv.enable && blockIdx.x == 0 && threadIdx.x < 256) {
+        // update B's ridge system (see k_admm: same scheme), consumer warps 0..7 of CTA 0 before their first pass
+        __shared__ double inv_scratch[256];
+        ridge_job_run<(NT + 1) / 2, 3, false>(a.inv, a.st, a.st->k, a.R, a.RS, inv_scratch);
+    }
     int s = 0; uint32_t ph = 0;
     const int rg = rho8(g);
     const int bw = warp & (kCW - 1), mh = warp >> 3;      // row block of the pass, half of its 32 rows (m-tiles 2mh, 2mh+1)

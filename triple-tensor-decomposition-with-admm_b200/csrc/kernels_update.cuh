@@ -45,15 +45,24 @@ struct UpdArgs {
     int ns2;                  // (the per-rank partials of C3'C3 in the exchange mailbox), summed in order
     long s2stride;
     // N>1 peer exchange inside the kernel (xmerge): every row CTA writes its reduced rows into this rank's slot of every
-    // rank's mailbox (block 0 adds `extra_n` doubles, the local C3'C3, behind them), raises its flag [rank][cta]
-    // everywhere, waits for the flags [r][cta] of all ranks in the own mailbox and sums the slots in rank order.
+    // rank's mailbox, raises its flag [rank][cta] everywhere, waits for the flags [r][cta] of all ranks in the own
+    // mailbox and sums the slots in rank order.
+    // C3'C3 (the one small Gram with per-rank partials) travels EARLY: update C pushes its local partial from the end
+    // of its Gram phase (sc_push) into a parity-double-buffered region of every mailbox, so that the ridge inverses
+    // of the next iteration's updates A and B (sc_wait: S2 = the stack of the ranks' partials) start at once instead of
+    // after an exchange of their own.
     int xmerge;
+    int sc_wait, sc_push;     // this launch consumes / produces the exchanged C3'C3
+    long s2par_stride;        // doubles between the two parity buffers of the S2 stack
+    const unsigned* sc_flags; // own mailbox: [2 parities][8] epochs of the C3'C3 pushes
+    long sc_off, sc_flag_off; // offsets inside a mailbox: doubles to the C3'C3 region, u32 index of its flags (from the flag area)
+    long flag_area_off;       // doubles from the mailbox base to the flag area
+    int gram_cap;             // CTAs that may take part (and spin) in the Gram phase
+    int inv_here;             // block 0 inverts the ridge system (else an earlier kernel published it and raised flags[0])
     long fstride;             // flags per rank in the flag block of this exchange (>= grid size)
     double* const* peers;     // [nranks] mailbox bases
     long push_off, pflag_off; // offsets in doubles inside a mailbox: this rank's slot / the flag row of the exchange
-    const double* extra_src;
-    long extra_off;
-    int extra_n, rank, nranks;
+    int rank, nranks;
     const unsigned* xflags;   // flag row of the exchange in the own mailbox
     const double* xbox;       // slot 0 of the exchange region in the own mailbox
     long xslot;               // slot stride
@@ -68,7 +77,7 @@ struct UpdArgs {
     unsigned* gram_cnt;       // [<= 64] per entry-slice arrival counters (zero between launches)
     int gr;                   // row slices of the Gram phase
     IterState* st;
-    unsigned* flags;          // [0] inverse published, [1] row CTAs done, [2] Gram CTAs done; all zero between launches
+    unsigned* flags;          // [0] inverse published, [1] row CTAs done, [2] Gram CTAs done, [3] pre-computation punted; all zero between launches
     int apply;
     int n, R, RS, ldt;
     long long* dbg;           // optional [16] globaltimer stamps (diagnostics; TRITD_DEBUG_STAMPS)
@@ -115,7 +124,13 @@ __device__ __forceinline__ double rcp_newton(double x) {
 // max(size) * eps(sigma_max) may truncate: the caller runs pinv_jacobi instead), 2 in the threads whose entries of the
 // system itself are NaN / Inf (the caller votes).
 constexpr int kRidgeOk = 0, kRidgeIll = 1, kRidgeNonFinite = 2;
-template <int PQ>
+// BAR = 0: the calling CTA has exactly 256 threads (__syncthreads); BAR > 0: the first 256 threads of a larger CTA call
+// it and synchronise on named barrier BAR.
+template <int BAR> __device__ __forceinline__ void bar256() {
+    if (BAR == 0) __syncthreads();
+    else asm volatile("bar.sync %0, 256;" ::"n"(BAR) : "memory");
+}
+template <int PQ, int BAR = 0>
 __device__ int invert_ridge_system(const double* S1, const double* S2, int ns2, long s2stride, double alpha, int R, int RS, double* out,
                                     double* sm /* >= 256 doubles */, long long* dbg = nullptr) {
     double* prow = sm;        // [2][64]
@@ -163,7 +178,7 @@ __device__ int invert_ridge_system(const double* S1, const double* S2, int ns2, 
                 gq[p][q] = v;
             }
     }
-    __syncthreads();
+    bar256<BAR>();
     if (dbg && threadIdx.x == 0) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); dbg[13] = t_; }
     bool bad = false;
     double pmin = 1.7976931348623157e308, pmax = 0.0;
@@ -223,7 +238,7 @@ __device__ int invert_ridge_system(const double* S1, const double* S2, int ns2, 
                     for (int p = 0; p < PQ; ++p) pcn[ty + 16 * p] = gq[p][NP];
                 }
             }
-            __syncthreads();
+            bar256<BAR>();
         }
     }
 #pragma unroll
@@ -244,14 +259,16 @@ __device__ int invert_ridge_system(const double* S1, const double* S2, int ns2, 
 // pinv = V diag(1/lam_k if |lam_k| > R * eps(max|lam|) else 0) V'.  Only block 0 runs this, and only when
 // invert_ridge_system reported kRidgeIll (rank-deficient or nearly so: duplicated factor columns, lambda2 = 0, the
 // 1e-9 ridge of update_C against sigma_max > ~1e5): a rare path, ~1 ms.  Returns the number of truncated values.
+template <int BAR = 0>
 __device__ int pinv_jacobi(const double* S1, const double* S2, int ns2, long s2stride, double alpha, int R, int RS, double* out,
                            double* sm /* >= 2*R*(R+1) + 3*64 doubles */) {
     const int tid = threadIdx.x, P = R + 1;
+    constexpr int NTH = 256;
     double* G = sm;                       // [R][P]
     double* V = sm + R * P;               // [R][P]
     double* cs = V + R * P;               // [32 pairs][2] rotations of the round, then [64] weights
     __shared__ int s_rot, s_trunc;
-    for (int e = tid; e < R * R; e += blockDim.x) {
+    for (int e = tid; e < R * R; e += NTH) {
         const int i = e / R, j = e - i * R;
         double t2 = S2[i * RS + j];
         for (int u = 1; u < ns2; ++u) t2 += S2[u * s2stride + i * RS + j];
@@ -260,11 +277,11 @@ __device__ int pinv_jacobi(const double* S1, const double* S2, int ns2, long s2s
         G[i * P + j] = v;
         V[i * P + j] = i == j ? 1.0 : 0.0;
     }
-    __syncthreads();
+    bar256<BAR>();
     const int n = (R + 1) & ~1, half = n >> 1;       // players of the round-robin tournament (a dummy one when R is odd)
     for (int sweep = 0; sweep < 30; ++sweep) {
         if (tid == 0) s_rot = 0;
-        __syncthreads();
+        bar256<BAR>();
         for (int rd = 0; rd < n - 1; ++rd) {
             // pair q of round rd: (n-1, rd) for q = 0, else ((rd+q) mod (n-1), (rd-q) mod (n-1))
             if (tid < half) {
@@ -283,9 +300,9 @@ __device__ int pinv_jacobi(const double* S1, const double* S2, int ns2, long s2s
                 }
                 cs[2 * tid] = c; cs[2 * tid + 1] = sn;
             }
-            __syncthreads();
+            bar256<BAR>();
             // columns p,q of G and V for every row: (x_p, x_q) <- (c x_p - s x_q, s x_p + c x_q)
-            for (int e = tid; e < R * half; e += blockDim.x) {
+            for (int e = tid; e < R * half; e += NTH) {
                 const int i = e / half, pr = e - i * half;
                 int p_ = pr == 0 ? n - 1 : (rd + pr) % (n - 1), q_ = pr == 0 ? rd : (rd - pr + (n - 1)) % (n - 1);
                 if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
@@ -297,9 +314,9 @@ __device__ int pinv_jacobi(const double* S1, const double* S2, int ns2, long s2s
                     V[i * P + p_] = c * vp - sn * vq; V[i * P + q_] = sn * vp + c * vq;
                 }
             }
-            __syncthreads();
+            bar256<BAR>();
             // rows p,q of G for every column
-            for (int e = tid; e < R * half; e += blockDim.x) {
+            for (int e = tid; e < R * half; e += NTH) {
                 const int j = e / half, pr = e - j * half;
                 int p_ = pr == 0 ? n - 1 : (rd + pr) % (n - 1), q_ = pr == 0 ? rd : (rd - pr + (n - 1)) % (n - 1);
                 if (p_ > q_) { const int t_ = p_; p_ = q_; q_ = t_; }
@@ -309,10 +326,10 @@ __device__ int pinv_jacobi(const double* S1, const double* S2, int ns2, long s2s
                     G[p_ * P + j] = c * gp - sn * gq; G[q_ * P + j] = sn * gp + c * gq;
                 }
             }
-            __syncthreads();
+            bar256<BAR>();
         }
         if (s_rot == 0) break;            // (uniform: read after the barrier that ended the last round)
-        __syncthreads();
+        bar256<BAR>();
     }
     // weights 1/lam_k above MATLAB's cutoff max(size(G)) * eps(norm(G)), eps(x) = 2^(floor(log2 x) - 52)
     if (tid == 0) {
@@ -328,15 +345,76 @@ __device__ int pinv_jacobi(const double* S1, const double* S2, int ns2, long s2s
         }
         s_trunc = nt;
     }
-    __syncthreads();
-    for (int e = tid; e < R * R; e += blockDim.x) {
+    bar256<BAR>();
+    for (int e = tid; e < R * R; e += NTH) {
         const int i = e / R, j = e - i * R;
         double acc = 0.0;
         for (int k = 0; k < R; ++k) acc = fma(V[i * P + k] * cs[k], V[j * P + k], acc);
         out[i * RS + j] = acc;
     }
-    __syncthreads();
+    bar256<BAR>();
     return s_trunc;
+}
+
+// The whole ridge-system step for a group of 256 threads (k_upd's block 0, or the first 256 threads of the first
+// k_admm / k_ppass CTA to finish, which pre-compute the NEXT update's inverse while their grid drains): direct inverse,
+// the pinv path when the reference's pinv would truncate, status and statistics.  `sm` must hold
+// max(256, 2 R (R+1) + 192) doubles.
+struct RidgeJob {
+    const double *S1, *S2;    // [RS][RS]; S2 may be a stack of ns2 matrices (per-rank partials), summed in order
+    int ns2;
+    long s2stride;
+    double alpha;
+    double* Minv;             // [R][RS] out
+    int enable;
+    // N>1: S2 = the exchanged C3'C3, two parity buffers; wait for the ranks' pushes (see UpdArgs::sc_wait)
+    int sc_wait;
+    long s2par_stride;
+    const unsigned* sc_flags;
+    int nranks;
+    unsigned xbase;
+    unsigned* done_flag;      // done_flag[0] = 1 (release) when Minv is published; done_flag[3] = 1 instead when a
+                              // pre-computing kernel punts (ill-conditioned / non-finite system: the update kernel's block 0,
+                              // which has the shared memory for the pinv path, then does the whole job itself)
+};
+
+// FULL: with the pinv path (needs max(256, 2 R (R+1) + 192) doubles of scratch); else 256 doubles suffice and an
+// ill-conditioned system is left to the update kernel (done_flag[3]).
+template <int PQ, int BAR, bool FULL>
+__device__ __forceinline__ void ridge_job_run(const RidgeJob& j, IterState* st, int k_of_consumer, int R, int RS, double* sm, long long* dbg = nullptr) {
+    const int tid = threadIdx.x;
+    const double* S2 = j.S2;
+    if (j.sc_wait) {
+        // the ranks' C3'C3 partials pushed by the previous update C (or the initialisation): parity (k+1)&1, epoch xbase + k,
+        // k = iteration index the CONSUMING update runs in
+        const unsigned want = j.xbase + (unsigned)k_of_consumer;
+        const int par = (k_of_consumer + 1) & 1;
+        if (tid < j.nranks)
+            while ((int)(ld_acquire_sys_u32(j.sc_flags + par * 8 + tid) - want) < 0) __nanosleep(40);
+        bar256<BAR>();
+        S2 += par * j.s2par_stride;
+    }
+    const int cond = invert_ridge_system<PQ, BAR>(j.S1, S2, j.ns2, j.s2stride, j.alpha, R, RS, j.Minv, sm, dbg);
+    // (`cond` is uniform except for kRidgeNonFinite, which every thread decides from its own entries: vote)
+    __shared__ int s_vote[2];
+    if (tid == 0) { s_vote[0] = 0; s_vote[1] = 0; }
+    bar256<BAR>();
+    if (cond == kRidgeNonFinite) s_vote[0] = 1;
+    if (cond == kRidgeIll) s_vote[1] = 1;
+    bar256<BAR>();
+    if (!FULL) {
+        if (tid == 0) st_release_u32((s_vote[0] || s_vote[1]) ? j.done_flag + 3 : j.done_flag, 1u);
+        return;
+    }
+    if (s_vote[0]) {
+        if (tid == 0) atomicExch(&st->status, kStatusNumeric);
+    } else if (s_vote[1]) {
+        // the reference's pinv would (or might) truncate: do exactly what it does
+        const int nt = pinv_jacobi<BAR>(j.S1, S2, j.ns2, j.s2stride, j.alpha, R, RS, j.Minv, sm);
+        if (tid == 0) { atomicAdd(&st->pinv_fallbacks, 1); atomicAdd(&st->pinv_truncated, nt); }
+    }
+    bar256<BAR>();
+    if (tid == 0) st_release_u32(j.done_flag, 1u);
 }
 
 // S[a][b] = sum_i X[i][a] * X[i][b] over rows [0,n) of a row-major n x RS factor; S is RS x RS.
@@ -409,26 +487,15 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
     if (blockIdx.x == 0 && !a.apply) {
         return;
     } else if (blockIdx.x == 0) {
-        if (a.xmerge && a.extra_n > 0) {   // the local C3'C3 travels behind the RHS rows; S2 below is the stack of all ranks' partials
-            for (int r = 0; r < a.nranks; ++r) {
-                double* dst = a.peers[(a.rank + 1 + r) % a.nranks] + a.push_off + a.extra_off;
-                for (int e = tid; e < a.extra_n; e += kUpdThreads) dst[e] = a.extra_src[e];
-            }
-            xchg_publish_and_wait(a.peers, a.pflag_off, a.fstride, a.rank, a.nranks, a.xflags, epoch);
-        }
         // ---------------- the ridge system, inverted while the row CTAs reduce ----------------
-        const int cond = invert_ridge_system<PQ>(a.S1, a.S2, a.ns2, a.s2stride, a.alpha, R, RS, a.Minv, red, a.dbg);
-        // (every thread saw the same pivots, so `cond` is uniform; the votes are belt and braces)
-        const int nonfinite = __syncthreads_or(cond == kRidgeNonFinite), ill = __syncthreads_or(cond == kRidgeIll);
-        if (nonfinite) {
-            if (tid == 0) atomicExch(&a.st->status, kStatusNumeric);
-        } else if (ill) {
-            // the reference's pinv would (or might) truncate: do exactly what it does
-            const int nt = pinv_jacobi(a.S1, a.S2, a.ns2, a.s2stride, a.alpha, R, RS, a.Minv, sm);
-            if (tid == 0) { a.st->pinv_fallbacks += 1; a.st->pinv_truncated += nt; }
+        // (unless the previous k_admm / k_ppass already did it while its grid drained: inv_here == 0)
+        if (a.inv_here || ld_acquire_u32(&a.flags[3]) != 0u) {       // (a pre-computing kernel has long finished: plain stream order)
+            RidgeJob j;
+            j.S1 = a.S1; j.S2 = a.S2; j.ns2 = a.ns2; j.s2stride = a.s2stride; j.alpha = a.alpha; j.Minv = a.Minv; j.enable = 1;
+            j.sc_wait = a.sc_wait; j.s2par_stride = a.s2par_stride; j.sc_flags = a.sc_flags; j.nranks = a.nranks; j.xbase = a.xbase;
+            j.done_flag = &a.flags[0];
+            ridge_job_run<PQ, 0, true>(j, a.st, a.st->k, R, RS, sm, a.dbg);
         }
-        __syncthreads();
-        if (tid == 0) st_release_u32(&a.flags[0], 1u);
         TRITD_STAMP(0, 1)
     } else {
         // ---------------- RHS rows: fixed-order strided sum ----------------
@@ -566,7 +633,7 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
     const int nslice = G * a.gr;
     // Only the first `npart` CTAs take part (and spin): the row CTAs behind them must be able to become resident,
     // so the number of waiting CTAs stays well below the number of CTA slots of the GPU.
-    const int npart = min(min(nslice, (int)gridDim.x), kUpdMaxGramCtas);
+    const int npart = min(min(nslice, (int)gridDim.x), a.gram_cap);
     if ((int)blockIdx.x >= npart) return;
     cta_wait_eq(&a.flags[1], (unsigned)nrowcta);
     TRITD_STAMP(0, 2)
@@ -632,9 +699,26 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
     }
     __syncthreads();
     TRITD_STAMP(0, 12)
+    __shared__ int s_lastgram;
     if (tid == 0) {
-        if (atom_acq_rel_add_u32(&a.flags[2], 1u) == (unsigned)npart - 1) {      // last Gram CTA: leave the flags zero for the next launch
-            a.flags[0] = 0u; a.flags[1] = 0u; a.flags[2] = 0u;
+        s_lastgram = atom_acq_rel_add_u32(&a.flags[2], 1u) == (unsigned)npart - 1;
+        if (s_lastgram) { a.flags[0] = 0u; a.flags[1] = 0u; a.flags[2] = 0u; a.flags[3] = 0u; }  // last Gram CTA: leave the flags zero for the next launch
+    }
+    if (a.sc_push) {
+        // update C, N>1: the finished local C3'C3 goes to every rank's mailbox now (parity k&1, epoch xbase + k + 1);
+        // the next iteration's updates A and B find it there
+        __syncthreads();
+        if (s_lastgram) {
+            const int k = a.st->k;
+            const long dst_off = a.sc_off + (long)(k & 1) * a.s2par_stride + (long)a.rank * RS * RS;
+            for (int r = 0; r < a.nranks; ++r) {
+                double* dst = a.peers[(a.rank + 1 + r) % a.nranks] + dst_off;
+                for (int e = tid; e < RS * RS; e += kUpdThreads) dst[e] = __ldcg(a.gram_out + e);
+            }
+            __syncthreads();
+            if (tid < a.nranks)
+                st_release_sys_u32(reinterpret_cast<unsigned*>(a.peers[tid] + a.flag_area_off) + a.sc_flag_off + (k & 1) * 8 + a.rank,
+                                   a.xbase + (unsigned)k + 1u);
         }
     }
     TRITD_STAMP(0, 3)

@@ -34,4 +34,17 @@ __device__ __forceinline__ void cta_wait_ranks(const unsigned* flags, int n, uns
     __syncthreads();
 }
 
+// The initial C3'C3 partial (tritd_problem_init) goes to every mailbox the same way update C's later ones do:
+// parity 1, epoch xbase (the first update A waits for exactly that).
+__global__ void __launch_bounds__(256) k_push_sc(const double* src, double* const* peers, long dst_off, long flag_area_off, long flag_idx,
+                                                 int nranks, int n, unsigned epoch) {
+    for (int r = 0; r < nranks; ++r) {
+        double* dst = peers[r] + dst_off;
+        for (int e = threadIdx.x; e < n; e += 256) dst[e] = src[e];
+    }
+    __syncthreads();
+    if (threadIdx.x < (unsigned)nranks)
+        st_release_sys_u32(reinterpret_cast<unsigned*>(peers[threadIdx.x] + flag_area_off) + flag_idx, epoch);
+}
+
 }  // namespace tritd

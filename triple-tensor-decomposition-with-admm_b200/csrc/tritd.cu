@@ -318,8 +318,8 @@ struct tritd_problem {
     double* gpart = nullptr;             // [3][kGramSlices][RS][RS] row-slice partial Grams of k_upd
     // N>1 peer exchange (kernels_xchg.cuh): local mailbox, the peers' mailboxes mapped with CUDA IPC
     bool xchg = false;
-    double* box = nullptr;               // [A: nranks x slotA | B: nranks x slotB | N: nranks x 8 | flags (u32)]
-    size_t slotA = 0, slotB = 0, offB = 0, offN = 0, offF = 0, box_doubles = 0, fsA = 0, fsB = 0;
+    double* box = nullptr;               // [A: nranks x slotA | B: nranks x slotB | N: nranks x 8 | S: 2 x nranks x RS^2 | flags (u32)]
+    size_t slotA = 0, slotB = 0, offB = 0, offN = 0, offS = 0, offF = 0, box_doubles = 0, fsA = 0, fsB = 0;
     std::vector<void*> peer_map;         // cudaIpcOpenMemHandle mappings (nullptr for the own rank)
     double** peers = nullptr;            // device array [nranks] of mailbox bases
     unsigned xbase = 0;
@@ -342,6 +342,7 @@ struct tritd_problem {
     int* ctaTab = nullptr;               // per k_admm CTA: (i-tile, index among the tile's CTAs, CTAs of that tile)
     int* tileCnt = nullptr;              // CTAs (= partials of X1*F') per i-tile
     int partSlots = 0;                   // the largest of them: partF is [i-tile][partSlots][128][RS]
+    bool pre_inv = false;                // the ridge inverses of updates A / B are computed by the previous k_admm / k_ppass (see fill_ridge_job)
     int jgp = 2;                         // k_admm: column groups per stage asked for (AdmmCfg::JGP)
     int gridA = 0, tileH = 128, nitA = 1;  // k_admm: rows per i-tile (16 x consumer warps used) and number of i-tiles
     bool rhsA_ready = false;             // partF holds X1*F' of the current T
@@ -429,9 +430,16 @@ static int launch_mttkrp1(tritd_problem* p, const CUtensorMap& map, const double
     return TRITD_OK;
 }
 
-static int launch_ppass(tritd_problem* p, const CUtensorMap& mapT) {
+static void fill_ridge_job(tritd_problem* p, int which, RidgeJob& j);
+
+static int launch_ppass(tritd_problem* p, const CUtensorMap& mapT, bool with_inv_B = false) {
     tritd_ctx* c = p->ctx;
     PpassArgs a;
+    memset(&a.inv, 0, sizeof(a.inv));
+    if (with_inv_B) fill_ridge_job(p, 1, a.inv);
+    a.st = p->st; a.R = p->R;
+    // the scalar Gauss-Jordan inverse takes ~0.27 us per column; a row block of this pass ~0.05 us per (16-row chunk x n-tile)
+    a.inv_rb = (int)std::lround(0.27 * p->R / (0.05 * ((p->n1 + 15) / 16) * p->NT));
     a.P = p->P; a.stop = &p->st->stop;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS;
     a.n_jb = p->n_jc; a.n_rb = (long)p->n3 * p->n_jc; a.units = p->unitsP;
@@ -472,6 +480,10 @@ static int launch_admm(tritd_problem* p) {
     a.nslots = p->xchg ? p->box + p->offN : nullptr; a.nflags = p->xchg ? reinterpret_cast<const unsigned*>(p->box + p->offF) : nullptr;
     a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase;
     a.n1s = p->n1;
+    memset(&a.inv, 0, sizeof(a.inv));
+    if (p->pre_inv) fill_ridge_job(p, 0, a.inv);
+    a.R = p->R;
+    a.inv_stages = (int)std::ceil(0.27 * p->R / (p->jgp == 1 ? 1.7 : 3.3));     // ~0.27 us per column vs ~3.3 us per two-group stage
     a.cta_tab = p->ctaTab; a.part_slots = p->partSlots; a.dbg = p->dbgA;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc; a.tile_h = p->tileH;
 #define CALL(NT_, KS_)                                                                                                       \
@@ -490,12 +502,32 @@ static int launch_admm(tritd_problem* p) {
 // transposed.  which = 0/1/2 (A/B/C) selects the scratch inverse and the hand-shake flags.  apply == false: only
 // reduce the RHS rows into rhs_out (the all-reduce comes next).
 constexpr int kGramSlices = 8;     // row slices of k_upd's Gram phase
+constexpr size_t kFlagsSC = 8, kFlagsFixed = 24;   // u32 indices inside a mailbox's flag area: [norms: 8][C3'C3: 2 x 8][exchanges ...]
 static int gram_slices(int n) { return std::max(1, std::min(kGramSlices, (n + 63) / 64)); }
 
 enum UpdSrc { kSrcDirect = 0, kSrcPartF = 1, kSrcPB = 2, kSrcPC = 3 };
 
+// The ridge system of update `which` (0 = A: S_B o S_C + lambda2 I, 1 = B: S_A o S_C + lambda2 I), as a job for the first
+// k_admm / k_ppass CTA to finish (the inverse is then ready before the update kernel starts; its block 0 skips it).
+static void fill_ridge_job(tritd_problem* p, int which, RidgeJob& j) {
+    tritd_ctx* c = p->ctx;
+    memset(&j, 0, sizeof(j));
+    j.enable = 1;
+    j.S1 = which == 0 ? p->SB : p->SA;
+    j.S2 = p->bufA + (size_t)p->n1 * p->RS; j.ns2 = 1; j.s2stride = 0;
+    if (p->xchg) {
+        j.S2 = p->box + p->offS; j.ns2 = c->nranks; j.s2stride = (long)p->RS * p->RS;
+        j.sc_wait = 1; j.s2par_stride = (long)c->nranks * p->RS * p->RS;
+        j.sc_flags = reinterpret_cast<const unsigned*>(p->box + p->offF) + kFlagsSC;
+        j.nranks = c->nranks; j.xbase = p->xbase;
+    }
+    j.alpha = p->opts.lambda2;
+    j.Minv = p->Minv + (size_t)which * p->RS * p->RS;
+    j.done_flag = p->flags + 4 * which;
+}
+
 static int launch_upd(tritd_problem* p, int which, int src, bool apply, const double* rhs_direct, double* rhs_out,
-                      const double* S1, const double* S2, double alpha, double* X, double* XT, int n, double* S_out) {
+                      const double* S1, const double* S2, double alpha, double* X, double* XT, int n, double* S_out, bool inv_here = true) {
     tritd_ctx* c = p->ctx;
     UpdArgs a;
     memset(&a, 0, sizeof(a));
@@ -512,29 +544,37 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
         default: return fail(TRITD_ERR_INVALID, "bad update source");
     }
     a.S1 = S1; a.S2 = S2; a.alpha = alpha; a.gr = gram_slices(n);
-    a.ns2 = 1; a.s2stride = 0;
-    if (p->xchg) {
-        // C3'C3 lives in the exchange mailbox as per-rank partials behind the RHS_A slots
-        if (S2 == p->bufA + (size_t)p->n1 * p->RS) { a.S2 = p->box + (size_t)p->n1 * p->RS; a.ns2 = c->nranks; a.s2stride = (long)p->slotA; }
-        if (apply && which < 2) {
+    a.ns2 = 1; a.s2stride = 0; a.inv_here = inv_here ? 1 : 0;
+    if (p->xchg && apply) {
+        a.peers = p->peers; a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase;
+        a.flag_area_off = (long)p->offF; a.sc_flag_off = (long)kFlagsSC; a.sc_off = (long)p->offS;
+        a.s2par_stride = (long)c->nranks * p->RS * p->RS;
+        // C3'C3 lives in the exchange mailbox as per-rank partials (two parity buffers), pushed by update C
+        if (S2 == p->bufA + (size_t)p->n1 * p->RS) {
+            a.S2 = p->box + p->offS; a.ns2 = c->nranks; a.s2stride = (long)p->RS * p->RS;
+            a.sc_wait = 1; a.sc_flags = reinterpret_cast<const unsigned*>(p->box + p->offF) + kFlagsSC;
+        }
+        if (which == 2) a.sc_push = 1;
+        if (which < 2) {
             // updates A and B: the exchange of the RHS rows (and, for A, of the local C3'C3) happens inside the kernel
             const int ex = which;
             a.xmerge = 1;
-            a.peers = p->peers; a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase;
             a.push_off = (long)((ex == 0 ? 0 : p->offB) + (ex == 0 ? p->slotA : p->slotB) * c->rank);
             // flag block of this exchange: u32 index 8 (+ nranks * fsA for B) from the start of the flag area
-            const size_t fu = 8 + (ex == 0 ? 0 : (size_t)c->nranks * p->fsA);
+            const size_t fu = kFlagsFixed + (ex == 0 ? 0 : (size_t)c->nranks * p->fsA);
             a.pflag_off = (long)(p->offF + fu / 2);
             a.fstride = (long)(ex == 0 ? p->fsA : p->fsB);
             a.xflags = reinterpret_cast<const unsigned*>(p->box + p->offF) + fu;
             a.xbox = p->box + (ex == 0 ? 0 : p->offB);
             a.xslot = (long)(ex == 0 ? p->slotA : p->slotB);
-            // a CTA that waits for its counterparts on the other ranks keeps its slot: keep the grid within one wave
-            // (more rows per CTA) so that later waves do not each pay the exchange latency
-            while (a.wpr > 1 && (n + 8 / a.wpr - 1) / (8 / a.wpr) + 1 > p->upd_wave) a.wpr >>= 1;
-            if (ex == 0) { a.extra_src = p->bufA + (size_t)p->n1 * p->RS; a.extra_off = (long)p->n1 * p->RS; a.extra_n = p->RS * p->RS; }
         }
     }
+    // Row CTAs that wait -- for block 0's inverse (when it is computed in this launch) or, N>1, for their counterparts
+    // on the other ranks -- hold their slot meanwhile: keep such a grid within ONE wave (more rows per CTA) so that no
+    // second wave starts its reduction only after the first one has left.  (With the inverse pre-computed and no
+    // exchange nothing waits, and the finer grid streams P with more loads in flight.)
+    if (apply && (a.xmerge || a.inv_here))
+        while (a.wpr > 1 && (n + 8 / a.wpr - 1) / (8 / a.wpr) + 1 > p->upd_wave) a.wpr >>= 1;
     a.gram_part = p->gpart + (size_t)which * kGramSlices * p->RS * p->RS; a.gram_cnt = p->flags + 16 + 64 * which;
     a.Minv = p->Minv + (size_t)which * p->RS * p->RS;
     a.rhs_out = rhs_out; a.X = X; a.XT = XT; a.gram_out = S_out;
@@ -544,6 +584,7 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
     const size_t sm = upd_smem_bytes(p->RS);
     const int rows = 8 / a.wpr;
     const unsigned grid = (unsigned)((n + rows - 1) / rows + 1);
+    a.gram_cap = (int)grid <= p->upd_wave ? (int)grid : kUpdMaxGramCtas;
     switch ((p->R + 15) / 16) {
         case 1: k_upd<1><<<grid, kUpdThreads, sm, c->stream>>>(a); break;
         case 2: k_upd<2><<<grid, kUpdThreads, sm, c->stream>>>(a); break;
@@ -559,14 +600,15 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
 static void exchange_layout(tritd_problem* p) {
     const int nr = p->ctx->nranks;
     const size_t RS = p->RS;
-    p->slotA = (size_t)p->n1 * RS + RS * RS;
+    p->slotA = (size_t)p->n1 * RS;
     p->slotB = (size_t)p->n2 * RS;
     p->offB = p->slotA * nr;
     p->offN = p->offB + p->slotB * nr;
-    p->offF = p->offN + (size_t)8 * nr;               // flags (u32): [norms: 8] [exchange A: nr x fsA] [exchange B: nr x fsB]
+    p->offS = p->offN + (size_t)8 * nr;               // C3'C3 partials: [2 parities][nr][RS*RS]
+    p->offF = p->offS + (size_t)2 * nr * RS * RS;     // flags (u32): [norms: 8] [C3'C3: 2 x 8] [exchange A: nr x fsA] [exchange B: nr x fsB]
     p->fsA = ((size_t)p->n1 + 1 + 7) & ~(size_t)7;   // one flag per k_upd CTA (<= n + 1 CTAs), per rank
     p->fsB = ((size_t)p->n2 + 1 + 7) & ~(size_t)7;
-    p->box_doubles = p->offF + (8 + (size_t)nr * (p->fsA + p->fsB)) / 2 + 8;
+    p->box_doubles = p->offF + (kFlagsFixed + (size_t)nr * (p->fsA + p->fsB)) / 2 + 8;
 }
 
 // the mailbox bases of all ranks are known: upload them, size the one-wave limit of the exchanging grids
@@ -576,15 +618,6 @@ static int exchange_finish(tritd_problem* p, const std::vector<double*>& bases) 
     int s;
     if ((s = dalloc(p, &p->peers, (size_t)nr)) != TRITD_OK) return s;
     CU_TRY(cudaMemcpy(p->peers, bases.data(), sizeof(double*) * nr, cudaMemcpyHostToDevice));
-    int occ = 0;
-    const size_t sm = upd_smem_bytes(p->RS);
-    switch ((p->R + 15) / 16) {
-        case 1: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<1>, kUpdThreads, sm)); break;
-        case 2: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<2>, kUpdThreads, sm)); break;
-        case 3: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<3>, kUpdThreads, sm)); break;
-        default: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<4>, kUpdThreads, sm)); break;
-    }
-    p->upd_wave = std::max(1, occ * c->num_sms);
     p->xchg = true;
     return TRITD_OK;
 }
@@ -835,6 +868,14 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
             CU_TRY(cudaFuncSetAttribute(k_upd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, usm));
             CU_TRY(cudaFuncSetAttribute(k_upd<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, usm));
             CU_TRY(cudaFuncSetAttribute(k_upd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, usm));
+            int occ = 0;
+            switch ((p->R + 15) / 16) {
+                case 1: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<1>, kUpdThreads, (size_t)usm)); break;
+                case 2: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<2>, kUpdThreads, (size_t)usm)); break;
+                case 3: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<3>, kUpdThreads, (size_t)usm)); break;
+                default: CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_upd<4>, kUpdThreads, (size_t)usm)); break;
+            }
+            p->upd_wave = std::max(1, occ * c->num_sms);      // k_upd CTAs resident at once
             return TRITD_OK;
         };
         if ((s = q()) != TRITD_OK) return bail(s);
@@ -1047,11 +1088,19 @@ static int problem_init_finish(tritd_problem* p) {
     // small Grams of the initial factors: SB = B2'B2, SC (partial over local rows) = C3'C3
     ST_TRY(launch_small_gram(p, p->B2, p->n2, p->SB));
     ST_TRY(launch_small_gram(p, p->C3, p->n3, p->bufA + (size_t)p->n1 * p->RS));
-    CU_TRY(cudaStreamSynchronize(st));
-    p->xbase = c->xepoch;                 // epochs of this solve: xbase + 1 .. xbase + maxIter (same on every rank)
+    p->xbase = c->xepoch;                 // epochs of this solve: xbase (initial C3'C3), xbase + 1 .. xbase + maxIter (same on every rank)
     c->xepoch += (unsigned)p->opts.maxIter + 1u;
+    if (p->xchg) {
+        // the local partial of C3'C3 goes to every mailbox like update C's later ones (parity 1, epoch xbase)
+        k_push_sc<<<1, 256, 0, st>>>(p->bufA + (size_t)p->n1 * p->RS, p->peers, (long)(p->offS + ((size_t)c->nranks + c->rank) * p->RS * p->RS),
+                                    (long)p->offF, (long)(kFlagsSC + 8 + c->rank), c->nranks, p->RS * p->RS, p->xbase);
+        CU_TRY(cudaGetLastError());
+        c->launches += 1;
+    }
+    CU_TRY(cudaStreamSynchronize(st));
     p->initialized = true;
     p->rhsA_ready = false;
+    p->pre_inv = !(c->nranks > 1 && !p->xchg) && !getenv("TRITD_NO_PREINV");       // (NCCL path: C3'C3 arrives only with update A's all-reduce)
     p->graph_off = getenv("TRITD_NO_GRAPH") != nullptr;
     if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }     // opts (lambda2) are baked into the graph
     p->printed_k = 0;
@@ -1093,19 +1142,20 @@ static int enqueue_iteration(tritd_problem* p) {
     else if (multi && !xc) ST_TRY(launch_upd(p, 0, kSrcPartF, false, nullptr, rhsA, nullptr, nullptr, 0.0, nullptr, nullptr, p->n1, nullptr));
     ST_TRY(mark());
     if (multi && !xc) ST_TRY(allreduce_sum(c, p->bufA, nA));
+    // (from the second iteration on the previous k_admm has already inverted update A's ridge system)
     ST_TRY(launch_upd(p, 0, direct_A ? kSrcDirect : kSrcPartF, true, rhsA, nullptr, p->SB, SC, p->opts.lambda2, p->A1,
-                      p->A1T, p->n1, p->SA));
+                      p->A1T, p->n1, p->SA, !(p->pre_inv && p->rhsA_ready)));
     ST_TRY(mark());
 
     // update_B (:83-88) with the new A: RHS = X2*G' = sum_t C3(t,:) .* P(t,j,:), Gram = (A1'A1) o (C3'C3) + lambda2*I
-    ST_TRY(launch_ppass(p, p->mapT));
+    ST_TRY(launch_ppass(p, p->mapT, p->pre_inv));         // (its first CTA to finish inverts update B's ridge system)
     ST_TRY(mark());
     if (multi && !xc) {
         ST_TRY(launch_upd(p, 1, kSrcPB, false, nullptr, p->rhsB, nullptr, nullptr, 0.0, nullptr, nullptr, p->n2, nullptr));
         ST_TRY(allreduce_sum(c, p->rhsB, (size_t)p->n2 * p->RS));
     }
     ST_TRY(launch_upd(p, 1, multi && !xc ? kSrcDirect : kSrcPB, true, p->rhsB, nullptr, p->SA, SC, p->opts.lambda2, p->B2,
-                      nullptr, p->n2, p->SB));
+                      nullptr, p->n2, p->SB, !p->pre_inv));
 
     // update_C (:90-95) with the new A, B: slice-local; ridge fixed at 1e-9.  Leaves SC = C3'C3 over the local
     // slices in bufA, where the next exchange sums it over the ranks.
@@ -1551,6 +1601,20 @@ static int admm_group(tritd_ctx* G, const double* D_host, const unsigned char* m
     cudaEventElapsedTime(&it_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (s != TRITD_OK) return fail_out(s);
+    if (getenv("TRITD_DEBUG_STAMPS")) {            // diagnostics: globaltimer stamps of the last iteration's three k_upd launches, per device
+        for (int g = 0; g < nd; ++g) {
+            long long h[48];
+            if (!ps[g]->dbg) continue;
+            cudaSetDevice(ps[g]->ctx->device);
+            cudaMemcpy(h, ps[g]->dbg, sizeof(h), cudaMemcpyDeviceToHost);
+            for (int w = 0; w < 3; ++w) {
+                const long long* q = h + 16 * w; const long long b = q[0];
+                fprintf(stderr, "dev %d upd %c: block0 inv_init=%lld inv_done=%lld gram_wait_done=%lld gram_computed=%lld end=%lld | block1 start=%lld reduced=%lld "
+                        "inv_seen=%lld applied=%lld rows_done=%lld  (ns since block 0 start; start abs %lld)\n", g, "ABC"[w], q[13] - b, q[1] - b, q[2] - b,
+                        q[12] - b, q[3] - b, q[4] - b, q[5] - b, q[6] - b, q[9] - b, q[7] - b, b);
+            }
+        }
+    }
 
     tq = now_ms();
     for (int g = 0; g < nd && s == TRITD_OK; ++g) {
