@@ -58,7 +58,8 @@ typedef enum {
     TRITD_ERR_CUDA = 2,         /* CUDA runtime/driver failure or no device */
     TRITD_ERR_NCCL = 3,         /* NCCL missing or a collective failed */
     TRITD_ERR_NUMERIC = 4,      /* a ridge system contains NaN / Inf (MATLAB's pinv raises an error there too) */
-    TRITD_ERR_UNSUPPORTED = 5   /* r > TRITD_MAX_R */
+    TRITD_ERR_UNSUPPORTED = 5,  /* r > TRITD_MAX_R, or an operation the context kind does not offer */
+    TRITD_ERR_TIMEOUT = 6       /* a bounded device-side wait gave up (a peer rank died / broken exchange); results invalid */
 } tritd_status;
 
 #define TRITD_MAX_R 8           /* triple rank r (R = r^2 <= 64 columns per factor) */

@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
             *reinterpret_cast<double2*>(box + a.norm_off) = make_double2(red[0], red[1]);
             st_release_sys_u32(reinterpret_cast<unsigned*>(box + a.nflag_off) + a.rank, epoch);
         }
-        cta_wait_ranks(a.nflags, a.nranks, epoch);
+        cta_wait_ranks(a.nflags, a.nranks, epoch, &a.st->status);
         if (threadIdx.x == 0) {
             double ta = 0.0, tb = 0.0;
             for (int r = 0; r < a.nranks; ++r) { ta += __ldcg(a.nslots + 8 * r); tb += __ldcg(a.nslots + 8 * r + 1); }

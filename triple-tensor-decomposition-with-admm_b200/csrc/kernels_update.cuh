@@ -101,9 +101,14 @@ __device__ __forceinline__ unsigned atom_acq_rel_add_u32(unsigned* p, unsigned v
 }
 // CTA-wide wait until *p == want: thread 0 polls with acquire loads, the barrier extends the acquire to the CTA
 // (release/acquire are cumulative over bar.sync, so no full fence.sc is needed on either side).
-__device__ __forceinline__ void cta_wait_eq(const unsigned* p, unsigned want) {
-    if (threadIdx.x == 0)
-        while (ld_acquire_u32(p) != want) __nanosleep(20);
+__device__ __forceinline__ void cta_wait_eq(const unsigned* p, unsigned want, int* status) {
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        while (ld_acquire_u32(p) != want) {
+            __nanosleep(20);
+            if (++spins > kSpinLimit) { atomicExch(status, kStatusHang); break; }     // bounded: see kernels_xchg.cuh
+        }
+    }
     __syncthreads();
 }
 
@@ -390,7 +395,7 @@ __device__ __forceinline__ void ridge_job_run(const RidgeJob& j, IterState* st, 
         const unsigned want = j.xbase + (unsigned)k_of_consumer;
         const int par = (k_of_consumer + 1) & 1;
         if (tid < j.nranks)
-            while ((int)(ld_acquire_sys_u32(j.sc_flags + par * 8 + tid) - want) < 0) __nanosleep(40);
+            spin_until_epoch(j.sc_flags + par * 8 + tid, want, &st->status);
         bar256<BAR>();
         S2 += par * j.s2par_stride;
     }
@@ -444,12 +449,12 @@ constexpr int kUpdThreads = 256;
 // all ranks r in the own mailbox.  No grid-wide step, no CTA waits for a CTA of the same grid: nothing has to be
 // co-resident.  Flags hold epochs (monotonic), so they never need a reset.
 __device__ __forceinline__ void xchg_publish_and_wait(double* const* peers, long pflag_off, long fstride, int rank, int nranks,
-                                                      const unsigned* xflags, unsigned epoch) {
+                                                      const unsigned* xflags, unsigned epoch, int* status) {
     __syncthreads();
     if (threadIdx.x < (unsigned)nranks) {
         st_release_sys_u32(reinterpret_cast<unsigned*>(peers[threadIdx.x] + pflag_off) + rank * fstride + blockIdx.x, epoch);
         const unsigned* f = xflags + threadIdx.x * fstride + blockIdx.x;
-        while ((int)(ld_acquire_sys_u32(f) - epoch) < 0) __nanosleep(40);
+        spin_until_epoch(f, epoch, status);
     }
     __syncthreads();
 }
@@ -561,7 +566,7 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
         }
         if (!a.apply) return;
         if (a.xmerge) {
-            xchg_publish_and_wait(a.peers, a.pflag_off, a.fstride, a.rank, a.nranks, a.xflags, epoch);
+            xchg_publish_and_wait(a.peers, a.pflag_off, a.fstride, a.rank, a.nranks, a.xflags, epoch, &a.st->status);
             // the all-reduced rows: the ranks' slots summed in rank order (the same on every rank)
             if (warp < rows && row0 + warp < a.n) {
 #pragma unroll
@@ -585,7 +590,7 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
         TRITD_STAMP(1, 5)
 
         // ---------------- apply the inverse: X[row][:] = RHS[row][:] * inv(G) ----------------
-        cta_wait_eq(&a.flags[0], 1u);              // (also orders the rhs_s writes above)
+        cta_wait_eq(&a.flags[0], 1u, &a.st->status);              // (also orders the rhs_s writes above)
         TRITD_STAMP(1, 6)
         for (int e = tid; e < R * RS; e += kUpdThreads) Ms[e] = __ldcg(a.Minv + e);
         __syncthreads();
@@ -635,7 +640,7 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
     // so the number of waiting CTAs stays well below the number of CTA slots of the GPU.
     const int npart = min(min(nslice, (int)gridDim.x), a.gram_cap);
     if ((int)blockIdx.x >= npart) return;
-    cta_wait_eq(&a.flags[1], (unsigned)nrowcta);
+    cta_wait_eq(&a.flags[1], (unsigned)nrowcta, &a.st->status);
     TRITD_STAMP(0, 2)
     const int el = tid % ES, grp = tid / ES, rpg = 64 / RG;
     __shared__ int s_lastslice;

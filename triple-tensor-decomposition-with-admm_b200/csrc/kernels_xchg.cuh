@@ -26,11 +26,23 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Every spin in this library is bounded: a wait that has not been satisfied after kSpinLimit polls (several seconds --
+// a peer rank died, or a protocol error) raises IterState::status = kStatusHang and falls through, so that the solve
+// ends with TRITD_ERR_TIMEOUT instead of hanging the GPU.  The results of such a solve are meaningless.
+constexpr int kStatusHang = 2;
+constexpr unsigned kSpinLimit = 10u * 1000u * 1000u;   // x (40 ns sleep + one acquire load) ~ 10 s
+__device__ __forceinline__ void spin_until_epoch(const unsigned* flag, unsigned epoch, int* status) {
+    unsigned spins = 0;
+    while ((int)(ld_acquire_sys_u32(flag) - epoch) < 0) {
+        __nanosleep(40);
+        if (++spins > kSpinLimit) { atomicExch(status, kStatusHang); break; }
+    }
+}
+
 // CTA-wide wait until the `n` flags at `flags` (one per source rank) are all >= epoch; lanes of warp 0 poll one
 // rank each (n <= 32).  Epochs only grow, so ">=" also covers a source rank that is already one exchange ahead.
-__device__ __forceinline__ void cta_wait_ranks(const unsigned* flags, int n, unsigned epoch) {
-    if (threadIdx.x < (unsigned)n)
-        while ((int)(ld_acquire_sys_u32(flags + threadIdx.x) - epoch) < 0) __nanosleep(40);
+__device__ __forceinline__ void cta_wait_ranks(const unsigned* flags, int n, unsigned epoch, int* status) {
+    if (threadIdx.x < (unsigned)n) spin_until_epoch(flags + threadIdx.x, epoch, status);
     __syncthreads();
 }
 

@@ -1256,6 +1256,9 @@ static int fetch_state(tritd_problem* p) {
     if (p->st_host->status == kStatusNumeric)
         return fail(TRITD_ERR_NUMERIC, "ridge system contains NaN / Inf at iteration %d (pinv: input must not contain NaN or Inf)",
                     p->st_host->k + 1);
+    if (p->st_host->status == kStatusHang)
+        return fail(TRITD_ERR_TIMEOUT, "a device-side wait (inter-CTA hand-shake or peer exchange) timed out at iteration %d: a peer rank died or the exchange is broken",
+                    p->st_host->k + 1);
     return TRITD_OK;
 }
 
@@ -1317,6 +1320,8 @@ static int iterate_many(const std::vector<tritd_problem*>& ps, int32_t max_more,
         if (p->st_host->status == kStatusNumeric)
             return fail(TRITD_ERR_NUMERIC, "ridge system contains NaN / Inf at iteration %d (pinv: input must not contain NaN or Inf)",
                         p->st_host->k + 1);
+        if (p->st_host->status == kStatusHang)
+            return fail(TRITD_ERR_TIMEOUT, "a device-side wait timed out at iteration %d", p->st_host->k + 1);
         return print_progress(p);
     };
     while (remaining > 0 && !p->st_host->stop) {
