@@ -220,12 +220,17 @@ struct PpassArgs {
 };
 
 constexpr int kPW = 16;           // k_ppass consumer warps: two per row block (m-tiles 0,1 / 2,3), 4 per scheduler
+// ring depth of k_ppass: as many (8 T boxes + factor box) stages as 227 KB hold, at most 6
+__host__ __device__ constexpr int ppass_stages(int NT) {
+    return (220 * 1024) / (kCW * kBoxBytes + NT * 8 * 128) > 6 ? 6 : (220 * 1024) / (kCW * kBoxBytes + NT * 8 * 128);
+}
 
 template <int NT>
 __global__ void __launch_bounds__((kPW + 1) * 32, 1)
 k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapA1T, const PpassArgs a) {
     if (*a.stop) return;
     constexpr int kStageDoubles = kCW * (kBoxBytes / 8) + NT * 8 * 16;
+    constexpr int kStages = ppass_stages(NT);       // (shadows the 4 of k_mttkrp1)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double* stage_base = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(stage_base + (size_t)kStages * kStageDoubles);
@@ -248,25 +253,31 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
     __syncthreads();
 
     if (warp == kPW) {
-        if (lane == 0) {
-            tma_prefetch_desc(&mapT);
-            tma_prefetch_desc(&mapA1T);
-            int s = 0; uint32_t ph = 0;
-            for (long u = 0; u < npass; ++u) {
-                const long rb0 = rbA + u * kCW;
-                const int nvalid = (int)min((long)kCW, rbB - rb0);
-                for (int kc = 0; kc < nkc; ++kc) {
+        // Producer warp: lane w < 8 owns slot w of every stage (its row block's (t, jb) is worked out once per pass, not
+        // once per chunk), lane 8 the factor box; lane 0 waits for the slot and arms the barrier, then the nine lanes
+        // issue their TMA loads side by side -- one thread doing all of it (eight 64-bit divisions and nine issues
+        // per stage) was the slowest link of the kernel.
+        if (lane == 0) { tma_prefetch_desc(&mapT); tma_prefetch_desc(&mapA1T); }
+        int s = 0; uint32_t ph = 0;
+        for (long u = 0; u < npass; ++u) {
+            const long rb0 = rbA + u * kCW;
+            const int nvalid = (int)min((long)kCW, rbB - rb0);
+            int t = 0, jb = 0;
+            if (lane < nvalid) {
+                const unsigned rb = (unsigned)(rb0 + lane);
+                t = (int)(rb / (unsigned)a.n_jb);
+                jb = (int)(rb - (unsigned)t * (unsigned)a.n_jb);
+            }
+            for (int kc = 0; kc < nkc; ++kc) {
+                double* dst = stage_base + (size_t)s * kStageDoubles;
+                if (lane == 0) {
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], nvalid * kBoxBytes + NT * 8 * 128);
-                    double* dst = stage_base + (size_t)s * kStageDoubles;
-                    for (int w = 0; w < nvalid; ++w) {
-                        const long rb = rb0 + w;
-                        const int t = (int)(rb / a.n_jb), jb = (int)(rb - (long)t * a.n_jb);
-                        tma_load_3d(dst + w * (kBoxBytes / 8), &mapT, &full[s], kc * 16, jb * kBoxRows, t);
-                    }
-                    tma_load_2d(dst + kCW * (kBoxBytes / 8), &mapA1T, &full[s], kc * 16, 0);
-                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (lane < nvalid) tma_load_3d(dst + lane * (kBoxBytes / 8), &mapT, &full[s], kc * 16, jb * kBoxRows, t);
+                else if (lane == kCW) tma_load_2d(dst + kCW * (kBoxBytes / 8), &mapA1T, &full[s], kc * 16, 0);
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
         return;

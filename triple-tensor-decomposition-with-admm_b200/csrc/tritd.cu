@@ -129,6 +129,7 @@ struct tritd_ctx {
     PFN_encodeTiled encode = nullptr;
     tritd_problem* cached = nullptr;     // device state of the last tritd_admm_f64 call, reused when the shape repeats
     bool cache_poisoned = false;         // the last call failed half-way: the cached state must not be reused
+    tritd_problem* hcached = nullptr;    // factor-level state of the last triple_product / evaluate call (same reuse rule)
     // single-process multi-GPU (tritd_create_devices): the context the caller holds is a GROUP of one member
     // context per device (rank g of `nranks` = number of devices, no NCCL communicator, peer access instead of IPC)
     bool inproc = false;                 // member of a group
@@ -255,6 +256,7 @@ extern "C" int tritd_problem_get_E(tritd_problem* p, double* E_host);
 extern "C" int tritd_trim(tritd_ctx* c) {
     if (!c) return fail(TRITD_ERR_INVALID, "ctx is NULL");
     if (c->cached) { tritd_problem_destroy(c->cached); c->cached = nullptr; }
+    if (c->hcached) { tritd_problem_destroy(c->hcached); c->hcached = nullptr; }
     for (tritd_problem* q : c->gcached) tritd_problem_destroy(q);
     c->gcached.clear();
     return TRITD_OK;
@@ -410,7 +412,7 @@ static int make_map(tritd_ctx* c, CUtensorMap* map, void* base, int rank, const 
     }
 
 static size_t smem_mttkrp1(int NT) { return (size_t)kStages * kCW * kBoxBytes + (size_t)NT * 8 * kPJ * 8 + 2 * kStages * 8; }
-static size_t smem_ppass(int NT) { return (size_t)kStages * (kCW * kBoxBytes + NT * 8 * 128) + 2 * kStages * 8; }
+static size_t smem_ppass(int NT) { return (size_t)ppass_stages(NT) * (kCW * kBoxBytes + NT * 8 * 128) + 2 * ppass_stages(NT) * 8; }
 
 static int launch_mttkrp1(tritd_problem* p, const CUtensorMap& map, const double* B2, const double* C3, double* rhs_out) {
     tritd_ctx* c = p->ctx;
@@ -571,9 +573,11 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
     }
     // Row CTAs that wait -- for block 0's inverse (when it is computed in this launch) or, N>1, for their counterparts
     // on the other ranks -- hold their slot meanwhile: keep such a grid within ONE wave (more rows per CTA) so that no
-    // second wave starts its reduction only after the first one has left.  (With the inverse pre-computed and no
-    // exchange nothing waits, and the finer grid streams P with more loads in flight.)
-    if (apply && (a.xmerge || a.inv_here))
+    // second wave starts its reduction only after the first one has left.  Light reductions are latency bound and
+    // want one wave too (1024 rows, r = 8: 58 vs 82 us for updates B + C); only a reduction that streams a lot of P with
+    // nothing to wait for keeps the finest grid, for the loads in flight (512^3, r = 6: 110 vs 130 us).
+    const bool heavy = (double)a.count * n * p->RS * 8.0 > 64e6;
+    if (apply && (a.xmerge || a.inv_here || !heavy))
         while (a.wpr > 1 && (n + 8 / a.wpr - 1) / (8 / a.wpr) + 1 > p->upd_wave) a.wpr >>= 1;
     a.gram_part = p->gpart + (size_t)which * kGramSlices * p->RS * p->RS; a.gram_cnt = p->flags + 16 + 64 * which;
     a.Minv = p->Minv + (size_t)which * p->RS * p->RS;
@@ -1013,16 +1017,14 @@ static void unpack_C(const std::vector<double>& in, int n3, int R, int RS, doubl
 
 static int upload_factors(tritd_problem* p, const double* A0, const double* B0, const double* C0) {
     cudaStream_t st = p->ctx->stream;
-    std::vector<double> h;
-    pack_A(A0, p->n1, p->R, p->RS, h);
-    CU_TRY(cudaMemcpyAsync(p->A1, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    pack_B(B0, p->n2, p->r, p->RS, h);
-    CU_TRY(cudaMemcpyAsync(p->B2, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));
-    pack_C(C0, p->n3, p->R, p->RS, h);
-    CU_TRY(cudaMemcpyAsync(p->C3, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    std::vector<double> ha, hb, hc;
+    pack_A(A0, p->n1, p->R, p->RS, ha);
+    pack_B(B0, p->n2, p->r, p->RS, hb);
+    pack_C(C0, p->n3, p->R, p->RS, hc);
+    CU_TRY(cudaMemcpyAsync(p->A1, ha.data(), ha.size() * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(p->B2, hb.data(), hb.size() * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(p->C3, hc.data(), hc.size() * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));           // (the staging vectors die here)
     return TRITD_OK;
 }
 
@@ -1751,13 +1753,27 @@ static int reconstruct_to(tritd_problem* p, double* dst, int ld) {
 // dense (ld = n1) when the 16-byte vector stores of k_fused stay aligned, else padded to even
 static int dense_ld(int n1) { return (n1 + 1) & ~1; }
 
+// The factor-level state (factors, small scratch; no N-sized array) of the standalone helpers is kept in the context and
+// reused while the shape repeats: the caller's post-solve triple_product(A,B,C) (traffic_triple_comparison.m:62) then costs
+// the factor upload and one kernel, not a dozen allocations.
+static int helper_problem(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int r, tritd_problem** out) {
+    tritd_problem* p = c->hcached;
+    if (p && !(p->n1 == n1 && p->n2 == n2 && p->n3 == n3 && p->r == r)) { tritd_problem_destroy(p); p = nullptr; c->hcached = nullptr; }
+    if (!p) {
+        ST_TRY(problem_create(c, n1, n2, n3, r, kLevelFactors, &p));
+        c->hcached = p;
+    }
+    *out = p;
+    return TRITD_OK;
+}
+
 static int triple_product_common(tritd_ctx* c, const double* A, const double* B, const double* C, int64_t n1, int64_t n2,
                                  int64_t n3, int r, double* Xhat, bool out_on_device) {
     if (!c || !A || !B || !C || !Xhat) return fail(TRITD_ERR_INVALID, "NULL argument");
     ST_TRY(check_r(r));
     tritd_problem* p = nullptr;
-    ST_TRY(problem_create(c, n1, n2, n3, r, kLevelFactors, &p));          // factors + small state only
-    auto done = [&](int code) { cudaStreamSynchronize(c->stream); tritd_problem_destroy(p); return code; };
+    ST_TRY(helper_problem(c, n1, n2, n3, r, &p));                         // factors + small state only
+    auto done = [&](int code) { cudaStreamSynchronize(c->stream); return code; };
     int s = upload_factors(p, A, B, C);
     if (s != TRITD_OK) return done(s);
     const int ld = dense_ld(p->n1);
@@ -1875,10 +1891,9 @@ extern "C" int tritd_evaluate_f64(tritd_ctx* c, const double* A, const double* B
     if (!c || !A || !B || !C || !gt_host) return fail(TRITD_ERR_INVALID, "NULL argument");
     ST_TRY(check_r(r));
     tritd_problem* p = nullptr;
-    ST_TRY(problem_create(c, n1, n2, n3, r, kLevelFactors, &p));
+    ST_TRY(helper_problem(c, n1, n2, n3, r, &p));
     int s = upload_factors(p, A, B, C);
     if (s == TRITD_OK) s = evaluate_with(p, gt_host, mask_host, rmse, nrmse);
-    tritd_problem_destroy(p);
     return s;
 }
 
