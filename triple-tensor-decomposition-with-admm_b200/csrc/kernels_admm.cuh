@@ -60,7 +60,13 @@ struct AdmmArgs {
 // JGP: column groups per stage asked for (1 or 2).  Two-group stages give every warp two independent dependency
 // chains between barriers; one-group stages are half as large, so twice as many fit the ring and twice as many loads
 // are in flight per SM -- which wins depends on the shape (chosen at problem set-up, tritd.cu).
-template <int KS, int NT, int JGP = 2> struct AdmmCfg {
+// SW: 16-row strips per consumer warp (1 or 2).  With two, an i-tile is up to 256 rows deep and a stage is ONE 8-column
+// group of it: the same 64 KB per stage and the same two independent chains per warp as a two-group stage.  A tensor
+// of 192..240 rows (12..15 strips) is then ONE tile whose boxes cover whole columns: with a dense leading dimension
+// (ld1 = rows) every box is one contiguous, 256-byte aligned run in HBM (8 columns x 1920 B for 240 rows) -- no pad
+// rows to drag along, no second shallower tile whose CTAs take as long as full ones (240 x 320 x 300: 257.7 -> 248 us,
+// profiles/r02_sw_experiments.md).  The B fragments of both contractions are loaded once for the two strips.
+template <int KS, int NT, int JGP = 2, int SW = 1> struct AdmmCfg {
     static constexpr int PL = FusedCfg<KS>::PL;
     static constexpr int NB = 4;                                                // boxes per stage
     // large R: the B operand of L is read from the transposed chunk too (2-way bank conflict on a small share of
@@ -70,8 +76,8 @@ template <int KS, int NT, int JGP = 2> struct AdmmCfg {
     static constexpr int kAvail = 227 * 1024 - kFixed;
     // a stage holds JG groups of 8 columns: two when three such stages fit (more independent work per warp
     // between barriers), else one
-    static constexpr int JG = (JGP >= 2 && (kAvail / (NB * 2 * 8 * 128 * 8 + 1024)) >= 3) ? 2 : 1;
-    static constexpr int kBoxD = 8 * JG * 128;                                  // doubles per array per stage: [8 warps][8*JG j][16 i]
+    static constexpr int JG = (JGP >= 2 && SW == 1 && (kAvail / (NB * 2 * 8 * 128 * 8 + 1024)) >= 3) ? 2 : 1;
+    static constexpr int kBoxD = 8 * SW * JG * 128;                             // doubles per array per stage: [8*SW strips][8*JG j][16 i]
     static constexpr int kStageBytes = NB * kBoxD * 8 + 1024;                   // + the C3 row of the slice; keeps boxes 1 KB aligned
     static constexpr int S = (kAvail / kStageBytes) > 8 ? 8 : (kAvail / kStageBytes);
     static constexpr size_t kSmem = (size_t)S * kStageBytes + kFixed;
@@ -144,14 +150,17 @@ constexpr int kAdmmThreads = 384;
 
 // MASKED: the opt-in completion variant (tritd_admm_masked_f64): unobserved entries are stored as NaN
 // in D; there O = E = Y_L = Y_O = 0, the residuals do not count and the next target is T' = L (imputation).
-template <int KS, int NT, bool MASKED, int JGP = 2>
+template <int KS, int NT, bool MASKED, int JGP = 2, int SW = 1>
 __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant__ AdmmMaps maps_full, const __grid_constant__ AdmmMaps maps_last,
                                                           const AdmmArgs a) {
-    using Cfg = AdmmCfg<KS, NT, JGP>;
+    using Cfg = AdmmCfg<KS, NT, JGP, SW>;
     constexpr int PL = Cfg::PL, NB = Cfg::NB, S = Cfg::S, JG = Cfg::JG, kBoxD = Cfg::kBoxD;
     constexpr int kStageD = Cfg::kStageBytes / 8;
     constexpr int SPU = 4 / JG;           // stages per unit (32 columns of one slice)
-    constexpr bool kFoldA = KS <= 8;      // fold C3[t,:] into the A fragments once per slice (else into B per use)
+    // fold C3[t,:] into the A fragments once per slice (else into B per use; with two strips per warp the folded copy
+    // would not fit the register file)
+    constexpr bool kFoldA = KS <= 8 && SW == 1;
+    constexpr int kPartH = 128 * SW;      // rows of a CTA's X1*F' partial
     if (a.st->stop) return;
     const int k_start = a.st->k;          // iteration index of this launch (the last CTA advances it at the very end)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -172,12 +181,13 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
     const long dq = (a.inv.enable && it == a.cta_tab[0]) ? a.inv_stages : 0;
     const long q0 = max(0L, (Q + dq) * x / gi - dq), q1 = max(0L, (Q + dq) * (x + 1) / gi - dq);
     const long nq = q1 - q0;
-    const int nwf = a.tile_h >> 4;                                   // 16-row strips (= consumer warps) of a full i-tile
-    const int nact = min(nwf, (a.n1s - it * a.tile_h + 15) >> 4);     // ... of THIS tile (the last tile may have fewer)
+    const int nwf = a.tile_h >> 4;                                   // 16-row strips of a full i-tile (<= 8 * SW)
+    const int nstr = min(nwf, (a.n1s - it * a.tile_h + 15) >> 4);     // ... of THIS tile (the last tile may have fewer)
+    const int nact = min(8, nstr);                                   // consumer warps with work: warp w owns strips w (and w + 8)
     // TMA box depth in i_hi = strips of this tile: the last tile has its own tensor maps, so that no box ever
     // reaches past the tensor in i (boxes clipped by the out-of-bounds logic measured ~7 % slower)
-    const int nw = nact;
-    const AdmmMaps& maps = nact < nwf ? maps_last : maps_full;
+    const int nw = nstr;
+    const AdmmMaps& maps = nstr < nwf ? maps_last : maps_full;
     const int i_hi0 = it * nwf;                                      // first strip of this tile
     const long u0 = q0 / SPU;
     const int jc0 = (int)(u0 / a.n3), t0 = (int)(u0 - (long)jc0 * a.n3), sg0 = (int)(q0 - u0 * SPU);
@@ -243,33 +253,43 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
       if (warp < nact) {
         // ---------------- consumers ----------------
         const int g = lane >> 2, tig = lane & 3;
-        const int i0 = it * a.tile_h + warp * 16 + 2 * g;
         AdmmPrm prm;
         {
             const IterState& S0 = *a.st;
             prm.muL = S0.muL; prm.muO = S0.muO; prm.rmuL = S0.rmuL; prm.rmuO = S0.rmuO; prm.thr = S0.thr;
             prm.musum = S0.musum; prm.rmusum = 1.0 / S0.musum; prm.rmuL_next = S0.rmuL_next;
         }
-        double aF[2][KS];
-#pragma unroll
-        for (int s = 0; s < KS; ++s) {
-            aF[0][s] = (i0 < a.n1) ? __ldg(a.A1 + (size_t)i0 * a.RS + 4 * s + tig) : 0.0;
-            aF[1][s] = (i0 + 1 < a.n1) ? __ldg(a.A1 + (size_t)(i0 + 1) * a.RS + 4 * s + tig) : 0.0;
-        }
-        double acc[2][NT][2];
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
-        double aS[2][kFoldA ? KS : 1];
         double sL = 0.0, sO = 0.0;
+        const int nthr = nact * 32;
+        // NS = strips this warp really has (SW, or 1 for the warp whose second strip lies below the tile): the body is
+        // instantiated per NS so that the strips of a stage share one basic block (their chains interleave)
+        auto body = [&](auto ns_tag) {
+        constexpr int NS = decltype(ns_tag)::value;
+        double aF[NS][2][KS];
+#pragma unroll
+        for (int h2 = 0; h2 < NS; ++h2) {
+            const int i0 = it * a.tile_h + (warp + 8 * h2) * 16 + 2 * g;
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                aF[h2][0][s] = (i0 < a.n1) ? __ldg(a.A1 + (size_t)i0 * a.RS + 4 * s + tig) : 0.0;
+                aF[h2][1][s] = (i0 + 1 < a.n1) ? __ldg(a.A1 + (size_t)(i0 + 1) * a.RS + 4 * s + tig) : 0.0;
+            }
+        }
+        double acc[NS][2][NT][2];
+#pragma unroll
+        for (int h2 = 0; h2 < NS; ++h2)
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n) acc[h2][m][n][0] = acc[h2][m][n][1] = 0.0;
+        double aS[NS][2][kFoldA ? KS : 1];
         // swizzled offsets (in double2 units) of this lane's two columns c = 0, 1 of the first column group inside its
-        // warp's [8*JG j][16 i] block; the second group is 64 further (8 rows of 128 B, same swizzle phase)
+        // first strip's [8*JG j][16 i] block; the second group is 64 further (8 rows of 128 B, same swizzle phase), the
+        // second strip 8 strips further
         const int off0 = warp * (64 * JG) + (2 * tig) * 8 + (g ^ (2 * tig));
         const int off1 = warp * (64 * JG) + (2 * tig + 1) * 8 + (g ^ (2 * tig + 1));
         int slot = 0; uint32_t ph = 0;
         int jc = jc0, t = t0, cur_jc = -1;
-        const int nthr = nact * 32;
 
         const long u_end = nq > 0 ? (q1 - 1) / SPU + 1 : u0;
         for (long u = u0; u < u_end; ++u) {
@@ -310,58 +330,72 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
 #pragma unroll
                     for (int s = 0; s < KS; ++s) {
                         const double c3 = c3row[4 * s + tig];
-                        aS[0][s] = aF[0][s] * c3;
-                        aS[1][s] = aF[1][s] * c3;
+#pragma unroll
+                        for (int h2 = 0; h2 < NS; ++h2) {
+                            aS[h2][0][s] = aF[h2][0][s] * c3;
+                            aS[h2][1][s] = aF[h2][1][s] * c3;
+                        }
                     }
                 }
                 double c3s[NT];                              // column scales of the MTTKRP B fragments (1 when the chunk is pre-scaled)
 #pragma unroll
                 for (int n = 0; n < NT; ++n) c3s[n] = Cfg::kShareB ? 1.0 : c3row[8 * n + g];
                 double2* s2 = reinterpret_cast<double2*>(st);
-                // the JG column groups of a stage are independent: one basic block, so their DMMA and
-                // element-wise dependency chains interleave
+                // the JG column groups (and the NS strips) of a stage are independent: one basic block, so their
+                // DMMA and element-wise dependency chains interleave
 #pragma unroll
                 for (int h = 0; h < JG; ++h) {
                     const int jg = sg * JG + h;
-                    // L patch: l[m][c] = L(i0 + m, j0 + 2*tig + c, t)
-                    double l[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                    // L patch: l[strip][m][c] = L(i0 + m, j0 + 2*tig + c, t); a B fragment serves all strips
+                    double l[NS][2][2];
+#pragma unroll
+                    for (int h2 = 0; h2 < NS; ++h2) l[h2][0][0] = l[h2][0][1] = l[h2][1][0] = l[h2][1][1] = 0.0;
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
                         double b = Cfg::kShareB ? B2T[(4 * ks + tig) * kPJ + jg * 8 + g] : B2s[(jg * 8 + g) * PL + 4 * ks + tig];
-                        if (kFoldA) {
-                            dmma884(l[0][0], l[0][1], aS[0][ks], b);
-                            dmma884(l[1][0], l[1][1], aS[1][ks], b);
-                        } else {
-                            if (!Cfg::kShareB) b *= c3row[4 * ks + tig];
-                            dmma884(l[0][0], l[0][1], aF[0][ks], b);
-                            dmma884(l[1][0], l[1][1], aF[1][ks], b);
+                        if (!kFoldA && !Cfg::kShareB) b *= c3row[4 * ks + tig];
+#pragma unroll
+                        for (int h2 = 0; h2 < NS; ++h2) {
+                            if (kFoldA) {
+                                dmma884(l[h2][0][0], l[h2][0][1], aS[h2][0][ks], b);
+                                dmma884(l[h2][1][0], l[h2][1][1], aS[h2][1][ks], b);
+                            } else {
+                                dmma884(l[h2][0][0], l[h2][0][1], aF[h2][0][ks], b);
+                                dmma884(l[h2][1][0], l[h2][1][1], aF[h2][1][ks], b);
+                            }
                         }
                     }
-                    double2 tn[2];
+                    double2 tn[NS][2];
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const int off = (c ? off1 : off0) + 64 * h;
-                        const double2 d = s2[off];
-                        double2 yl = s2[kBoxD / 2 + off];
-                        double2 e = s2[2 * (kBoxD / 2) + off];
-                        double2 yo = s2[3 * (kBoxD / 2) + off];
-                        double2 o;
-                        admm_point2<MASKED>(prm, d.x, l[0][c], yl.x, e.x, yo.x, o.x, tn[c].x, sL, sO);
-                        admm_point2<MASKED>(prm, d.y, l[1][c], yl.y, e.y, yo.y, o.y, tn[c].y, sL, sO);
-                        s2[off] = tn[c];
-                        s2[kBoxD / 2 + off] = yl;
-                        s2[2 * (kBoxD / 2) + off] = e;
-                        s2[3 * (kBoxD / 2) + off] = yo;
+                    for (int h2 = 0; h2 < NS; ++h2) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int off = (c ? off1 : off0) + 64 * h + h2 * (8 * 64 * JG);
+                            const double2 d = s2[off];
+                            double2 yl = s2[kBoxD / 2 + off];
+                            double2 e = s2[2 * (kBoxD / 2) + off];
+                            double2 yo = s2[3 * (kBoxD / 2) + off];
+                            double2 o;
+                            admm_point2<MASKED>(prm, d.x, l[h2][0][c], yl.x, e.x, yo.x, o.x, tn[h2][c].x, sL, sO);
+                            admm_point2<MASKED>(prm, d.y, l[h2][1][c], yl.y, e.y, yo.y, o.y, tn[h2][c].y, sL, sO);
+                            s2[off] = tn[h2][c];
+                            s2[kBoxD / 2 + off] = yl;
+                            s2[2 * (kBoxD / 2) + off] = e;
+                            s2[3 * (kBoxD / 2) + off] = yo;
+                        }
                     }
                     // next iteration's X1*F': acc[m][n] += T'(i,j) B2(j,k) C3(t,k); k-step c covers j = j0 + 2*tig + c
 #pragma unroll
                     for (int n = 0; n < NT; ++n) {
                         const double2 b = *reinterpret_cast<const double2*>(B2T + (8 * n + g) * kPJ + jg * 8 + 2 * tig);
                         const double b0 = Cfg::kShareB ? b.x : b.x * c3s[n], b1 = Cfg::kShareB ? b.y : b.y * c3s[n];
-                        dmma884(acc[0][n][0], acc[0][n][1], tn[0].x, b0);
-                        dmma884(acc[1][n][0], acc[1][n][1], tn[0].y, b0);
-                        dmma884(acc[0][n][0], acc[0][n][1], tn[1].x, b1);
-                        dmma884(acc[1][n][0], acc[1][n][1], tn[1].y, b1);
+#pragma unroll
+                        for (int h2 = 0; h2 < NS; ++h2) {
+                            dmma884(acc[h2][0][n][0], acc[h2][0][n][1], tn[h2][0].x, b0);
+                            dmma884(acc[h2][1][n][0], acc[h2][1][n][1], tn[h2][0].y, b0);
+                            dmma884(acc[h2][0][n][0], acc[h2][0][n][1], tn[h2][1].x, b1);
+                            dmma884(acc[h2][1][n][0], acc[h2][1][n][1], tn[h2][1].y, b1);
+                        }
                     }
                 }
                 fence_proxy_async_smem();
@@ -371,19 +405,24 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
             }
             if (++t == a.n3) { t = 0; ++jc; }
         }
-        double* p = a.partM + ((size_t)it * a.part_slots + x) * 128 * a.RS;
+        double* p = a.partM + ((size_t)it * a.part_slots + x) * kPartH * a.RS;
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int h2 = 0; h2 < NS; ++h2)
 #pragma unroll
-            for (int n = 0; n < NT; ++n)
-                *reinterpret_cast<double2*>(p + (size_t)(warp * 16 + 2 * g + m) * a.RS + 8 * n + 2 * tig) =
-                    make_double2(acc[m][n][0], acc[m][n][1]);
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+                    *reinterpret_cast<double2*>(p + (size_t)((warp + 8 * h2) * 16 + 2 * g + m) * a.RS + 8 * n + 2 * tig) =
+                        make_double2(acc[h2][m][n][0], acc[h2][m][n][1]);
+        };
+        if (SW > 1 && warp + 8 < nstr) body(std::integral_constant<int, SW>{});
+        else body(std::integral_constant<int, 1>{});
         sL = warp_sum(sL);
         sO = warp_sum(sO);
         if (lane == 0) { red[warp] = sL; red[8 + warp] = sO; }
       } else {
         // consumer warp whose 16 rows lie entirely outside the tensor: contributes zeros
-        double* p = a.partM + ((size_t)it * a.part_slots + x) * 128 * a.RS;
+        double* p = a.partM + ((size_t)it * a.part_slots + x) * kPartH * a.RS;
         for (int e = lane; e < 16 * a.RS; e += 32) p[(size_t)warp * 16 * a.RS + e] = 0.0;
         if (lane == 0) { red[warp] = 0.0; red[8 + warp] = 0.0; }
       }

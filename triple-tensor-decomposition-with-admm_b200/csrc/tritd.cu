@@ -346,6 +346,7 @@ struct tritd_problem {
     int partSlots = 0;                   // the largest of them: partF is [i-tile][partSlots][128][RS]
     bool pre_inv = false;                // the ridge inverses of updates A / B are computed by the previous k_admm / k_ppass (see fill_ridge_job)
     int jgp = 2;                         // k_admm: column groups per stage asked for (AdmmCfg::JGP)
+    int swA = 1;                         // k_admm: 16-row strips per consumer warp (AdmmCfg::SW); partials are [128 * swA][RS]
     int gridA = 0, tileH = 128, nitA = 1;  // k_admm: rows per i-tile (16 x consumer warps used) and number of i-tiles
     bool rhsA_ready = false;             // partF holds X1*F' of the current T
     int n_it = 0, n_jc = 0, gridM = 0, gridP = 0, gridF = 0, gi = 0;
@@ -471,6 +472,24 @@ static int launch_fused(tritd_problem* p, int mode, double* Lout) {
     return TRITD_OK;
 }
 
+// k_admm with two strips per consumer warp exists for the ranks whose fragments fit the register file (r <= 5)
+constexpr bool admm_sw2_ok(int KS) { return KS <= 8; }
+template <int KS, int NT> static void launch_admm_sw2(tritd_problem* p, const AdmmArgs& a) {
+    if constexpr (admm_sw2_ok(KS)) {
+        cudaStream_t st = p->ctx->stream;
+        if (p->masked) k_admm<KS, NT, true, 1, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS, NT, 1, 2>::kSmem, st>>>(p->maps, p->mapsLast, a);
+        else k_admm<KS, NT, false, 1, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS, NT, 1, 2>::kSmem, st>>>(p->maps, p->mapsLast, a);
+    }
+}
+template <int KS, int NT> static cudaError_t admm_sw2_attr() {
+    if constexpr (admm_sw2_ok(KS)) {
+        cudaError_t e = cudaFuncSetAttribute(k_admm<KS, NT, false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AdmmCfg<KS, NT, 1, 2>::kSmem);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(k_admm<KS, NT, true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AdmmCfg<KS, NT, 1, 2>::kSmem);
+    }
+    return cudaSuccess;
+}
+
 // The fused iteration kernel (TMA in / DMMA / TMA out); also leaves the next X1*F' partials in partF.
 static int launch_admm(tritd_problem* p) {
     tritd_ctx* c = p->ctx;
@@ -485,11 +504,12 @@ static int launch_admm(tritd_problem* p) {
     memset(&a.inv, 0, sizeof(a.inv));
     if (p->pre_inv) fill_ridge_job(p, 0, a.inv);
     a.R = p->R;
-    a.inv_stages = (int)std::ceil(0.27 * p->R / (p->jgp == 1 ? 1.7 : 3.3));     // ~0.27 us per column vs ~3.3 us per two-group stage
+    a.inv_stages = (int)std::ceil(0.27 * p->R / (p->jgp == 1 && p->swA == 1 ? 1.7 : 3.3));     // ~0.27 us per column vs ~3.3 us per 64 KB stage
     a.cta_tab = p->ctaTab; a.part_slots = p->partSlots; a.dbg = p->dbgA;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc; a.tile_h = p->tileH;
 #define CALL(NT_, KS_)                                                                                                       \
-    if (p->masked && p->jgp == 1) k_admm<KS_, NT_, true, 1><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream>>>(p->maps, p->mapsLast, a);  \
+    if (p->swA == 2) launch_admm_sw2<KS_, NT_>(p, a);                                                                         \
+    else if (p->masked && p->jgp == 1) k_admm<KS_, NT_, true, 1><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream>>>(p->maps, p->mapsLast, a);  \
     else if (p->masked) k_admm<KS_, NT_, true, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream>>>(p->maps, p->mapsLast, a);  \
     else if (p->jgp == 1) k_admm<KS_, NT_, false, 1><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream>>>(p->maps, p->mapsLast, a); \
     else k_admm<KS_, NT_, false, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream>>>(p->maps, p->mapsLast, a);
@@ -538,8 +558,8 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
     switch (src) {
         case kSrcDirect: a.v = rhs_direct; a.stride = 0; a.count = 1; break;
         case kSrcPartF:
-            a.v = p->partF; a.stride = 128 * RS; a.count = p->partSlots; a.tile_cnt = p->tileCnt;
-            a.tile_h = p->tileH; a.tile_stride = (long)p->partSlots * 128 * RS; a.wpr = 8;
+            a.v = p->partF; a.stride = 128 * p->swA * RS; a.count = p->partSlots; a.tile_cnt = p->tileCnt;
+            a.tile_h = p->tileH; a.tile_stride = (long)p->partSlots * 128 * p->swA * RS; a.wpr = 8;
             break;
         case kSrcPB: a.v = p->P; a.stride = (long)p->n2 * RS; a.count = p->n3; a.w = p->C3; a.wstride = RS; a.wpr = 8; break;
         case kSrcPC: a.v = p->P; a.stride = RS; a.count = p->n2; a.row_stride = (long)p->n2 * RS; a.w = p->B2; a.wstride = RS; a.wpr = 8; break;
@@ -741,31 +761,40 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
     p->RS = (p->R + 7) / 8 * 8;
     const RankCfg rc = rank_cfg(r);
     p->NT = rc.NT; p->KS = rc.KS;
-    // Leading dimension: a multiple of 16 rows (padded rows exist and stay zero: TMA views the rows as (16, ld1/16)),
-    // and DRAM-friendly: measured on B200 (profiles/r02_tile_experiments.md), the streaming kernels run 7-10 % faster when
-    // every column starts on a 2 KB boundary (ld1 a multiple of 256 rows... of 128 rows suffices for 128-row tiles)
-    // than on a 128-byte one, with 256-byte alignment (multiples of 32 rows) in between -- the 1 KB column chunks
-    // of an i-tile then never straddle a DRAM interleave block.  So: round up to 128 rows when that costs <= 1/8
-    // extra memory, else to 32 rows.
-    p->ld1 = (p->n1 + 15) & ~15;
-    {
-        const int l128 = (p->n1 + 127) & ~127, l32 = (p->n1 + 31) & ~31;
-        if ((l128 - p->n1) * 8 <= p->n1) p->ld1 = l128;
-        else if ((l32 - p->n1) * 8 <= p->n1) p->ld1 = l32;
-    }
-    if (const char* e = getenv("TRITD_LD1")) p->ld1 = std::max((p->n1 + 15) & ~15, atoi(e) & ~15);
-    p->ldt = p->ld1;
-    p->Np = (size_t)p->ld1 * p->n2 * p->n3;
     p->n_it = (p->n1 + 127) / 128;
     p->n_jc = (p->n2 + kBoxRows - 1) / kBoxRows;
+    const int nwr_ = (p->n1 + 15) / 16;                      // 16-row strips
     // k_admm stage size: two 8-column groups per stage, except on small slabs (few stages per CTA), where the finer
     // one-group stages balance the CTAs better and keep more loads in flight during the short kernel
     {
-        const int nwr_ = (p->n1 + 15) / 16, nit_ = (nwr_ + 7) / 8;
+        const int nit_ = (nwr_ + 7) / 8;
         const long stages2 = (long)p->n_jc * p->n3 * 2 / std::max(1, c->num_sms / nit_);
         p->jgp = stages2 < 24 ? 1 : 2;
     }
     if (const char* e = getenv("TRITD_ADMM_JG")) p->jgp = atoi(e) == 1 ? 1 : 2;
+    // Two strips per consumer warp (AdmmCfg::SW): 12..15 strips (192..240 rows) become ONE i-tile whose boxes cover whole
+    // columns, instead of a full and a shallower 128-row tile.  Needs 64 KB stages worth having (large slab) and
+    // fragments of two strips that fit the register file (r <= 5, admm_sw2_ok).  Measured (profiles/r02_sw_experiments.md):
+    // 240 rows 257.7 -> 248 us, 208 rows 243 -> 230 us, 192 rows 228 -> 218 us; 256 rows (two full tiles) and
+    // tensors of several uneven tiles (300 rows) are faster with one strip per warp.
+    p->swA = (p->jgp == 2 && r <= 5 && nwr_ >= 12 && nwr_ <= 15) ? 2 : 1;
+    if (const char* e = getenv("TRITD_ADMM_SW")) p->swA = (atoi(e) == 2 && r <= 5) ? 2 : 1;
+    if (p->swA == 2) p->jgp = 1;
+    // Leading dimension: a multiple of 16 rows (padded rows exist and stay zero: TMA views the rows as (16, ld1/16)).
+    // One-tile layout (swA == 2): dense, so that a box of 8 whole columns is one contiguous run in HBM.  Otherwise
+    // DRAM-friendly for 128-row tiles: measured on B200 (profiles/r02_tile_experiments.md), the streaming kernels run
+    // 7-10 % faster when every column starts on a 2 KB boundary than on a 128-byte one, with 256-byte alignment
+    // (multiples of 32 rows) in between -- the 1 KB column chunks of an i-tile then never straddle a DRAM interleave
+    // block.  So: round up to 128 rows when that costs <= 1/8 extra memory, else to 32 rows.
+    p->ld1 = 16 * nwr_;
+    if (p->swA == 1) {
+        const int l128 = (p->n1 + 127) & ~127, l32 = (p->n1 + 31) & ~31;
+        if ((l128 - p->n1) * 8 <= p->n1) p->ld1 = l128;
+        else if ((l32 - p->n1) * 8 <= p->n1) p->ld1 = l32;
+    }
+    if (const char* e = getenv("TRITD_LD1")) p->ld1 = std::max(16 * nwr_, atoi(e) & ~15);
+    p->ldt = p->ld1;
+    p->Np = (size_t)p->ld1 * p->n2 * p->n3;
 
     int s = TRITD_OK;
     auto bail = [&](int code) { tritd_problem_destroy(p); return code; };
@@ -823,13 +852,13 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
         // CTAs in proportion to its measured stage time was tried and lost: 284 vs 267 us on 240 x 320 x 300,
         // profiles/r02_tile_experiments.md.)
         const int nwr = (p->n1 + 15) / 16;
-        p->nitA = (nwr + 7) / 8;
+        p->nitA = (nwr + 8 * p->swA - 1) / (8 * p->swA);
         p->tileH = 16 * ((nwr + p->nitA - 1) / p->nitA);
         std::vector<int> per(p->nitA, std::max(c->num_sms / p->nitA, 1));
         p->gridA = 0; p->partSlots = 0;
         for (int x : per) { p->gridA += x; p->partSlots = std::max(p->partSlots, x); }
         if (solver) {
-            PALLOC(partF, (size_t)p->nitA * p->partSlots * 128 * p->RS);
+            PALLOC(partF, (size_t)p->nitA * p->partSlots * 128 * p->swA * p->RS);
             PALLOC(ctaTab, 3 * p->gridA);
             PALLOC(tileCnt, p->nitA);
             std::vector<int> tab(3 * p->gridA);
@@ -864,7 +893,8 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
     CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                 (int)AdmmCfg<KS_, NT_, 2>::kSmem));                                               \
     CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                (int)AdmmCfg<KS_, NT_, 1>::kSmem));
+                                (int)AdmmCfg<KS_, NT_, 1>::kSmem));                                               \
+    CU_TRY((admm_sw2_attr<KS_, NT_>()));
             TRITD_DISPATCH_R(r, CALL)
 #undef CALL
             const int usm = (int)upd_smem_bytes(p->RS);
@@ -904,7 +934,7 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
         int jgroups = 1;
         {
             auto q = [&]() -> int {
-#define CALL(NT_, KS_) jgroups = p->jgp == 1 ? AdmmCfg<KS_, NT_, 1>::JG : AdmmCfg<KS_, NT_, 2>::JG;
+#define CALL(NT_, KS_) jgroups = p->swA == 2 ? AdmmCfg<KS_, NT_, 1, 2>::JG : p->jgp == 1 ? AdmmCfg<KS_, NT_, 1>::JG : AdmmCfg<KS_, NT_, 2>::JG;
                 TRITD_DISPATCH_R(r, CALL)
 #undef CALL
                 return TRITD_OK;
