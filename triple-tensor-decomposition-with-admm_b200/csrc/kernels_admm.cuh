@@ -293,24 +293,14 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
 
         const long u_end = nq > 0 ? (q1 - 1) / SPU + 1 : u0;
         for (long u = u0; u < u_end; ++u) {
-            if (Cfg::kShareB) {
-                // large R: ONE chunk serves both contractions, pre-scaled with the slice's C3 row once per unit:
-                // BC[k][j] = B2(j,k) * C3(t,k) is the B operand of L (K = k) and of the MTTKRP (N = k) alike, so
-                // neither multiplies per use (64 FP64 multiplies per lane and stage less on the shared FP64 pipe)
+            if (jc != cur_jc) {             // uniform over the consumers: all walk the same sequence
                 asm volatile("bar.sync 1, %0;" ::"r"(nthr));
-                for (int e = threadIdx.x; e < NT * 8 * 32; e += nthr) {
-                    const int j = e / (NT * 8), k = e - j * (NT * 8);
-                    const int jj = jc * 32 + j;
-                    B2T[k * kPJ + j] = (jj < a.n2) ? a.B2[(size_t)jj * a.RS + k] * __ldg(a.C3 + (size_t)t * a.RS + k) : 0.0;
-                }
-                asm volatile("bar.sync 1, %0;" ::"r"(nthr));
-            } else if (jc != cur_jc) {             // uniform over the consumers: all walk the same sequence
-                asm volatile("bar.sync 1, %0;" ::"r"(nthr));
-                for (int e = threadIdx.x; e < 32 * 4 * KS; e += nthr) {
-                    const int j = e / (4 * KS), k = e - j * (4 * KS);
-                    const int jj = jc * 32 + j;
-                    B2s[j * PL + k] = (jj < a.n2) ? a.B2[(size_t)jj * a.RS + k] : 0.0;
-                }
+                if (!Cfg::kShareB)
+                    for (int e = threadIdx.x; e < 32 * 4 * KS; e += nthr) {
+                        const int j = e / (4 * KS), k = e - j * (4 * KS);
+                        const int jj = jc * 32 + j;
+                        B2s[j * PL + k] = (jj < a.n2) ? a.B2[(size_t)jj * a.RS + k] : 0.0;
+                    }
                 for (int e = threadIdx.x; e < NT * 8 * 32; e += nthr) {
                     const int j = e / (NT * 8), k = e - j * (NT * 8);
                     const int jj = jc * 32 + j;
@@ -337,9 +327,9 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
                         }
                     }
                 }
-                double c3s[NT];                              // column scales of the MTTKRP B fragments (1 when the chunk is pre-scaled)
+                double c3s[NT];                              // column scales of the MTTKRP B fragments
 #pragma unroll
-                for (int n = 0; n < NT; ++n) c3s[n] = Cfg::kShareB ? 1.0 : c3row[8 * n + g];
+                for (int n = 0; n < NT; ++n) c3s[n] = c3row[8 * n + g];
                 double2* s2 = reinterpret_cast<double2*>(st);
                 // the JG column groups (and the NS strips) of a stage are independent: one basic block, so their
                 // DMMA and element-wise dependency chains interleave
@@ -353,7 +343,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
                         double b = Cfg::kShareB ? B2T[(4 * ks + tig) * kPJ + jg * 8 + g] : B2s[(jg * 8 + g) * PL + 4 * ks + tig];
-                        if (!kFoldA && !Cfg::kShareB) b *= c3row[4 * ks + tig];
+                        if (!kFoldA) b *= c3row[4 * ks + tig];
 #pragma unroll
                         for (int h2 = 0; h2 < NS; ++h2) {
                             if (kFoldA) {
@@ -388,7 +378,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
 #pragma unroll
                     for (int n = 0; n < NT; ++n) {
                         const double2 b = *reinterpret_cast<const double2*>(B2T + (8 * n + g) * kPJ + jg * 8 + 2 * tig);
-                        const double b0 = Cfg::kShareB ? b.x : b.x * c3s[n], b1 = Cfg::kShareB ? b.y : b.y * c3s[n];
+                        const double b0 = b.x * c3s[n], b1 = b.y * c3s[n];
 #pragma unroll
                         for (int h2 = 0; h2 < NS; ++h2) {
                             dmma884(acc[h2][0][n][0], acc[h2][0][n][1], tn[h2][0].x, b0);

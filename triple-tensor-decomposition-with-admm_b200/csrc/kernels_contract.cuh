@@ -290,7 +290,10 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
     }
     int s = 0; uint32_t ph = 0;
     const int rg = rho8(g);
-    const int bw = warp & (kCW - 1), mh = warp >> 3;      // row block of the pass, half of its 32 rows (m-tiles 2mh, 2mh+1)
+    // Row block of the pass and half of its 32 rows (m-tiles 2mh, 2mh+1): warps 2b and 2b+1 share block b, so the valid
+    // blocks of a partial pass spread over the four schedulers (5 blocks: 3+3+2+2 warps, 3/4 of a full pass's DMMA time;
+    // with blocks b and b+8... on one scheduler a 5-block pass cost as much as a full one)
+    const int bw = warp >> 1, mh = warp & 1;
     for (long u = 0; u < npass; ++u) {
         const long rb = rbA + u * kCW + bw;
         const bool valid = rb < rbB;
