@@ -225,7 +225,14 @@ __host__ __device__ constexpr int ppass_stages(int NT) {
     return (220 * 1024) / (kCW * kBoxBytes + NT * 8 * 128) > 6 ? 6 : (220 * 1024) / (kCW * kBoxBytes + NT * 8 * 128);
 }
 
-template <int NT>
+// R = 8 (NT - 1) + 1 (r = 3, 5, 7): the last n-tile would hold ONE real column.  That column is formed with scalar DFMA
+// from the A fragments already in registers (8 DFMA instead of 8 DMMA per warp and stage: 16 instead of 128 cycles of
+// the shared FP64 pipe) and reduced over the quad at the end of the pass: a quarter less DMMA work at r = 5.
+__host__ __device__ constexpr bool ppass_scalar_col(int NT, int KS) {
+    return (NT == 2 && KS == 3) || (NT == 4 && KS == 7) || (NT == 7 && KS == 13);
+}
+
+template <int NT, bool SC = false>
 __global__ void __launch_bounds__((kPW + 1) * 32, 1)
 k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapA1T, const PpassArgs a) {
     if (*a.stop) return;
@@ -297,11 +304,13 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
     for (long u = 0; u < npass; ++u) {
         const long rb = rbA + u * kCW + bw;
         const bool valid = rb < rbB;
-        double acc[2][NT][2];
+        constexpr int NTD = SC ? NT - 1 : NT;             // n-tiles formed with DMMA
+        double acc[2][NTD][2];
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
-            for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+            for (int n = 0; n < NTD; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+        double sacc[2] = {0.0, 0.0};                      // SC: this lane's share of column 8 * NTD for its two rows
 
         for (int kc = 0; kc < nkc; ++kc) {
             mbar_wait(&full[s], ph);
@@ -316,13 +325,18 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
 #pragma unroll
                     for (int m = 0; m < 2; ++m) af[m] = lds_swz128(box, 8 * (2 * mh + m) + rg, 4 * h + tig);
 #pragma unroll
-                    for (int n = 0; n < NT; ++n) {
+                    for (int n = 0; n < NTD; ++n) {
                         const double2 b = lds_swz128(fbox, 8 * n + rg, 4 * h + tig);
 #pragma unroll
                         for (int m = 0; m < 2; ++m) {
                             dmma884(acc[m][n][0], acc[m][n][1], af[m].x, b.x);
                             dmma884(acc[m][n][0], acc[m][n][1], af[m].y, b.y);
                         }
+                    }
+                    if (SC) {
+                        const double2 b = lds_swz128(fbox, 8 * NTD, 4 * h + tig);     // A1(i, 8 NTD) for this lane's two i
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) sacc[m] = fma(af[m].y, b.y, fma(af[m].x, b.x, sacc[m]));
                     }
                 }
             }
@@ -339,10 +353,26 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
                 if (j < a.n2) {
                     double* p = a.P + ((size_t)t * a.n2 + j) * a.RS;
 #pragma unroll
-                    for (int n = 0; n < NT; ++n) {
+                    for (int n = 0; n < NTD; ++n) {
                         p[8 * n + tig] = acc[m][n][0];
                         p[8 * n + tig + 4] = acc[m][n][1];
                     }
+                }
+            }
+        }
+        if (SC) {             // (all lanes take part in the shuffles; rows of an invalid block hold zeros)
+            const int t = valid ? (int)(rb / a.n_jb) : 0, jb = valid ? (int)(rb - (long)t * a.n_jb) : 0;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                double v = sacc[m];
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                const int j = jb * kBoxRows + 8 * (2 * mh + m) + rg;
+                // columns 8 NTD + 1 .. RS - 1 are padding: zero (the update kernels read whole rows)
+                if (valid && j < a.n2) {
+                    double* p = a.P + ((size_t)t * a.n2 + j) * a.RS + 8 * NTD;
+                    p[tig] = tig == 0 ? v : 0.0;
+                    p[tig + 4] = 0.0;
                 }
             }
         }

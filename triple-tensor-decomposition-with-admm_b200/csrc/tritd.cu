@@ -447,7 +447,7 @@ static int launch_ppass(tritd_problem* p, const CUtensorMap& mapT, bool with_inv
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS;
     a.n_jb = p->n_jc; a.n_rb = (long)p->n3 * p->n_jc; a.units = p->unitsP;
 #define CALL(NT_, KS_) \
-    k_ppass<NT_><<<p->gridP, (kPW + 1) * 32, p->smemP, c->stream>>>(mapT, p->mapA1T, a);
+    k_ppass<NT_, ppass_scalar_col(NT_, KS_)><<<p->gridP, (kPW + 1) * 32, p->smemP, c->stream>>>(mapT, p->mapA1T, a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
     CU_TRY(cudaGetLastError());
@@ -885,7 +885,7 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
         auto q = [&]() -> int {
 #define CALL(NT_, KS_)                                                                                            \
     CU_TRY(cudaFuncSetAttribute(k_mttkrp1<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemM));    \
-    CU_TRY(cudaFuncSetAttribute(k_ppass<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemP));      \
+    CU_TRY(cudaFuncSetAttribute(k_ppass<NT_, ppass_scalar_col(NT_, KS_)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smemP));      \
     CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                 (int)AdmmCfg<KS_, NT_, 2>::kSmem));                                               \
     CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
