@@ -24,6 +24,15 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // 16-byte bank groups: rho = {0,4,1,5,2,6,3,7}.
 __device__ __forceinline__ int rho8(int g) { return (g >> 1) | ((g & 1) << 2); }
 
+// Programmatic dependent launch: the kernels of the iteration are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs become resident and run their
+// prologue (barrier set-up, descriptor prefetch) while this grid drains.  pdl_wait() returns once every grid this one
+// depends on has completed and its memory is visible (a no-op for a plainly launched kernel); EVERY thread calls it
+// before it reads anything an earlier kernel wrote and before it exits, so completion stays transitive along the
+// chain.  pdl_trigger() lets the dependents be scheduled; they still wait for this grid's completion themselves.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------
 // shared-memory addresses, mbarrier, TMA
 // ---------------------------------------------------------------------------

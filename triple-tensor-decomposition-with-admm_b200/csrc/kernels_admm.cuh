@@ -161,8 +161,6 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
     // would not fit the register file)
     constexpr bool kFoldA = KS <= 8 && SW == 1;
     constexpr int kPartH = 128 * SW;      // rows of a CTA's X1*F' partial
-    if (a.st->stop) return;
-    const int k_start = a.st->k;          // iteration index of this launch (the last CTA advances it at the very end)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);              // [S][NB boxes + C3 row]
     double* B2s = ring + (size_t)S * kStageD;                        // [32 j][PL]      B-operand of L
@@ -196,15 +194,19 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], nact); }
         mbar_fence_init();
         if (a.dbg) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.dbg[2 * blockIdx.x] = t_; }
+        tma_prefetch_desc(&maps.D); tma_prefetch_desc(&maps.YL); tma_prefetch_desc(&maps.E);
+        tma_prefetch_desc(&maps.YO); tma_prefetch_desc(&maps.T);
     }
     __syncthreads();
+    pdl_wait();                           // everything above overlapped the tail of the previous kernel
+    pdl_trigger();
+    if (a.st->stop) return;
+    const int k_start = a.st->k;          // iteration index of this launch (the last CTA advances it at the very end)
 
     if (warp >= 8) {
         // ---------------- TMA warpgroup: loads, stores, slot recycling ----------------
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == 8 && lane == 0 && nq > 0) {
-            tma_prefetch_desc(&maps.D); tma_prefetch_desc(&maps.YL); tma_prefetch_desc(&maps.E);
-            tma_prefetch_desc(&maps.YO); tma_prefetch_desc(&maps.T);
             int ljc = jc0, lt = t0, ljg = sg0, ls = 0;               // load cursor
             auto issue_load = [&]() {
                 double* st = ring + (size_t)ls * kStageD;

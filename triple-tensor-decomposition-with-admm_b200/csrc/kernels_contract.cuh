@@ -235,7 +235,6 @@ __host__ __device__ constexpr bool ppass_scalar_col(int NT, int KS) {
 template <int NT, bool SC = false>
 __global__ void __launch_bounds__((kPW + 1) * 32, 1)
 k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapA1T, const PpassArgs a) {
-    if (*a.stop) return;
     constexpr int kStageDoubles = kCW * (kBoxBytes / 8) + NT * 8 * 16;
     constexpr int kStages = ppass_stages(NT);       // (shadows the 4 of k_mttkrp1)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -256,15 +255,18 @@ k_ppass(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtens
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kPW); }
         mbar_fence_init();
+        tma_prefetch_desc(&mapT); tma_prefetch_desc(&mapA1T);
     }
     __syncthreads();
+    pdl_wait();                          // everything above overlapped the tail of the previous kernel
+    pdl_trigger();
+    if (*a.stop) return;
 
     if (warp == kPW) {
         // Producer warp: lane w < 8 owns slot w of every stage (its row block's (t, jb) is worked out once per pass, not
         // once per chunk), lane 8 the factor box; lane 0 waits for the slot and arms the barrier, then the nine lanes
         // issue their TMA loads side by side -- one thread doing all of it (eight 64-bit divisions and nine issues
         // per stage) was the slowest link of the kernel.
-        if (lane == 0) { tma_prefetch_desc(&mapT); tma_prefetch_desc(&mapA1T); }
         int s = 0; uint32_t ph = 0;
         for (long u = 0; u < npass; ++u) {
             const long rb0 = rbA + u * kCW;

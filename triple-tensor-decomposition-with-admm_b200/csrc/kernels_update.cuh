@@ -468,6 +468,8 @@ __host__ __device__ inline size_t upd_smem_bytes(int RS) {
 
 template <int PQ>   // ceil(R / 16): the register patch of the inversion; also fixes the columns per lane (1 for RS <= 32, else 2)
 __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
+    pdl_wait();
+    pdl_trigger();
     if (a.st->stop) return;
     constexpr int KPL = PQ <= 2 ? 1 : 2;
     constexpr int CH = 8;                         // independent accumulation chains (= loads in flight) per lane and column

@@ -361,6 +361,7 @@ struct tritd_problem {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;    // TRITD_NPHASE + 1 events per profiled iteration
     cudaGraphExec_t graph = nullptr;     // one steady-state iteration, captured once and replayed
+    cudaGraphExec_t graphN = nullptr;    // kGraphBatch iterations in one graph
     int graph_launches = 0;              // kernels inside the graph
     bool graph_off = false;              // capture failed or TRITD_NO_GRAPH set: plain launches
     std::vector<void*> allocs;
@@ -412,6 +413,22 @@ static int make_map(tritd_ctx* c, CUtensorMap* map, void* base, int rank, const 
         default: return fail(TRITD_ERR_UNSUPPORTED, "r=%d unsupported (1..%d)", r, TRITD_MAX_R); \
     }
 
+// Launch of an iteration kernel.  TRITD_PDL=1: programmatic dependent launch (common.cuh, pdl_wait) -- the kernel may
+// become resident while the previous kernel of the stream drains; inside a captured graph this becomes a programmatic
+// edge.  Measured on B200 it LOSES 2.5-3.5 us per iteration against plain graph edges (cfg3 350.1 vs 341.6 us,
+// 240 x 320 x 38: 92.1 vs 88.7 us; profiles/r02_pdl.log): the gaps between graph nodes are already ~1 us.  Off by default.
+static bool g_pdl = getenv("TRITD_PDL") != nullptr;
+template <typename... KA, typename... A>
+static cudaError_t launch_k(void (*kern)(KA...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
+
 static size_t smem_mttkrp1(int NT) { return (size_t)kStages * kCW * kBoxBytes + (size_t)NT * 8 * kPJ * 8 + 2 * kStages * 8; }
 static size_t smem_ppass(int NT) { return (size_t)ppass_stages(NT) * (kCW * kBoxBytes + NT * 8 * 128) + 2 * ppass_stages(NT) * 8; }
 
@@ -447,7 +464,7 @@ static int launch_ppass(tritd_problem* p, const CUtensorMap& mapT, bool with_inv
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS;
     a.n_jb = p->n_jc; a.n_rb = (long)p->n3 * p->n_jc; a.units = p->unitsP;
 #define CALL(NT_, KS_) \
-    k_ppass<NT_, ppass_scalar_col(NT_, KS_)><<<p->gridP, (kPW + 1) * 32, p->smemP, c->stream>>>(mapT, p->mapA1T, a);
+    CU_TRY(launch_k(k_ppass<NT_, ppass_scalar_col(NT_, KS_)>, p->gridP, (kPW + 1) * 32, p->smemP, c->stream, mapT, p->mapA1T, a));
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
     CU_TRY(cudaGetLastError());
@@ -477,8 +494,8 @@ constexpr bool admm_sw2_ok(int KS) { return KS <= 8; }
 template <int KS, int NT> static void launch_admm_sw2(tritd_problem* p, const AdmmArgs& a) {
     if constexpr (admm_sw2_ok(KS)) {
         cudaStream_t st = p->ctx->stream;
-        if (p->masked) k_admm<KS, NT, true, 1, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS, NT, 1, 2>::kSmem, st>>>(p->maps, p->mapsLast, a);
-        else k_admm<KS, NT, false, 1, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS, NT, 1, 2>::kSmem, st>>>(p->maps, p->mapsLast, a);
+        if (p->masked) launch_k(k_admm<KS, NT, true, 1, 2>, p->gridA, kAdmmThreads, AdmmCfg<KS, NT, 1, 2>::kSmem, st, p->maps, p->mapsLast, a);
+        else launch_k(k_admm<KS, NT, false, 1, 2>, p->gridA, kAdmmThreads, AdmmCfg<KS, NT, 1, 2>::kSmem, st, p->maps, p->mapsLast, a);
     }
 }
 template <int KS, int NT> static cudaError_t admm_sw2_attr() {
@@ -509,10 +526,10 @@ static int launch_admm(tritd_problem* p) {
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc; a.tile_h = p->tileH;
 #define CALL(NT_, KS_)                                                                                                       \
     if (p->swA == 2) launch_admm_sw2<KS_, NT_>(p, a);                                                                         \
-    else if (p->masked && p->jgp == 1) k_admm<KS_, NT_, true, 1><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream>>>(p->maps, p->mapsLast, a);  \
-    else if (p->masked) k_admm<KS_, NT_, true, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream>>>(p->maps, p->mapsLast, a);  \
-    else if (p->jgp == 1) k_admm<KS_, NT_, false, 1><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream>>>(p->maps, p->mapsLast, a); \
-    else k_admm<KS_, NT_, false, 2><<<p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream>>>(p->maps, p->mapsLast, a);
+    else if (p->masked && p->jgp == 1) launch_k(k_admm<KS_, NT_, true, 1>, p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream, p->maps, p->mapsLast, a);  \
+    else if (p->masked) launch_k(k_admm<KS_, NT_, true, 2>, p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream, p->maps, p->mapsLast, a);  \
+    else if (p->jgp == 1) launch_k(k_admm<KS_, NT_, false, 1>, p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream, p->maps, p->mapsLast, a); \
+    else launch_k(k_admm<KS_, NT_, false, 2>, p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream, p->maps, p->mapsLast, a);
     TRITD_DISPATCH_R(p->r, CALL)
 #undef CALL
     CU_TRY(cudaGetLastError());
@@ -610,10 +627,10 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
     const unsigned grid = (unsigned)((n + rows - 1) / rows + 1);
     a.gram_cap = (int)grid <= p->upd_wave ? (int)grid : kUpdMaxGramCtas;
     switch ((p->R + 15) / 16) {
-        case 1: k_upd<1><<<grid, kUpdThreads, sm, c->stream>>>(a); break;
-        case 2: k_upd<2><<<grid, kUpdThreads, sm, c->stream>>>(a); break;
-        case 3: k_upd<3><<<grid, kUpdThreads, sm, c->stream>>>(a); break;
-        default: k_upd<4><<<grid, kUpdThreads, sm, c->stream>>>(a); break;
+        case 1: launch_k(k_upd<1>, grid, kUpdThreads, sm, c->stream, a); break;
+        case 2: launch_k(k_upd<2>, grid, kUpdThreads, sm, c->stream, a); break;
+        case 3: launch_k(k_upd<3>, grid, kUpdThreads, sm, c->stream, a); break;
+        default: launch_k(k_upd<4>, grid, kUpdThreads, sm, c->stream, a); break;
     }
     CU_TRY(cudaGetLastError());
     c->launches += 1;
@@ -733,6 +750,7 @@ extern "C" void tritd_problem_destroy(tritd_problem* p) {
     for (void* q : p->allocs) cudaFree(q);
     for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
     if (p->graph) cudaGraphExecDestroy(p->graph);
+    if (p->graphN) cudaGraphExecDestroy(p->graphN);
     if (p->st_host) cudaFreeHost(p->st_host);
     if (p->poll) { cudaFreeHost(p->poll); cudaEventDestroy(p->poll_ev[0]); cudaEventDestroy(p->poll_ev[1]); }
     delete p;
@@ -1134,7 +1152,8 @@ static int problem_init_finish(tritd_problem* p) {
     p->rhsA_ready = false;
     p->pre_inv = !(c->nranks > 1 && !p->xchg) && !getenv("TRITD_NO_PREINV");       // (NCCL path: C3'C3 arrives only with update A's all-reduce)
     p->graph_off = getenv("TRITD_NO_GRAPH") != nullptr;
-    if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }     // opts (lambda2) are baked into the graph
+    if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }     // opts (lambda2) are baked into the graphs
+    if (p->graphN) { cudaGraphExecDestroy(p->graphN); p->graphN = nullptr; }
     p->printed_k = 0;
     return TRITD_OK;
 }
@@ -1225,36 +1244,49 @@ extern "C" int tritd_debug_admm_stamps(tritd_problem* p, long long* out, int* ta
     return p->gridA;
 }
 
-// One iteration: the first one (and profiled ones) as plain launches, every later one as a replay of a CUDA graph
-// captured from the very same enqueue_iteration() -- all iteration state lives in device memory, so the graph
-// needs no parameter updates -- which removes the launch gaps between the ~9 small dependent kernels.
-static int run_iteration(tritd_problem* p) {
+constexpr int kGraphBatch = 10;      // iterations per replayed graph (the cadence of the host's look at the stopping rule)
+static int capture_graph(tritd_problem* p, int iters, cudaGraphExec_t* out, bool* failed) {
+    tritd_ctx* c = p->ctx;
+    const int64_t l0 = c->launches;
+    cudaGraph_t g = nullptr;
+    *failed = true;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return TRITD_OK; }
+    int s = TRITD_OK;
+    for (int i = 0; i < iters && s == TRITD_OK; ++i) s = enqueue_iteration(p);
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    p->graph_launches = (int)((c->launches - l0) / iters);
+    c->launches = l0;
+    if (s != TRITD_OK || e != cudaSuccess || !g || cudaGraphInstantiate(out, g, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (g) cudaGraphDestroy(g);
+        *out = nullptr;
+        return TRITD_OK;
+    }
+    cudaGraphDestroy(g);
+    *failed = false;
+    return TRITD_OK;
+}
+
+// `n` iterations: the first one (and profiled ones) as plain launches, every later one as a replay of a CUDA graph
+// captured from the very same enqueue_iteration() -- all iteration state lives in device memory, so the graphs
+// need no parameter updates.  Whole batches of kGraphBatch iterations replay ONE graph, inside which every kernel is
+// a programmatic dependent of its predecessor (also across the iteration boundary).
+static int run_iterations(tritd_problem* p, int n) {
     tritd_ctx* c = p->ctx;
     if (c->inproc) CU_TRY(cudaSetDevice(c->device));      // members of a group are driven by one host thread
-    if (p->profiling || !p->rhsA_ready || p->graph_off) return enqueue_iteration(p);
-    if (!p->graph) {
-        const int64_t l0 = c->launches;
-        cudaGraph_t g = nullptr;
-        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-            cudaGetLastError();
-            p->graph_off = true;
-            return enqueue_iteration(p);
+    while (n > 0) {
+        if (p->profiling || !p->rhsA_ready || p->graph_off) { ST_TRY(enqueue_iteration(p)); --n; continue; }
+        const bool batch = n >= kGraphBatch;
+        cudaGraphExec_t& ge = batch ? p->graphN : p->graph;
+        if (!ge) {
+            bool failed = false;
+            ST_TRY(capture_graph(p, batch ? kGraphBatch : 1, &ge, &failed));
+            if (failed) { p->graph_off = true; continue; }
         }
-        const int s = enqueue_iteration(p);
-        const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-        p->graph_launches = (int)(c->launches - l0);
-        c->launches = l0;
-        if (s != TRITD_OK || e != cudaSuccess || !g || cudaGraphInstantiate(&p->graph, g, 0) != cudaSuccess) {
-            cudaGetLastError();
-            if (g) cudaGraphDestroy(g);
-            p->graph = nullptr;
-            p->graph_off = true;
-            return enqueue_iteration(p);
-        }
-        cudaGraphDestroy(g);
+        CU_TRY(cudaGraphLaunch(ge, c->stream));
+        c->launches += (int64_t)p->graph_launches * (batch ? kGraphBatch : 1);
+        n -= batch ? kGraphBatch : 1;
     }
-    CU_TRY(cudaGraphLaunch(p->graph, c->stream));
-    c->launches += p->graph_launches;
     return TRITD_OK;
 }
 
@@ -1297,8 +1329,7 @@ static int fetch_state(tritd_problem* p) {
 extern "C" int tritd_problem_enqueue(tritd_problem* p, int32_t n) {
     if (!p || !p->initialized) return fail(TRITD_ERR_INVALID, "problem not initialised");
     CU_TRY(cudaSetDevice(p->ctx->device));
-    for (int i = 0; i < n; ++i) ST_TRY(run_iteration(p));
-    return TRITD_OK;
+    return run_iterations(p, n);
 }
 
 extern "C" int tritd_problem_sync(tritd_problem* p) {
@@ -1358,8 +1389,10 @@ static int iterate_many(const std::vector<tritd_problem*>& ps, int32_t max_more,
     };
     while (remaining > 0 && !p->st_host->stop) {
         const int batch = std::min(remaining, 10 - k_enq % 10);
-        for (int i = 0; i < batch; ++i)
-            for (tritd_problem* q : ps) ST_TRY(run_iteration(q));
+        if (ps.size() == 1) ST_TRY(run_iterations(p, batch));
+        else
+            for (int i = 0; i < batch; ++i)               // groups: iteration by iteration across the devices
+                for (tritd_problem* q : ps) ST_TRY(run_iterations(q, 1));
         k_enq += batch; remaining -= batch;
         CU_TRY(cudaSetDevice(c->device));
         CU_TRY(cudaMemcpyAsync(&p->poll[slot], p->st, sizeof(IterState), cudaMemcpyDeviceToHost, c->stream));
