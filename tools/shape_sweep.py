@@ -22,7 +22,7 @@ def run(n1, n2, n3, r, iters=100):
     N = n1 * n2 * n3
     per = [m / n for m in ms]
     print(f"{n1}x{n2}x{n3} r={r}: " + " ".join(f"{nm}={v*1e3:.1f}us" for nm, v in zip(tritd.PHASES, per)) +
-          f" | total={sum(per)*1e3:.1f}us fused={64*N/per[4]*1e-6:.0f}GB/s ppass={8*N/per[2]*1e-6:.0f}GB/s", flush=True)
+          f" | total={sum(per)*1e3:.1f}us fused={48*N/per[4]*1e-6:.0f}GB/s ppass={8*N/per[2]*1e-6:.0f}GB/s", flush=True)
 
 if __name__ == "__main__":
     shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]] or [(240, 320, 300, 5)]

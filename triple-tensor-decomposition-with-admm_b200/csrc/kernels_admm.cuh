@@ -8,16 +8,23 @@
 //   :74-78   X1*F' of the NEXT iteration's update_A (mode-1 MTTKRP of the new T), accumulated
 //            from registers so T is read from HBM only once per iteration (by k_ppass).
 //
+// State kept in HBM between iterations: D, Y_L, the next target T and ONE array Z for the sparse pair (E, Y_O):
+// Z = R3 = O + (1/muO)*Y_O of the last iteration (:46).  E = soft_threshold(Z, lambda/muO) is re-derived where it is
+// needed (:47), and the dual follows from the reference's own update (:53), Y_O' = Y_O + muO*(O - E) = muO*(R3 - E) =
+// muO*(Z - E) -- an identity in exact arithmetic, so the iterates are the reference's up to a few roundings of
+// |Y_O| <= lambda per element and iteration (measured against the oracle: DESIGN 4.1).  That removes one N-sized read and
+// one N-sized write per iteration: 48 instead of 64 bytes per element.
+//
 // Structure: CTA = 8 consumer warps x 16 rows i (an i-tile of <= 128 rows) + 1 warp that drives TMA.
-// A stage is JG (1 or 2) groups of 8 columns j of slice t for the whole i-tile, i.e. four 8*JG KB boxes
-// (D, Y_L, E, Y_O) fetched by ONE TMA op each through a 4-D view (i_lo=16, j, i_hi, t) of the
+// A stage is JG (1 or 2) groups of 8 columns j of slice t for the whole i-tile, i.e. three 8*JG KB boxes
+// (D, Y_L, Z) fetched by ONE TMA op each through a 4-D view (i_lo=16, j, i_hi, t) of the
 // column-major arrays, which lands as [warp][8 j][16 i] with the 128B swizzle pattern the DMMA
 // accumulator layout reads conflict-free.  Consumers update the boxes in place (T over D; O is not stored
 // inside the loop, k_recover_O rebuilds it on demand); the TMA
 // warp then streams the boxes back with one TMA store each and refills the slot.  No thread touches HBM with a
 // load/store instruction; rows/columns outside the tensor are zero-filled on load and clipped on store by the
 // tensor maps (ld1 is a multiple of 16 so the padded rows exist and stay zero).  Algorithmic traffic:
-// 4 reads + 4 writes = 64 bytes per element.
+// 3 reads (D, Y_L, Z) + 3 writes (T', Y_L', Z') = 48 bytes per element.
 #pragma once
 #include "common.cuh"
 #include "kernels_contract.cuh"
@@ -27,7 +34,7 @@
 
 namespace tritd {
 
-struct AdmmMaps { CUtensorMap D, YL, E, YO, T, O; };
+struct AdmmMaps { CUtensorMap D, YL, Z, T, O; };
 
 struct AdmmArgs {
     const double *A1, *B2, *C3;        // [n][RS]
@@ -60,15 +67,9 @@ struct AdmmArgs {
 // JGP: column groups per stage asked for (1 or 2).  Two-group stages give every warp two independent dependency
 // chains between barriers; one-group stages are half as large, so twice as many fit the ring and twice as many loads
 // are in flight per SM -- which wins depends on the shape (chosen at problem set-up, tritd.cu).
-// SW: 16-row strips per consumer warp (1 or 2).  With two, an i-tile is up to 256 rows deep and a stage is ONE 8-column
-// group of it: the same 64 KB per stage and the same two independent chains per warp as a two-group stage.  A tensor
-// of 192..240 rows (12..15 strips) is then ONE tile whose boxes cover whole columns: with a dense leading dimension
-// (ld1 = rows) every box is one contiguous, 256-byte aligned run in HBM (8 columns x 1920 B for 240 rows) -- no pad
-// rows to drag along, no second shallower tile whose CTAs take as long as full ones (240 x 320 x 300: 257.7 -> 248 us,
-// profiles/r02_sw_experiments.md).  The B fragments of both contractions are loaded once for the two strips.
-template <int KS, int NT, int JGP = 2, int SW = 1> struct AdmmCfg {
+template <int KS, int NT, int JGP = 2> struct AdmmCfg {
     static constexpr int PL = FusedCfg<KS>::PL;
-    static constexpr int NB = 4;                                                // boxes per stage
+    static constexpr int NB = 3;                                                // boxes per stage (D, Y_L, Z)
     // large R: the B operand of L is read from the transposed chunk too (2-way bank conflict on a small share of
     // the shared-memory traffic) so that the second layout's 17 KB buy a two-group stage
     static constexpr bool kShareB = KS > 8;
@@ -76,8 +77,8 @@ template <int KS, int NT, int JGP = 2, int SW = 1> struct AdmmCfg {
     static constexpr int kAvail = 227 * 1024 - kFixed;
     // a stage holds JG groups of 8 columns: two when three such stages fit (more independent work per warp
     // between barriers), else one
-    static constexpr int JG = (JGP >= 2 && SW == 1 && (kAvail / (NB * 2 * 8 * 128 * 8 + 1024)) >= 3) ? 2 : 1;
-    static constexpr int kBoxD = 8 * SW * JG * 128;                             // doubles per array per stage: [8*SW strips][8*JG j][16 i]
+    static constexpr int JG = (JGP >= 2 && (kAvail / (NB * 2 * 8 * 128 * 8 + 1024)) >= 3) ? 2 : 1;
+    static constexpr int kBoxD = 8 * JG * 128;                                  // doubles per array per stage: [8 warps][8*JG j][16 i]
     static constexpr int kStageBytes = NB * kBoxD * 8 + 1024;                   // + the C3 row of the slice; keeps boxes 1 KB aligned
     static constexpr int S = (kAvail / kStageBytes) > 8 ? 8 : (kAvail / kStageBytes);
     static constexpr size_t kSmem = (size_t)S * kStageBytes + kFixed;
@@ -115,29 +116,37 @@ __device__ __forceinline__ double div_by(double a, double b, double y) {
 
 // One element of triple_decomp_ADMM.m:41-53 and the next T (:33); same association as the MATLAB
 // expressions, every operation an explicit round-to-nearest intrinsic (no FMA contraction).
-struct AdmmPrm { double muL, muO, rmuL, rmuO, thr, musum, rmusum, rmuL_next; };
+struct AdmmPrm { double muL, muO, rmuL, thr, musum, rmusum, rmuL_next, yo_scale, thr_prev; };
+
+// x - soft_threshold(x, thr) = x clipped to [-thr, thr]; soft_threshold(x, thr) = sign(x).*max(|x|-thr,0)
+// (soft_threshold.m:2) is then x - clip(x): the same subtraction |x| - thr for |x| > thr (negation is exact), x - x = 0
+// inside, and NaN where x is NaN (fmax / fmin drop the NaN, NaN - finite = NaN: MATLAB's sign(NaN)*0 = NaN).  Two DMNMX
+// and one DADD instead of a subtraction, a maximum, three comparisons and the selects.
+__device__ __forceinline__ double clip_thr(double x, double thr) { return fmin(fmax(x, -thr), thr); }
 
 template <bool MASKED>
-__device__ __forceinline__ void admm_point2(const AdmmPrm& p, double d, double l, double& yl, double& e, double& yo,
-                                            double& o, double& tn, double& sL, double& sO) {
+__device__ __forceinline__ void admm_point2(const AdmmPrm& p, double d, double l, double& yl, double& z, double& tn,
+                                            double& sL, double& sO) {
     if (MASKED && d != d) {              // unobserved entry (NaN in D): no constraint, impute the low-rank estimate
-        yl = 0.0; e = 0.0; yo = 0.0; o = 0.0; tn = l;
+        yl = 0.0; z = 0.0; tn = l;
         return;
     }
+    // The sparse pair of the previous iteration from Z = its R3 (:46): E = soft_threshold(R3, lambda/muO) = Z - clip(Z) (:47)
+    // and Y_O = Y_O_old + muO*(O - E) = muO*(R3 - E) = muO*clip(Z) (:53), so (1/muO')*Y_O = (muO/muO')*clip(Z).
+    // (Z = 0 before the first iteration: E = Y_O = 0.)
+    const double w = clip_thr(z, p.thr_prev);
+    const double e = __dsub_rn(z, w);
+    const double my = __dmul_rn(p.yo_scale, w);                          // (1/muO)*Y_O
     const double dl = __dsub_rn(d, l);                                   // D - L
     const double r1 = __dadd_rn(dl, __dmul_rn(p.rmuL, yl));              // R1 = D - L + (1/muL)*Y_L
-    const double my = __dmul_rn(p.rmuO, yo);                             // (1/muO)*Y_O
     const double r2 = __dsub_rn(e, my);                                  // R2 = E - (1/muO)*Y_O
-    o = div_by(__dadd_rn(__dmul_rn(p.muL, r1), __dmul_rn(p.muO, r2)), p.musum, p.rmusum);
+    const double o = div_by(__dadd_rn(__dmul_rn(p.muL, r1), __dmul_rn(p.muO, r2)), p.musum, p.rmusum);
     const double r3 = __dadd_rn(o, my);                                  // R3 = O + (1/muO)*Y_O
-    const double mx = fmax(__dsub_rn(fabs(r3), p.thr), 0.0);
-    // sign(R3).*max(|R3|-lambda/muO,0); MATLAB: sign(NaN) = NaN, max(NaN,0) = 0, NaN*0 = NaN -> E = NaN where R3 is NaN
-    const double en = r3 > 0.0 ? mx : (r3 < 0.0 ? -mx : (r3 != r3 ? r3 : 0.0));
+    const double en = __dsub_rn(r3, clip_thr(r3, p.thr));                // E = soft_threshold(R3, lambda/muO)
     const double resL = __dsub_rn(dl, o);                                // D - L - O
     const double resO = __dsub_rn(o, en);                                // O - E
     yl = __dadd_rn(yl, __dmul_rn(p.muL, resL));
-    yo = __dadd_rn(yo, __dmul_rn(p.muO, resO));
-    e = en;
+    z = r3;
     tn = __dadd_rn(__dsub_rn(d, o), __dmul_rn(p.rmuL_next, yl));         // next T = D - O + (1/muL')*Y_L
     sL = fma(resL, resL, sL);
     sO = fma(resO, resO, sO);
@@ -150,17 +159,15 @@ constexpr int kAdmmThreads = 384;
 
 // MASKED: the opt-in completion variant (tritd_admm_masked_f64): unobserved entries are stored as NaN
 // in D; there O = E = Y_L = Y_O = 0, the residuals do not count and the next target is T' = L (imputation).
-template <int KS, int NT, bool MASKED, int JGP = 2, int SW = 1>
+template <int KS, int NT, bool MASKED, int JGP = 2>
 __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant__ AdmmMaps maps_full, const __grid_constant__ AdmmMaps maps_last,
                                                           const AdmmArgs a) {
-    using Cfg = AdmmCfg<KS, NT, JGP, SW>;
+    using Cfg = AdmmCfg<KS, NT, JGP>;
     constexpr int PL = Cfg::PL, NB = Cfg::NB, S = Cfg::S, JG = Cfg::JG, kBoxD = Cfg::kBoxD;
     constexpr int kStageD = Cfg::kStageBytes / 8;
     constexpr int SPU = 4 / JG;           // stages per unit (32 columns of one slice)
-    // fold C3[t,:] into the A fragments once per slice (else into B per use; with two strips per warp the folded copy
-    // would not fit the register file)
-    constexpr bool kFoldA = KS <= 8 && SW == 1;
-    constexpr int kPartH = 128 * SW;      // rows of a CTA's X1*F' partial
+    constexpr bool kFoldA = KS <= 8;      // fold C3[t,:] into the A fragments once per slice (else into B per use)
+    constexpr int kPartH = 128;           // rows of a CTA's X1*F' partial
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);              // [S][NB boxes + C3 row]
     double* B2s = ring + (size_t)S * kStageD;                        // [32 j][PL]      B-operand of L
@@ -179,13 +186,12 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
     const long dq = (a.inv.enable && it == a.cta_tab[0]) ? a.inv_stages : 0;
     const long q0 = max(0L, (Q + dq) * x / gi - dq), q1 = max(0L, (Q + dq) * (x + 1) / gi - dq);
     const long nq = q1 - q0;
-    const int nwf = a.tile_h >> 4;                                   // 16-row strips of a full i-tile (<= 8 * SW)
-    const int nstr = min(nwf, (a.n1s - it * a.tile_h + 15) >> 4);     // ... of THIS tile (the last tile may have fewer)
-    const int nact = min(8, nstr);                                   // consumer warps with work: warp w owns strips w (and w + 8)
+    const int nwf = a.tile_h >> 4;                                   // 16-row strips (= consumer warps) of a full i-tile
+    const int nact = min(nwf, (a.n1s - it * a.tile_h + 15) >> 4);     // ... of THIS tile (the last tile may have fewer)
     // TMA box depth in i_hi = strips of this tile: the last tile has its own tensor maps, so that no box ever
     // reaches past the tensor in i (boxes clipped by the out-of-bounds logic measured ~7 % slower)
-    const int nw = nstr;
-    const AdmmMaps& maps = nstr < nwf ? maps_last : maps_full;
+    const int nw = nact;
+    const AdmmMaps& maps = nact < nwf ? maps_last : maps_full;
     const int i_hi0 = it * nwf;                                      // first strip of this tile
     const long u0 = q0 / SPU;
     const int jc0 = (int)(u0 / a.n3), t0 = (int)(u0 - (long)jc0 * a.n3), sg0 = (int)(q0 - u0 * SPU);
@@ -194,8 +200,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&done[s], nact); }
         mbar_fence_init();
         if (a.dbg) { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.dbg[2 * blockIdx.x] = t_; }
-        tma_prefetch_desc(&maps.D); tma_prefetch_desc(&maps.YL); tma_prefetch_desc(&maps.E);
-        tma_prefetch_desc(&maps.YO); tma_prefetch_desc(&maps.T);
+        tma_prefetch_desc(&maps.D); tma_prefetch_desc(&maps.YL); tma_prefetch_desc(&maps.Z); tma_prefetch_desc(&maps.T);
     }
     __syncthreads();
     pdl_wait();                           // everything above overlapped the tail of the previous kernel
@@ -211,11 +216,10 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
             auto issue_load = [&]() {
                 double* st = ring + (size_t)ls * kStageD;
                 const int j0 = ljc * 32 + ljg * (8 * JG);
-                mbar_expect_tx(&full[ls], 4 * nw * JG * 1024 + NT * 8 * 8);
+                mbar_expect_tx(&full[ls], NB * nw * JG * 1024 + NT * 8 * 8);
                 tma_load_4d(st, &maps.D, &full[ls], 0, j0, i_hi0, lt);
                 tma_load_4d(st + kBoxD, &maps.YL, &full[ls], 0, j0, i_hi0, lt);
-                tma_load_4d(st + 2 * kBoxD, &maps.E, &full[ls], 0, j0, i_hi0, lt);
-                tma_load_4d(st + 3 * kBoxD, &maps.YO, &full[ls], 0, j0, i_hi0, lt);
+                tma_load_4d(st + 2 * kBoxD, &maps.Z, &full[ls], 0, j0, i_hi0, lt);
                 bulk_load_1d(st + NB * kBoxD, a.C3 + (size_t)lt * a.RS, NT * 8 * 8, &full[ls]);   // C3 row of slice t
                 if (++ljg == SPU) { ljg = 0; if (++lt == a.n3) { lt = 0; ++ljc; } }
                 if (++ls == S) ls = 0;
@@ -229,8 +233,7 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
                 const int j0 = sjc * 32 + sjg * (8 * JG);
                 tma_store_4d(&maps.T, st, 0, j0, i_hi0, stt);
                 tma_store_4d(&maps.YL, st + kBoxD, 0, j0, i_hi0, stt);
-                tma_store_4d(&maps.E, st + 2 * kBoxD, 0, j0, i_hi0, stt);
-                tma_store_4d(&maps.YO, st + 3 * kBoxD, 0, j0, i_hi0, stt);
+                tma_store_4d(&maps.Z, st + 2 * kBoxD, 0, j0, i_hi0, stt);
                 tma_store_commit();
                 if (++sjg == SPU) { sjg = 0; if (++stt == a.n3) { stt = 0; ++sjc; } }
                 if (++ss == S) { ss = 0; sph ^= 1; }
@@ -258,36 +261,27 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         AdmmPrm prm;
         {
             const IterState& S0 = *a.st;
-            prm.muL = S0.muL; prm.muO = S0.muO; prm.rmuL = S0.rmuL; prm.rmuO = S0.rmuO; prm.thr = S0.thr;
+            prm.muL = S0.muL; prm.muO = S0.muO; prm.rmuL = S0.rmuL; prm.thr = S0.thr;
             prm.musum = S0.musum; prm.rmusum = 1.0 / S0.musum; prm.rmuL_next = S0.rmuL_next;
+            prm.yo_scale = S0.muO_prev * S0.rmuO; prm.thr_prev = S0.thr_prev;
         }
         double sL = 0.0, sO = 0.0;
         const int nthr = nact * 32;
-        // NS = strips this warp really has (SW, or 1 for the warp whose second strip lies below the tile): the body is
-        // instantiated per NS so that the strips of a stage share one basic block (their chains interleave)
-        auto body = [&](auto ns_tag) {
-        constexpr int NS = decltype(ns_tag)::value;
-        double aF[NS][2][KS];
+        const int i0 = it * a.tile_h + warp * 16 + 2 * g;
+        double aF[2][KS];
 #pragma unroll
-        for (int h2 = 0; h2 < NS; ++h2) {
-            const int i0 = it * a.tile_h + (warp + 8 * h2) * 16 + 2 * g;
-#pragma unroll
-            for (int s = 0; s < KS; ++s) {
-                aF[h2][0][s] = (i0 < a.n1) ? __ldg(a.A1 + (size_t)i0 * a.RS + 4 * s + tig) : 0.0;
-                aF[h2][1][s] = (i0 + 1 < a.n1) ? __ldg(a.A1 + (size_t)(i0 + 1) * a.RS + 4 * s + tig) : 0.0;
-            }
+        for (int s = 0; s < KS; ++s) {
+            aF[0][s] = (i0 < a.n1) ? __ldg(a.A1 + (size_t)i0 * a.RS + 4 * s + tig) : 0.0;
+            aF[1][s] = (i0 + 1 < a.n1) ? __ldg(a.A1 + (size_t)(i0 + 1) * a.RS + 4 * s + tig) : 0.0;
         }
-        double acc[NS][2][NT][2];
+        double acc[2][NT][2];
 #pragma unroll
-        for (int h2 = 0; h2 < NS; ++h2)
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
-            for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int n = 0; n < NT; ++n) acc[h2][m][n][0] = acc[h2][m][n][1] = 0.0;
-        double aS[NS][2][kFoldA ? KS : 1];
+            for (int n = 0; n < NT; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+        double aS[2][kFoldA ? KS : 1];
         // swizzled offsets (in double2 units) of this lane's two columns c = 0, 1 of the first column group inside its
-        // first strip's [8*JG j][16 i] block; the second group is 64 further (8 rows of 128 B, same swizzle phase), the
-        // second strip 8 strips further
+        // warp's [8*JG j][16 i] block; the second group is 64 further (8 rows of 128 B, same swizzle phase)
         const int off0 = warp * (64 * JG) + (2 * tig) * 8 + (g ^ (2 * tig));
         const int off1 = warp * (64 * JG) + (2 * tig + 1) * 8 + (g ^ (2 * tig + 1));
         int slot = 0; uint32_t ph = 0;
@@ -322,72 +316,55 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
 #pragma unroll
                     for (int s = 0; s < KS; ++s) {
                         const double c3 = c3row[4 * s + tig];
-#pragma unroll
-                        for (int h2 = 0; h2 < NS; ++h2) {
-                            aS[h2][0][s] = aF[h2][0][s] * c3;
-                            aS[h2][1][s] = aF[h2][1][s] * c3;
-                        }
+                        aS[0][s] = aF[0][s] * c3;
+                        aS[1][s] = aF[1][s] * c3;
                     }
                 }
                 double c3s[NT];                              // column scales of the MTTKRP B fragments
 #pragma unroll
                 for (int n = 0; n < NT; ++n) c3s[n] = c3row[8 * n + g];
                 double2* s2 = reinterpret_cast<double2*>(st);
-                // the JG column groups (and the NS strips) of a stage are independent: one basic block, so their
-                // DMMA and element-wise dependency chains interleave
+                // the JG column groups of a stage are independent: one basic block, so their DMMA and
+                // element-wise dependency chains interleave
 #pragma unroll
                 for (int h = 0; h < JG; ++h) {
                     const int jg = sg * JG + h;
-                    // L patch: l[strip][m][c] = L(i0 + m, j0 + 2*tig + c, t); a B fragment serves all strips
-                    double l[NS][2][2];
-#pragma unroll
-                    for (int h2 = 0; h2 < NS; ++h2) l[h2][0][0] = l[h2][0][1] = l[h2][1][0] = l[h2][1][1] = 0.0;
+                    // L patch: l[m][c] = L(i0 + m, j0 + 2*tig + c, t)
+                    double l[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
                     for (int ks = 0; ks < KS; ++ks) {
                         double b = Cfg::kShareB ? B2T[(4 * ks + tig) * kPJ + jg * 8 + g] : B2s[(jg * 8 + g) * PL + 4 * ks + tig];
                         if (!kFoldA) b *= c3row[4 * ks + tig];
-#pragma unroll
-                        for (int h2 = 0; h2 < NS; ++h2) {
-                            if (kFoldA) {
-                                dmma884(l[h2][0][0], l[h2][0][1], aS[h2][0][ks], b);
-                                dmma884(l[h2][1][0], l[h2][1][1], aS[h2][1][ks], b);
-                            } else {
-                                dmma884(l[h2][0][0], l[h2][0][1], aF[h2][0][ks], b);
-                                dmma884(l[h2][1][0], l[h2][1][1], aF[h2][1][ks], b);
-                            }
+                        if (kFoldA) {
+                            dmma884(l[0][0], l[0][1], aS[0][ks], b);
+                            dmma884(l[1][0], l[1][1], aS[1][ks], b);
+                        } else {
+                            dmma884(l[0][0], l[0][1], aF[0][ks], b);
+                            dmma884(l[1][0], l[1][1], aF[1][ks], b);
                         }
                     }
-                    double2 tn[NS][2];
+                    double2 tn[2];
 #pragma unroll
-                    for (int h2 = 0; h2 < NS; ++h2) {
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const int off = (c ? off1 : off0) + 64 * h + h2 * (8 * 64 * JG);
-                            const double2 d = s2[off];
-                            double2 yl = s2[kBoxD / 2 + off];
-                            double2 e = s2[2 * (kBoxD / 2) + off];
-                            double2 yo = s2[3 * (kBoxD / 2) + off];
-                            double2 o;
-                            admm_point2<MASKED>(prm, d.x, l[h2][0][c], yl.x, e.x, yo.x, o.x, tn[h2][c].x, sL, sO);
-                            admm_point2<MASKED>(prm, d.y, l[h2][1][c], yl.y, e.y, yo.y, o.y, tn[h2][c].y, sL, sO);
-                            s2[off] = tn[h2][c];
-                            s2[kBoxD / 2 + off] = yl;
-                            s2[2 * (kBoxD / 2) + off] = e;
-                            s2[3 * (kBoxD / 2) + off] = yo;
-                        }
+                    for (int c = 0; c < 2; ++c) {
+                        const int off = (c ? off1 : off0) + 64 * h;
+                        const double2 d = s2[off];
+                        double2 yl = s2[kBoxD / 2 + off];
+                        double2 z = s2[2 * (kBoxD / 2) + off];
+                        admm_point2<MASKED>(prm, d.x, l[0][c], yl.x, z.x, tn[c].x, sL, sO);
+                        admm_point2<MASKED>(prm, d.y, l[1][c], yl.y, z.y, tn[c].y, sL, sO);
+                        s2[off] = tn[c];
+                        s2[kBoxD / 2 + off] = yl;
+                        s2[2 * (kBoxD / 2) + off] = z;
                     }
                     // next iteration's X1*F': acc[m][n] += T'(i,j) B2(j,k) C3(t,k); k-step c covers j = j0 + 2*tig + c
 #pragma unroll
                     for (int n = 0; n < NT; ++n) {
                         const double2 b = *reinterpret_cast<const double2*>(B2T + (8 * n + g) * kPJ + jg * 8 + 2 * tig);
                         const double b0 = b.x * c3s[n], b1 = b.y * c3s[n];
-#pragma unroll
-                        for (int h2 = 0; h2 < NS; ++h2) {
-                            dmma884(acc[h2][0][n][0], acc[h2][0][n][1], tn[h2][0].x, b0);
-                            dmma884(acc[h2][1][n][0], acc[h2][1][n][1], tn[h2][0].y, b0);
-                            dmma884(acc[h2][0][n][0], acc[h2][0][n][1], tn[h2][1].x, b1);
-                            dmma884(acc[h2][1][n][0], acc[h2][1][n][1], tn[h2][1].y, b1);
-                        }
+                        dmma884(acc[0][n][0], acc[0][n][1], tn[0].x, b0);
+                        dmma884(acc[1][n][0], acc[1][n][1], tn[0].y, b0);
+                        dmma884(acc[0][n][0], acc[0][n][1], tn[1].x, b1);
+                        dmma884(acc[1][n][0], acc[1][n][1], tn[1].y, b1);
                     }
                 }
                 fence_proxy_async_smem();
@@ -399,16 +376,11 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         }
         double* p = a.partM + ((size_t)it * a.part_slots + x) * kPartH * a.RS;
 #pragma unroll
-        for (int h2 = 0; h2 < NS; ++h2)
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
-            for (int m = 0; m < 2; ++m)
-#pragma unroll
-                for (int n = 0; n < NT; ++n)
-                    *reinterpret_cast<double2*>(p + (size_t)((warp + 8 * h2) * 16 + 2 * g + m) * a.RS + 8 * n + 2 * tig) =
-                        make_double2(acc[h2][m][n][0], acc[h2][m][n][1]);
-        };
-        if (SW > 1 && warp + 8 < nstr) body(std::integral_constant<int, SW>{});
-        else body(std::integral_constant<int, 1>{});
+            for (int n = 0; n < NT; ++n)
+                *reinterpret_cast<double2*>(p + (size_t)(warp * 16 + 2 * g + m) * a.RS + 8 * n + 2 * tig) =
+                    make_double2(acc[m][n][0], acc[m][n][1]);
         sL = warp_sum(sL);
         sO = warp_sum(sO);
         if (lane == 0) { red[warp] = sL; red[8 + warp] = sO; }

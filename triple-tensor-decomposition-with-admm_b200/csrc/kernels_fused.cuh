@@ -20,6 +20,7 @@ struct IterState {
     int pinv_truncated;   // ... and the number of singular values they zeroed, like MATLAB's pinv
     int masked;           // completion variant: NaN in D marks an unobserved entry
     int pad_;
+    double muO_prev, thr_prev;   // muO and lambda/muO of the iteration that produced the stored Z = R3 (k_admm)
 };
 
 __host__ __device__ inline void iter_state_derive(IterState& s) {
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(256) k_sumsq_part(const double* x, size_t n, d
 // relative-change stopping rule, maxIter.  a, b = sum(resL.^2), sum(resO.^2) over the whole tensor.
 __device__ __forceinline__ void iter_finalize(IterState* st, double a, double b, double* errHist, double* errL, double* errO) {
     const int k = st->k;
+    st->muO_prev = st->muO; st->thr_prev = st->thr;
     st->muL = fmin(st->muL * st->rhoL, st->muL_max);
     st->muO = fmin(st->muO * st->rhoO, st->muO_max);
     iter_state_derive(*st);
@@ -216,6 +218,16 @@ __global__ void __launch_bounds__(256) k_finalize_als(IterState* st, const doubl
     st->k = k + 1;
     if (k >= 1 && fabs(errHist[k] - errHist[k - 1]) < st->tol * errHist[k - 1]) st->stop = 1;
     if (st->status != 0) st->stop = 1;
+}
+
+// E of the last finished iteration from the state the iteration keeps: Z = R3 of that iteration, E =
+// soft_threshold(R3, lambda/muO) with that iteration's muO (triple_decomp_ADMM.m:46-47; see k_admm).
+__global__ void __launch_bounds__(256) k_E_from_Z(const double* __restrict__ Z, const IterState* st, double* __restrict__ E, size_t n) {
+    const double thr = st->thr_prev;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const double z = Z[i];
+        E[i] = z - fmin(fmax(z, -thr), thr);          // = soft_threshold(z, thr), as k_admm forms it
+    }
 }
 
 // O of the last finished iteration, recovered from the state the iteration keeps:

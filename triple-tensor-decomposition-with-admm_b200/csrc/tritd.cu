@@ -311,7 +311,7 @@ struct tritd_problem {
     int n1 = 0, n2 = 0, n3 = 0, r = 0, R = 0, RS = 0, NT = 0, KS = 0;
     int ld1 = 0, ldt = 0;
     size_t Np = 0;                       // padded elements of one N-array: ld1 * n2 * n3
-    double *D = nullptr, *E = nullptr, *YL = nullptr, *YO = nullptr, *T = nullptr, *O = nullptr;
+    double *D = nullptr, *Z = nullptr, *YL = nullptr, *T = nullptr, *O = nullptr;   // Z: the sparse pair (E, Y_O) as one array (k_admm)
     double *A1 = nullptr, *B2 = nullptr, *C3 = nullptr, *A1T = nullptr;
     double *SA = nullptr, *SB = nullptr;
     double *bufA = nullptr;              // [rhsA (n1*RS) ; SC (RS*RS)] -- one all-reduce
@@ -346,7 +346,6 @@ struct tritd_problem {
     int partSlots = 0;                   // the largest of them: partF is [i-tile][partSlots][128][RS]
     bool pre_inv = false;                // the ridge inverses of updates A / B are computed by the previous k_admm / k_ppass (see fill_ridge_job)
     int jgp = 2;                         // k_admm: column groups per stage asked for (AdmmCfg::JGP)
-    int swA = 1;                         // k_admm: 16-row strips per consumer warp (AdmmCfg::SW); partials are [128 * swA][RS]
     int gridA = 0, tileH = 128, nitA = 1;  // k_admm: rows per i-tile (16 x consumer warps used) and number of i-tiles
     bool rhsA_ready = false;             // partF holds X1*F' of the current T
     int n_it = 0, n_jc = 0, gridM = 0, gridP = 0, gridF = 0, gi = 0;
@@ -489,24 +488,6 @@ static int launch_fused(tritd_problem* p, int mode, double* Lout) {
     return TRITD_OK;
 }
 
-// k_admm with two strips per consumer warp exists for the ranks whose fragments fit the register file (r <= 5)
-constexpr bool admm_sw2_ok(int KS) { return KS <= 8; }
-template <int KS, int NT> static void launch_admm_sw2(tritd_problem* p, const AdmmArgs& a) {
-    if constexpr (admm_sw2_ok(KS)) {
-        cudaStream_t st = p->ctx->stream;
-        if (p->masked) launch_k(k_admm<KS, NT, true, 1, 2>, p->gridA, kAdmmThreads, AdmmCfg<KS, NT, 1, 2>::kSmem, st, p->maps, p->mapsLast, a);
-        else launch_k(k_admm<KS, NT, false, 1, 2>, p->gridA, kAdmmThreads, AdmmCfg<KS, NT, 1, 2>::kSmem, st, p->maps, p->mapsLast, a);
-    }
-}
-template <int KS, int NT> static cudaError_t admm_sw2_attr() {
-    if constexpr (admm_sw2_ok(KS)) {
-        cudaError_t e = cudaFuncSetAttribute(k_admm<KS, NT, false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AdmmCfg<KS, NT, 1, 2>::kSmem);
-        if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(k_admm<KS, NT, true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AdmmCfg<KS, NT, 1, 2>::kSmem);
-    }
-    return cudaSuccess;
-}
-
 // The fused iteration kernel (TMA in / DMMA / TMA out); also leaves the next X1*F' partials in partF.
 static int launch_admm(tritd_problem* p) {
     tritd_ctx* c = p->ctx;
@@ -521,12 +502,11 @@ static int launch_admm(tritd_problem* p) {
     memset(&a.inv, 0, sizeof(a.inv));
     if (p->pre_inv) fill_ridge_job(p, 0, a.inv);
     a.R = p->R;
-    a.inv_stages = (int)std::ceil(0.27 * p->R / (p->jgp == 1 && p->swA == 1 ? 1.7 : 3.3));     // ~0.27 us per column vs ~3.3 us per 64 KB stage
+    a.inv_stages = (int)std::ceil(0.27 * p->R / (p->jgp == 1 ? 1.3 : 2.5));     // ~0.27 us per column vs ~2.5 us per two-group stage
     a.cta_tab = p->ctaTab; a.part_slots = p->partSlots; a.dbg = p->dbgA;
     a.n1 = p->n1; a.n2 = p->n2; a.n3 = p->n3; a.RS = p->RS; a.n_jc = p->n_jc; a.tile_h = p->tileH;
 #define CALL(NT_, KS_)                                                                                                       \
-    if (p->swA == 2) launch_admm_sw2<KS_, NT_>(p, a);                                                                         \
-    else if (p->masked && p->jgp == 1) launch_k(k_admm<KS_, NT_, true, 1>, p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream, p->maps, p->mapsLast, a);  \
+    if (p->masked && p->jgp == 1) launch_k(k_admm<KS_, NT_, true, 1>, p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream, p->maps, p->mapsLast, a);  \
     else if (p->masked) launch_k(k_admm<KS_, NT_, true, 2>, p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream, p->maps, p->mapsLast, a);  \
     else if (p->jgp == 1) launch_k(k_admm<KS_, NT_, false, 1>, p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 1>::kSmem, c->stream, p->maps, p->mapsLast, a); \
     else launch_k(k_admm<KS_, NT_, false, 2>, p->gridA, kAdmmThreads, AdmmCfg<KS_, NT_, 2>::kSmem, c->stream, p->maps, p->mapsLast, a);
@@ -575,8 +555,8 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
     switch (src) {
         case kSrcDirect: a.v = rhs_direct; a.stride = 0; a.count = 1; break;
         case kSrcPartF:
-            a.v = p->partF; a.stride = 128 * p->swA * RS; a.count = p->partSlots; a.tile_cnt = p->tileCnt;
-            a.tile_h = p->tileH; a.tile_stride = (long)p->partSlots * 128 * p->swA * RS; a.wpr = 8;
+            a.v = p->partF; a.stride = 128 * RS; a.count = p->partSlots; a.tile_cnt = p->tileCnt;
+            a.tile_h = p->tileH; a.tile_stride = (long)p->partSlots * 128 * RS; a.wpr = 8;
             break;
         case kSrcPB: a.v = p->P; a.stride = (long)p->n2 * RS; a.count = p->n3; a.w = p->C3; a.wstride = RS; a.wpr = 8; break;
         case kSrcPC: a.v = p->P; a.stride = RS; a.count = p->n2; a.row_stride = (long)p->n2 * RS; a.w = p->B2; a.wstride = RS; a.wpr = 8; break;
@@ -790,22 +770,13 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
         p->jgp = stages2 < 24 ? 1 : 2;
     }
     if (const char* e = getenv("TRITD_ADMM_JG")) p->jgp = atoi(e) == 1 ? 1 : 2;
-    // Two strips per consumer warp (AdmmCfg::SW): 12..15 strips (192..240 rows) become ONE i-tile whose boxes cover whole
-    // columns, instead of a full and a shallower 128-row tile.  Needs 64 KB stages worth having (large slab) and
-    // fragments of two strips that fit the register file (r <= 5, admm_sw2_ok).  Measured (profiles/r02_sw_experiments.md):
-    // 240 rows 257.7 -> 248 us, 208 rows 243 -> 230 us, 192 rows 228 -> 218 us; 256 rows (two full tiles) and
-    // tensors of several uneven tiles (300 rows) are faster with one strip per warp.
-    p->swA = (p->jgp == 2 && r <= 5 && nwr_ >= 12 && nwr_ <= 15) ? 2 : 1;
-    if (const char* e = getenv("TRITD_ADMM_SW")) p->swA = (atoi(e) == 2 && r <= 5) ? 2 : 1;
-    if (p->swA == 2) p->jgp = 1;
-    // Leading dimension: a multiple of 16 rows (padded rows exist and stay zero: TMA views the rows as (16, ld1/16)).
-    // One-tile layout (swA == 2): dense, so that a box of 8 whole columns is one contiguous run in HBM.  Otherwise
-    // DRAM-friendly for 128-row tiles: measured on B200 (profiles/r02_tile_experiments.md), the streaming kernels run
-    // 7-10 % faster when every column starts on a 2 KB boundary than on a 128-byte one, with 256-byte alignment
-    // (multiples of 32 rows) in between -- the 1 KB column chunks of an i-tile then never straddle a DRAM interleave
-    // block.  So: round up to 128 rows when that costs <= 1/8 extra memory, else to 32 rows.
+    // Leading dimension: a multiple of 16 rows (padded rows exist and stay zero: TMA views the rows as (16, ld1/16)),
+    // and DRAM-friendly: measured on B200 (profiles/r02_tile_experiments.md), the streaming kernels run 7-10 % faster when
+    // every column starts on a 2 KB boundary than on a 128-byte one, with 256-byte alignment (multiples of 32 rows) in
+    // between -- the 1 KB column chunks of an i-tile then never straddle a DRAM interleave block.  So: round up to 128
+    // rows when that costs <= 1/8 extra memory, else to 32 rows.
     p->ld1 = 16 * nwr_;
-    if (p->swA == 1) {
+    {
         const int l128 = (p->n1 + 127) & ~127, l32 = (p->n1 + 31) & ~31;
         if ((l128 - p->n1) * 8 <= p->n1) p->ld1 = l128;
         else if ((l32 - p->n1) * 8 <= p->n1) p->ld1 = l32;
@@ -817,7 +788,7 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
     int s = TRITD_OK;
     auto bail = [&](int code) { tritd_problem_destroy(p); return code; };
 #define PALLOC(ptr, count) if ((s = dalloc(p, &p->ptr, (count))) != TRITD_OK) return bail(s)
-    if (solver) { PALLOC(D, p->Np); PALLOC(E, p->Np); PALLOC(YL, p->Np); PALLOC(YO, p->Np); PALLOC(O, p->Np); }
+    if (solver) { PALLOC(D, p->Np); PALLOC(Z, p->Np); PALLOC(YL, p->Np); PALLOC(O, p->Np); }
     if (contract) PALLOC(T, p->Np);
     PALLOC(A1, (size_t)p->n1 * p->RS); PALLOC(B2, (size_t)p->n2 * p->RS); PALLOC(C3, (size_t)p->n3 * p->RS);
     PALLOC(A1T, (size_t)p->RS * p->ldt);
@@ -867,16 +838,17 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
         cudaMemset(p->flags, 0, (16 + 3 * 64) * 4);
         // k_admm: one CTA per SM.  The i-tiles are as even as 16-row warp strips allow (240 rows -> 128 + 112,
         // 130 rows -> 80 + 50) and every tile gets the same number of CTAs.  (Handing a shallower last tile fewer
-        // CTAs in proportion to its measured stage time was tried and lost: 284 vs 267 us on 240 x 320 x 300,
-        // profiles/r02_tile_experiments.md.)
+        // CTAs in proportion to its strips was tried twice and lost both times: 284 vs 267 us on 240 x 320 x 300 with four
+        // state arrays, 212.9 vs 201.3 us with three -- the time of a stage does not follow its depth;
+        // profiles/r02_tile_experiments.md, r02_zstate_experiments.md.)
         const int nwr = (p->n1 + 15) / 16;
-        p->nitA = (nwr + 8 * p->swA - 1) / (8 * p->swA);
+        p->nitA = (nwr + 7) / 8;
         p->tileH = 16 * ((nwr + p->nitA - 1) / p->nitA);
         std::vector<int> per(p->nitA, std::max(c->num_sms / p->nitA, 1));
         p->gridA = 0; p->partSlots = 0;
         for (int x : per) { p->gridA += x; p->partSlots = std::max(p->partSlots, x); }
         if (solver) {
-            PALLOC(partF, (size_t)p->nitA * p->partSlots * 128 * p->swA * p->RS);
+            PALLOC(partF, (size_t)p->nitA * p->partSlots * 128 * p->RS);
             PALLOC(ctaTab, 3 * p->gridA);
             PALLOC(tileCnt, p->nitA);
             std::vector<int> tab(3 * p->gridA);
@@ -911,8 +883,7 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
     CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                 (int)AdmmCfg<KS_, NT_, 2>::kSmem));                                               \
     CU_TRY(cudaFuncSetAttribute(k_admm<KS_, NT_, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                (int)AdmmCfg<KS_, NT_, 1>::kSmem));                                               \
-    CU_TRY((admm_sw2_attr<KS_, NT_>()));
+                                (int)AdmmCfg<KS_, NT_, 1>::kSmem));
             TRITD_DISPATCH_R(r, CALL)
 #undef CALL
             const int usm = (int)upd_smem_bytes(p->RS);
@@ -935,7 +906,7 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
 
     // zero everything once: pad rows / pad columns must be exact zeros forever
     cudaStream_t st = c->stream;
-    for (double* q : {p->D, p->E, p->YL, p->YO, p->T, p->O})
+    for (double* q : {p->D, p->Z, p->YL, p->T, p->O})
         if (q && cudaMemsetAsync(q, 0, p->Np * sizeof(double), st) != cudaSuccess) return bail(fail(TRITD_ERR_CUDA, "memset failed"));
     cudaMemsetAsync(p->A1T, 0, (size_t)p->RS * p->ldt * sizeof(double), st);
     cudaMemsetAsync(p->st, 0, sizeof(IterState), st);
@@ -952,7 +923,7 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
         int jgroups = 1;
         {
             auto q = [&]() -> int {
-#define CALL(NT_, KS_) jgroups = p->swA == 2 ? AdmmCfg<KS_, NT_, 1, 2>::JG : p->jgp == 1 ? AdmmCfg<KS_, NT_, 1>::JG : AdmmCfg<KS_, NT_, 2>::JG;
+#define CALL(NT_, KS_) jgroups = p->jgp == 1 ? AdmmCfg<KS_, NT_, 1>::JG : AdmmCfg<KS_, NT_, 2>::JG;
                 TRITD_DISPATCH_R(r, CALL)
 #undef CALL
                 return TRITD_OK;
@@ -962,9 +933,9 @@ static int problem_create(tritd_ctx* c, int64_t n1, int64_t n2, int64_t n3, int 
         cuuint32_t box4[4] = {16, (cuuint32_t)(8 * jgroups), (cuuint32_t)(p->tileH / 16), 1};
         const int strips = (p->n1 + 15) / 16, last_depth = strips - (p->nitA - 1) * (p->tileH / 16);
         cuuint32_t box4l[4] = {16, (cuuint32_t)(8 * jgroups), (cuuint32_t)last_depth, 1};
-        struct { CUtensorMap* m; CUtensorMap* ml; double* base; } mm[6] = {
-            {&p->maps.D, &p->mapsLast.D, p->D}, {&p->maps.YL, &p->mapsLast.YL, p->YL}, {&p->maps.E, &p->mapsLast.E, p->E},
-            {&p->maps.YO, &p->mapsLast.YO, p->YO}, {&p->maps.T, &p->mapsLast.T, p->T}, {&p->maps.O, &p->mapsLast.O, p->O}};
+        struct { CUtensorMap* m; CUtensorMap* ml; double* base; } mm[5] = {
+            {&p->maps.D, &p->mapsLast.D, p->D}, {&p->maps.YL, &p->mapsLast.YL, p->YL}, {&p->maps.Z, &p->mapsLast.Z, p->Z},
+            {&p->maps.T, &p->mapsLast.T, p->T}, {&p->maps.O, &p->mapsLast.O, p->O}};
         for (auto& q : mm) {
             if (solver && (s = make_map(c, q.m, q.base, 4, dims4, str4, box4)) != TRITD_OK) return bail(s);
             if (solver && (s = make_map(c, q.ml, q.base, 4, dims4, str4, box4l)) != TRITD_OK) return bail(s);
@@ -1092,7 +1063,7 @@ static int problem_init_local(tritd_problem* p, const tritd_opts* o, const doubl
     ST_TRY(upload_factors(p, A0, B0, C0));
 
     // O = E = Y_L = Y_O = 0 (:24-26); the first target T = D - O + (1/muL)*Y_L is D itself (:33)
-    for (double* q : {p->E, p->YL, p->YO, p->O}) CU_TRY(cudaMemsetAsync(q, 0, p->Np * sizeof(double), st));
+    for (double* q : {p->Z, p->YL, p->O}) CU_TRY(cudaMemsetAsync(q, 0, p->Np * sizeof(double), st));
     if (p->masked) {      // completion variant: the first target is the zero-filled data (the callers' own convention, traffic_triple_comparison.m:34-35)
         k_fill_unobserved<<<(unsigned)std::min<size_t>((p->Np + 255) / 256, (size_t)c->num_sms * 16), 256, 0, st>>>(p->D, p->T, p->Np);
         CU_TRY(cudaGetLastError());
@@ -1107,6 +1078,7 @@ static int problem_init_local(tritd_problem* p, const tritd_opts* o, const doubl
     h.rhoL = o->rho; h.rhoO = o->rho; h.lambda = o->lambda_; h.tol = o->tol; h.normD = 0.0;
     h.k = 0; h.stop = 0; h.status = 0; h.maxIter = o->maxIter; h.masked = p->masked ? 1 : 0;
     iter_state_derive(h);
+    h.muO_prev = h.muO; h.thr_prev = h.thr;      // (Z = 0: E = Y_O = 0 whatever these are)
     *p->st_host = h;
     CU_TRY(cudaMemcpyAsync(p->st, p->st_host, sizeof(IterState), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemsetAsync(p->flags, 0, (16 + 3 * 64) * 4, st));
@@ -1483,18 +1455,31 @@ extern "C" int tritd_problem_get_L_dev(tritd_problem* p, double* L_dev) {
     return s;
 }
 
-// E of the last finished iteration (the reference's header documents "O,E : sparse components (clone E)", :12)
+// E of the last finished iteration (the reference's header documents "O,E : sparse components (clone E)", :12).
+// The loop keeps Z = R3 instead of the pair (E, Y_O) (k_admm): E = soft_threshold(Z, lambda/muO) is materialised into
+// the p->O scratch on demand (stream order keeps an earlier copy of O out of it intact).
+static int materialise_E(tritd_problem* p) {
+    tritd_ctx* c = p->ctx;
+    ST_TRY(fetch_state(p));              // (the scalars of the last finished iteration are final)
+    const unsigned grid = (unsigned)std::min<size_t>((p->Np + 255) / 256, (size_t)c->num_sms * 16);
+    k_E_from_Z<<<grid, 256, 0, c->stream>>>(p->Z, p->st, p->O, p->Np);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return TRITD_OK;
+}
 extern "C" int tritd_problem_get_E(tritd_problem* p, double* E_host) {
     if (!p || !E_host || !p->initialized) return fail(TRITD_ERR_INVALID, "NULL argument / not initialised");
     CU_TRY(cudaSetDevice(p->ctx->device));
-    ST_TRY(copy_out(p, E_host, p->E));
+    ST_TRY(materialise_E(p));
+    ST_TRY(copy_out(p, E_host, p->O));
     CU_TRY(cudaStreamSynchronize(p->ctx->stream));
     return TRITD_OK;
 }
 extern "C" int tritd_problem_get_E_dev(tritd_problem* p, double* E_dev) {
     if (!p || !E_dev || !p->initialized) return fail(TRITD_ERR_INVALID, "NULL argument / not initialised");
     CU_TRY(cudaSetDevice(p->ctx->device));
-    return copy_out(p, E_dev, p->E);
+    ST_TRY(materialise_E(p));
+    return copy_out(p, E_dev, p->O);
 }
 // How often the ridge solves of this solve took the truncating pseudo-inverse path and how many singular values
 // that zeroed in total (what MATLAB's pinv does silently at :78/:86/:93).
