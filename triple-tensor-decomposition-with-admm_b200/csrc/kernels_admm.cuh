@@ -46,9 +46,8 @@ struct AdmmArgs {
     int finalize;                      // 1: the last CTA also runs the errHist / mu / stopping-rule step (:56-65)
     // N>1 peer exchange (kernels_xchg.cuh): the last CTA writes the pair into this rank's slot of every mailbox
     double* const* peers;              // nullptr: pair left in norms[] (NCCL path)
-    long norm_off, nflag_off;          // offsets in doubles inside a mailbox: this rank's pair / the flag row
+    long norm_off;                     // offset in doubles inside a mailbox: this rank's pair (two 16-byte words)
     const double* nslots;              // own mailbox: the ranks' pairs, 8 doubles apart
-    const unsigned* nflags;            // own mailbox: flag row of this exchange
     int rank, nranks;
     unsigned xbase;
     double* partM;                     // [i-tile][part_slots][128][RS]: this CTA's partial of the next X1*F' at (its tile, its index in the tile)
@@ -416,20 +415,18 @@ __global__ void __launch_bounds__(kAdmmThreads, 1) k_admm(const __grid_constant_
         else { a.norms[0] = sa; a.norms[1] = sb; red[0] = sa; red[1] = sb; }
     }
     if (!a.finalize && a.peers) {
-        // peer exchange of the residual sums by this (last) CTA: pair and flag of one mailbox come from the same
-        // thread (the release orders them); then wait for all ranks, sum in rank order -- every rank takes the same
-        // stopping decision -- and finalise the iteration
+        // peer exchange of the residual sums by this (last) CTA as self-validating words (kernels_xchg.cuh); then wait
+        // for all ranks, sum in rank order -- every rank takes the same stopping decision -- and finalise the iteration
         __syncthreads();
         const unsigned epoch = a.xbase + (unsigned)a.st->k + 1u;
         if (threadIdx.x < (unsigned)a.nranks) {
             double* box = a.peers[threadIdx.x];
-            *reinterpret_cast<double2*>(box + a.norm_off) = make_double2(red[0], red[1]);
-            st_release_sys_u32(reinterpret_cast<unsigned*>(box + a.nflag_off) + a.rank, epoch);
+            ll_store(box + a.norm_off, red[0], epoch);
+            ll_store(box + a.norm_off + 2, red[1], epoch);
         }
-        cta_wait_ranks(a.nflags, a.nranks, epoch, &a.st->status);
         if (threadIdx.x == 0) {
-            double ta = 0.0, tb = 0.0;
-            for (int r = 0; r < a.nranks; ++r) { ta += __ldcg(a.nslots + 8 * r); tb += __ldcg(a.nslots + 8 * r + 1); }
+            const double ta = ll_sum_ranks(a.nslots, 8, a.nranks, epoch, &a.st->status);
+            const double tb = ll_sum_ranks(a.nslots + 2, 8, a.nranks, epoch, &a.st->status);
             iter_finalize(a.st, ta, tb, a.errHist, a.errL, a.errO);
         }
     }

@@ -45,8 +45,10 @@ struct UpdArgs {
     int ns2;                  // (the per-rank partials of C3'C3 in the exchange mailbox), summed in order
     long s2stride;
     // N>1 peer exchange inside the kernel (xmerge): every row CTA writes its reduced rows into this rank's slot of every
-    // rank's mailbox, raises its flag [rank][cta] everywhere, waits for the flags [r][cta] of all ranks in the own
-    // mailbox and sums the slots in rank order.
+    // rank's mailbox as self-validating words (value + epoch, kernels_xchg.cuh), waits until the words of all ranks in
+    // its own mailbox show the epoch and sums the slots in rank order.  The rows are partitioned over the CTAs
+    // identically on every rank, so a thread only needs what its counterparts on the other ranks pushed: no grid-wide
+    // step, no CTA waits for a CTA of the same grid.
     // C3'C3 (the one small Gram with per-rank partials) travels EARLY: update C pushes its local partial from the end
     // of its Gram phase (sc_push) into a parity-double-buffered region of every mailbox, so that the ridge inverses
     // of the next iteration's updates A and B (sc_wait: S2 = the stack of the ranks' partials) start at once instead of
@@ -59,11 +61,9 @@ struct UpdArgs {
     long flag_area_off;       // doubles from the mailbox base to the flag area
     int gram_cap;             // CTAs that may take part (and spin) in the Gram phase
     int inv_here;             // block 0 inverts the ridge system (else an earlier kernel published it and raised flags[0])
-    long fstride;             // flags per rank in the flag block of this exchange (>= grid size)
     double* const* peers;     // [nranks] mailbox bases
-    long push_off, pflag_off; // offsets in doubles inside a mailbox: this rank's slot / the flag row of the exchange
+    long push_off;            // offset in doubles inside a mailbox: this rank's slot of the exchange (2 doubles per element)
     int rank, nranks;
-    const unsigned* xflags;   // flag row of the exchange in the own mailbox
     const double* xbox;       // slot 0 of the exchange region in the own mailbox
     long xslot;               // slot stride
     unsigned xbase;           // epoch of iteration k = xbase + k + 1
@@ -443,21 +443,6 @@ __global__ void __launch_bounds__(256) k_small_gram(const double* X, int n, int 
 
 constexpr int kUpdThreads = 256;
 
-// In-kernel exchange, CTA side.  The rows are partitioned over the CTAs identically on every rank, so CTA c only
-// needs what the CTAs c of the other ranks pushed: after its own stores into the peers' mailboxes (ordered by the
-// barrier + the system-scope release) it raises flag [rank][c] in every mailbox, then waits for the flags [r][c] of
-// all ranks r in the own mailbox.  No grid-wide step, no CTA waits for a CTA of the same grid: nothing has to be
-// co-resident.  Flags hold epochs (monotonic), so they never need a reset.
-__device__ __forceinline__ void xchg_publish_and_wait(double* const* peers, long pflag_off, long fstride, int rank, int nranks,
-                                                      const unsigned* xflags, unsigned epoch, int* status) {
-    __syncthreads();
-    if (threadIdx.x < (unsigned)nranks) {
-        st_release_sys_u32(reinterpret_cast<unsigned*>(peers[threadIdx.x] + pflag_off) + rank * fstride + blockIdx.x, epoch);
-        const unsigned* f = xflags + threadIdx.x * fstride + blockIdx.x;
-        spin_until_epoch(f, epoch, status);
-    }
-    __syncthreads();
-}
 constexpr int kUpdMaxGramCtas = 64;   // CTAs that may spin in the Gram phase (<< 148 SMs x resident CTAs)
 __host__ __device__ inline size_t upd_smem_bytes(int RS) {
     const int ms = RS * RS > 64 * RS ? RS * RS : 64 * RS;      // inv(G) tile / Gram row chunk [64][RS]
@@ -561,28 +546,21 @@ __global__ void __launch_bounds__(kUpdThreads) k_upd(const UpdArgs a) {
                         if (!a.apply) a.rhs_out[(size_t)(row0 + warp) * RS + k] = v;
                         else if (a.xmerge)
                             for (int r = 0; r < a.nranks; ++r)
-                                a.peers[(a.rank + 1 + r) % a.nranks][a.push_off + (size_t)(row0 + warp) * RS + k] = v;
+                                ll_store(a.peers[(a.rank + 1 + r) % a.nranks] + a.push_off + 2 * ((size_t)(row0 + warp) * RS + k), v, epoch);
                     }
                 }
             }
         }
         if (!a.apply) return;
         if (a.xmerge) {
-            xchg_publish_and_wait(a.peers, a.pflag_off, a.fstride, a.rank, a.nranks, a.xflags, epoch, &a.st->status);
-            // the all-reduced rows: the ranks' slots summed in rank order (the same on every rank)
+            // the all-reduced rows: every thread waits for ITS element from every rank (the words validate themselves,
+            // kernels_xchg.cuh) and sums the ranks' slots in rank order -- the same sum on every rank
             if (warp < rows && row0 + warp < a.n) {
 #pragma unroll
                 for (int q = 0; q < KPL; ++q) {
                     const int k = lane + 32 * q;
-                    if (k < RS) {
-                        double t[8];
-#pragma unroll
-                        for (int r = 0; r < 8; ++r) t[r] = r < a.nranks ? __ldcg(a.xbox + r * a.xslot + (size_t)(row0 + warp) * RS + k) : 0.0;
-                        double v = t[0];
-#pragma unroll
-                        for (int r = 1; r < 8; ++r) v += t[r];
-                        rhs_s[warp * 64 + k] = v;
-                    }
+                    if (k < RS)
+                        rhs_s[warp * 64 + k] = ll_sum_ranks(a.xbox + 2 * ((size_t)(row0 + warp) * RS + k), a.xslot, a.nranks, epoch, &a.st->status);
                 }
             }
         }

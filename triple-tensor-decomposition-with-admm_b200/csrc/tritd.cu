@@ -135,7 +135,7 @@ struct tritd_ctx {
     bool inproc = false;                 // member of a group
     std::vector<tritd_ctx*> sub;         // group: the members
     std::vector<tritd_problem*> gcached; // group: cached member problems of the last tritd_admm_f64 call
-    unsigned xepoch = 0;                 // peer exchange: first unused epoch (advances identically on every rank)
+    unsigned xepoch = 1;                 // peer exchange: first unused epoch (advances identically on every rank; 0 = the zeroed mailbox)
 };
 
 struct RankCfg { int NT, KS; };
@@ -321,7 +321,7 @@ struct tritd_problem {
     // N>1 peer exchange (kernels_xchg.cuh): local mailbox, the peers' mailboxes mapped with CUDA IPC
     bool xchg = false;
     double* box = nullptr;               // [A: nranks x slotA | B: nranks x slotB | N: nranks x 8 | S: 2 x nranks x RS^2 | flags (u32)]
-    size_t slotA = 0, slotB = 0, offB = 0, offN = 0, offS = 0, offF = 0, box_doubles = 0, fsA = 0, fsB = 0;
+    size_t slotA = 0, slotB = 0, offB = 0, offN = 0, offS = 0, offF = 0, box_doubles = 0;
     std::vector<void*> peer_map;         // cudaIpcOpenMemHandle mappings (nullptr for the own rank)
     double** peers = nullptr;            // device array [nranks] of mailbox bases
     unsigned xbase = 0;
@@ -495,8 +495,8 @@ static int launch_admm(tritd_problem* p) {
     a.A1 = p->A1; a.B2 = p->B2; a.C3 = p->C3; a.st = p->st; a.norm_part = p->norm_part; a.partM = p->partF;
     a.norms = p->norms; a.errHist = p->errHist; a.errL = p->errL; a.errO = p->errO;
     a.ticket = p->flags + 12; a.finalize = c->nranks == 1 ? 1 : 0;
-    a.peers = p->xchg ? p->peers : nullptr; a.norm_off = (long)(p->offN + 8 * (size_t)c->rank); a.nflag_off = (long)p->offF;
-    a.nslots = p->xchg ? p->box + p->offN : nullptr; a.nflags = p->xchg ? reinterpret_cast<const unsigned*>(p->box + p->offF) : nullptr;
+    a.peers = p->xchg ? p->peers : nullptr; a.norm_off = (long)(p->offN + 8 * (size_t)c->rank);
+    a.nslots = p->xchg ? p->box + p->offN : nullptr;
     a.rank = c->rank; a.nranks = c->nranks; a.xbase = p->xbase;
     a.n1s = p->n1;
     memset(&a.inv, 0, sizeof(a.inv));
@@ -579,11 +579,6 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
             const int ex = which;
             a.xmerge = 1;
             a.push_off = (long)((ex == 0 ? 0 : p->offB) + (ex == 0 ? p->slotA : p->slotB) * c->rank);
-            // flag block of this exchange: u32 index 8 (+ nranks * fsA for B) from the start of the flag area
-            const size_t fu = kFlagsFixed + (ex == 0 ? 0 : (size_t)c->nranks * p->fsA);
-            a.pflag_off = (long)(p->offF + fu / 2);
-            a.fstride = (long)(ex == 0 ? p->fsA : p->fsB);
-            a.xflags = reinterpret_cast<const unsigned*>(p->box + p->offF) + fu;
             a.xbox = p->box + (ex == 0 ? 0 : p->offB);
             a.xslot = (long)(ex == 0 ? p->slotA : p->slotB);
         }
@@ -621,15 +616,13 @@ static int launch_upd(tritd_problem* p, int which, int src, bool apply, const do
 static void exchange_layout(tritd_problem* p) {
     const int nr = p->ctx->nranks;
     const size_t RS = p->RS;
-    p->slotA = (size_t)p->n1 * RS;
-    p->slotB = (size_t)p->n2 * RS;
+    p->slotA = (size_t)2 * p->n1 * RS;                // 16-byte self-validating words (kernels_xchg.cuh): 2 doubles per element
+    p->slotB = (size_t)2 * p->n2 * RS;
     p->offB = p->slotA * nr;
     p->offN = p->offB + p->slotB * nr;
     p->offS = p->offN + (size_t)8 * nr;               // C3'C3 partials: [2 parities][nr][RS*RS]
-    p->offF = p->offS + (size_t)2 * nr * RS * RS;     // flags (u32): [norms: 8] [C3'C3: 2 x 8] [exchange A: nr x fsA] [exchange B: nr x fsB]
-    p->fsA = ((size_t)p->n1 + 1 + 7) & ~(size_t)7;   // one flag per k_upd CTA (<= n + 1 CTAs), per rank
-    p->fsB = ((size_t)p->n2 + 1 + 7) & ~(size_t)7;
-    p->box_doubles = p->offF + (kFlagsFixed + (size_t)nr * (p->fsA + p->fsB)) / 2 + 8;
+    p->offF = p->offS + (size_t)2 * nr * RS * RS;     // flags (u32): [(unused): 8] [C3'C3: 2 x 8]
+    p->box_doubles = p->offF + kFlagsFixed / 2 + 8;
 }
 
 // the mailbox bases of all ranks are known: upload them, size the one-wave limit of the exchanging grids
