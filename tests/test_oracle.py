@@ -154,3 +154,29 @@ def test_qi_design_matrices_against_their_scalar_definitions():
     assert np.allclose(orc.triple_product_qi(A, B, C), X, rtol=1e-13, atol=1e-13)
     assert np.allclose(np.reshape(np.reshape(A, (n1, r * r), order="F") @ orc.buildF_qi(B, C), (n1, n2, n3), order="F"), X,
                        rtol=1e-13, atol=1e-13)
+
+
+def test_sparse_pair_is_a_function_of_R3():
+    """The identity k_admm's state compression rests on, checked on the ORACLE's own iterates, which keep E and
+    Y_O like the reference (triple_decomp_ADMM.m:46-47,:53): with Z = R3 = O + (1/muO)*Y_O_old of an iteration,
+    E = Z - clip(Z, +-lambda/muO) bit for bit, and Y_O_new = Y_O_old + muO*(O - E) = muO*clip(Z) up to a few roundings of a
+    quantity bounded by lambda."""
+    from tritd import synth
+    w = synth.make_config("cfg1", shrink=(24, 20, 16))
+    opts = dict(w["opts"], maxIter=12, tol=0.0)
+    lam, mu0, rho = opts["lambda"], opts["mu"], opts["rho"]
+    seen = {"Y_O": np.zeros(w["D"].shape), "n": 0, "dev": 0.0}
+
+    def on_iter(k, A, B, C, O, E, Y_L, Y_O):
+        muO = min(mu0 * rho ** (k - 1), mu0 * 1e6)          # the muO iteration k ran with
+        thr = lam / muO
+        Z = O + (1 / muO) * seen["Y_O"]
+        clip = np.minimum(np.maximum(Z, -thr), thr)
+        assert np.array_equal(Z - clip, E)                  # soft_threshold(Z, thr), the very same subtraction
+        dev = np.abs(muO * clip - Y_O).max()
+        assert dev <= 8 * np.finfo(float).eps * lam, dev    # |Y_O| <= lambda
+        assert np.abs(Y_O).max() <= lam * (1 + 1e-12)
+        seen["Y_O"] = Y_O.copy(); seen["n"] += 1; seen["dev"] = max(seen["dev"], dev)
+
+    orc.triple_decomp_ADMM(w["D"], w["r"], opts, w["A0"], w["B0"], w["C0"], on_iter=on_iter)
+    assert seen["n"] == 12
