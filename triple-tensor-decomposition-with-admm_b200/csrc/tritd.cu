@@ -1236,7 +1236,7 @@ static int capture_graph(tritd_problem* p, int iters, cudaGraphExec_t* out, bool
 // captured from the very same enqueue_iteration() -- all iteration state lives in device memory, so the graphs
 // need no parameter updates.  Whole batches of kGraphBatch iterations replay ONE graph, inside which every kernel is
 // a programmatic dependent of its predecessor (also across the iteration boundary).
-static int run_iterations(tritd_problem* p, int n) {
+static int run_iterations(tritd_problem* p, int n, bool eager = false) {
     tritd_ctx* c = p->ctx;
     if (c->inproc) CU_TRY(cudaSetDevice(c->device));      // members of a group are driven by one host thread
     while (n > 0) {
@@ -1246,6 +1246,13 @@ static int run_iterations(tritd_problem* p, int n) {
         if (!ge) {
             bool failed = false;
             ST_TRY(capture_graph(p, batch ? kGraphBatch : 1, &ge, &failed));
+            if (failed) { p->graph_off = true; continue; }
+        }
+        if (eager && !p->graphN) {
+            // staged API (tritd_problem_enqueue): build the batch graph together with the first one, so that a caller who
+            // times a later enqueue (bench.py after its warm-up) never has the capture inside its timed region
+            bool failed = false;
+            ST_TRY(capture_graph(p, kGraphBatch, &p->graphN, &failed));
             if (failed) { p->graph_off = true; continue; }
         }
         CU_TRY(cudaGraphLaunch(ge, c->stream));
@@ -1294,7 +1301,7 @@ static int fetch_state(tritd_problem* p) {
 extern "C" int tritd_problem_enqueue(tritd_problem* p, int32_t n) {
     if (!p || !p->initialized) return fail(TRITD_ERR_INVALID, "problem not initialised");
     CU_TRY(cudaSetDevice(p->ctx->device));
-    return run_iterations(p, n);
+    return run_iterations(p, n, true);
 }
 
 extern "C" int tritd_problem_sync(tritd_problem* p) {
