@@ -20,6 +20,9 @@ for arg in sys.argv[1:] or ["240x320x300x5"]:
         st = np.array(out[:2 * n]).reshape(n, 2); tb = np.array(tab[:3 * n]).reshape(n, 3)
         t0 = st[:, 0].min()
         print(arg, "grid", n, "kernel span %.1f us" % ((st[:, 1].max() - t0) / 1e3))
+        dur = (st[:, 1] - st[:, 0]) / 1e3
+        top = np.argsort(-dur)[:5]
+        print("  slowest CTAs (id, tile, slot, us):", [(int(i), int(tb[i, 0]), int(tb[i, 1]), round(float(dur[i]), 1)) for i in top], " CTA 0: %.1f us" % dur[0])
         for q in sorted(set(tb[:, 0])):
             m = tb[:, 0] == q
             d = (st[m, 1] - st[m, 0]) / 1e3
