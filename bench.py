@@ -383,7 +383,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_admm (TMA in / DMMA L reconstruction + O/E/dual/T update on the state D, Y_L, Z + residual norms + next mode-1 MTTKRP / TMA out)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "traffic_source": "not measured in this run; one ncu --set full capture per change is committed under profiles/ "
-                                  "(dram__bytes_read.sum + dram__bytes_write.sum per launch, r02_*_ncu_summary.csv)",
+                                  "(dram__bytes_read.sum + dram__bytes_write.sum per launch: profiles/r02_final_cfg3_ncu_summary.csv, "
+                                  "590.5 MB + 502.0 MB for the cfg3 launch of this kernel; r02_final_cfg5slab_ncu_summary.csv)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": FUSED_BYTES * N_local, "kernel_ms": fused_ms,
                 "kernel_ms_source": "CUDA events recorded by the library around k_admm on the launching stream, averaged over a second pass of the same steps",
                 "survey_yardstick_64N": {"GBps": SURVEY_FUSED_BYTES * N_local / (fused_ms * 1e-3) * 1e-9,
