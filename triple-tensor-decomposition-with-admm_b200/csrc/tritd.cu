@@ -338,7 +338,7 @@ struct tritd_problem {
     IterState* poll = nullptr;           // pinned [2]: asynchronous copies of the iteration scalars (tritd_problem_iterate)
     cudaEvent_t poll_ev[2] = {nullptr, nullptr};
     CUtensorMap mapT, mapA1T;
-    alignas(64) AdmmMaps maps;           // boxes [strips of a full i-tile][8*JG j][16 i] of D, Y_L, E, Y_O, T, O for k_admm
+    alignas(64) AdmmMaps maps;           // boxes [strips of a full i-tile][8*JG j][16 i] of D, Y_L, Z, T, O for k_admm
     alignas(64) AdmmMaps mapsLast;       // the same with the depth of the last i-tile (no box reaches past the tensor in i)
     double* partF = nullptr;             // [gridA][128][RS] fused mode-1 partials (next iteration's X1*F')
     int* ctaTab = nullptr;               // per k_admm CTA: (i-tile, index among the tile's CTAs, CTAs of that tile)
