@@ -42,16 +42,32 @@ def _worker(rank, world, port, case, n3, iters, out_dir, exchange):
     o = dict(o, maxIter=iters, tol=0.0)
     t0, t1 = synth.slab_bounds(n3, world)[rank]
 
+    epoch = [1]                                                      # (0 = the zeroed mailbox: never a valid epoch)
+
     def allreduce(x):
         t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).copy())
         if exchange == "allreduce":
             dist.all_reduce(t)
             return t.numpy()
-        slots = [torch.empty_like(t) for _ in range(world)]        # the mailbox: one slot per source rank
-        dist.all_gather(slots, t)
-        acc = slots[0].numpy().copy()
-        for s_ in slots[1:]:                                         # rank order, the same on every rank
-            acc = acc + s_.numpy()
+        # the mailbox of csrc/kernels_xchg.cuh: one slot per source rank, every double travelling as the self-validating
+        # 16-byte word {lo, epoch, hi, epoch}; the receiver accepts a word only when both halves show the epoch of this
+        # exchange, then sums the ranks' values in rank order
+        epoch[0] += 1
+        bits = t.numpy().view(np.uint64).ravel()
+        words = np.empty((bits.size, 4), dtype=np.uint32)
+        words[:, 0] = (bits & 0xFFFFFFFF).astype(np.uint32); words[:, 2] = (bits >> 32).astype(np.uint32)
+        words[:, 1] = words[:, 3] = epoch[0]
+        w = torch.from_numpy(words.view(np.int32).copy())
+        slots = [torch.empty_like(w) for _ in range(world)]
+        dist.all_gather(slots, w)
+        acc = None
+        for s_ in slots:                                             # rank order, the same on every rank
+            q = s_.numpy().view(np.uint32)
+            assert (q[:, 1] == epoch[0]).all() and (q[:, 3] == epoch[0]).all()
+            stale = q.copy(); stale[:, 3] -= 1                       # a half from the previous exchange must not validate
+            assert not ((stale[:, 1] == epoch[0]) & (stale[:, 3] == epoch[0])).any()
+            v = ((q[:, 2].astype(np.uint64) << np.uint64(32)) | q[:, 0].astype(np.uint64)).view(np.float64).reshape(t.shape)
+            acc = v.copy() if acc is None else acc + v
         return acc
 
     A1, B2, C3 = orc.factors_to_unfolded(A0, B0, C0)
