@@ -1,6 +1,6 @@
 /* Minimal stand-in for MathWorks' mex.h / matrix.h, declaring only what the gateways in this
- * directory use, so they can be syntax-checked in an image without MATLAB or Octave.
- * NOT a MEX implementation: nothing here is ever linked. */
+ * directory use, so they can be compiled in an image without MATLAB or Octave.
+ * NOT a MEX implementation; the only definitions of these functions live in the test mock tests/mex_mock/mexmock.c. */
 #ifndef TRITD_STUB_MEX_H
 #define TRITD_STUB_MEX_H
 #include <stddef.h>

@@ -6,7 +6,8 @@
  * mask is logical, size of Y, true = observed.  Semantics: DESIGN.md 4.6 (no reference code exists for it): on the
  * observed entries the statements of triple_decomp_ADMM.m:33-65, unobserved entries carry no constraint and are
  * imputed with the low-rank estimate.  opts as for triple_decomp_ADMM (+ A0, B0, C0, device).
- * This image has neither MATLAB nor Octave: the file is syntax-checked against stub/mex.h. */
+ * This image has neither MATLAB nor Octave: the file is compiled against stub/mex.h and executed against the mock MEX
+ * runtime of tests/mex_mock (tests/test_mex_gateway.py). */
 #include <string.h>
 
 #include "mex.h"

@@ -8,7 +8,8 @@
  *
  * Build (on a machine with MATLAB + CUDA):
  *   mex -I../../include triple_decomp_ALS.c -L../tritd -ltritd
- * This image has neither MATLAB nor Octave: the file is syntax-checked against stub/mex.h.
+ * This image has neither MATLAB nor Octave: the file is compiled against stub/mex.h and executed against the mock MEX
+ * runtime of tests/mex_mock (tests/test_mex_gateway.py).
  */
 #include <string.h>
 

@@ -1,6 +1,7 @@
 /* MEX gateway: Xhat = triple_product(A, B, C)
  * Drop-in for fast_robust_triple_tensor/triple_product.m:1-8, which the reference's callers run
- * right after the solve (traffic_triple_comparison.m:62).  Syntax-checked against stub/mex.h. */
+ * right after the solve (traffic_triple_comparison.m:62).  Compiled against stub/mex.h, executed against the mock MEX
+ * runtime of tests/mex_mock (tests/test_mex_gateway.py, tests/test_zz_mex_gateway_gpu.py). */
 #include "mex.h"
 #include "tritd.h"
 
