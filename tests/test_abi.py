@@ -4,6 +4,8 @@ mirror validates arguments like the reference does."""
 import ctypes
 import os
 import re
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -86,3 +88,27 @@ def test_mex_gateway_sources_present():
     mex = os.path.join(ROOT, "triple-tensor-decomposition-with-admm_b200", "mex")
     for f in ("triple_decomp_ADMM.c", "triple_product.c"):
         assert os.path.exists(os.path.join(mex, f))
+
+
+def test_every_entry_point_rejects_a_null_handle():
+    """No entry point that takes a context / problem handle may crash on NULL: each must return an error status (and none
+    may compute anything without a device).  Run in a child process so that a crash fails this test, not the session."""
+    code = r'''
+import ctypes as C, sys
+sys.path.insert(0, %r)
+import tritd
+lib = tritd.load_library()
+n = 0
+for name, (res, args) in tritd.SYMBOLS.items():
+    if res is not C.c_int or not args or args[0] is not C.c_void_p:
+        continue
+    zero = [0 if a in (C.c_int, C.c_int32, C.c_int64) else 0.0 if a is C.c_double else None for a in args]
+    rc = getattr(lib, name)(*zero)
+    assert rc != 0, name
+    assert lib.tritd_last_error(), name
+    n += 1
+print("rejected", n)
+''' % os.path.join(ROOT, "triple-tensor-decomposition-with-admm_b200")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert int(out.stdout.split()[-1]) >= 35
