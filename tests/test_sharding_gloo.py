@@ -1,4 +1,4 @@
-"""N>1 host-side logic on CPU: world_size-2 gloo processes run the mode-3 sharded restatement of the
+"""N>1 host-side logic on CPU: world_size-2 (and 3, 4) gloo processes run the mode-3 sharded restatement of the
 iteration (oracle/tritd_oracle_sharded.py), exchanging [RHS_A ; C3'C3], RHS_B and the residual norms
 exactly where libtritd does, and must reproduce the unsharded oracle -- including an uneven split.
 Two exchange models: a gloo all-reduce (libtritd's NCCL path) and the peer-mailbox rule of
@@ -78,26 +78,33 @@ def _worker(rank, world, port, case, n3, iters, out_dir, exchange):
 
 
 @pytest.mark.parametrize("exchange", ["allreduce", "mailbox"])
-@pytest.mark.parametrize("case,n3,iters", [("small_40x36x24_r5", 24, 6), ("odd_33x17x9_r2", 9, 6)])
-def test_two_rank_sharded_iteration_equals_oracle(case, n3, iters, exchange, tmp_path):
+@pytest.mark.parametrize("world,case,n3,iters", [(2, "small_40x36x24_r5", 24, 6), (2, "odd_33x17x9_r2", 9, 6),
+                                                 (3, "small_40x36x24_r5", 23, 4), (4, "odd_33x17x9_r2", 9, 4)])
+def test_sharded_iteration_equals_oracle(world, case, n3, iters, exchange, tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     import make_golden
     import tritd_oracle as orc
     from conftest import rel_err
+    from tritd import synth
 
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), case, n3, iters, str(tmp_path), exchange), nprocs=world, join=True)
     D, r, o, A0, B0, C0 = make_golden.case_inputs(case)
+    D = np.asfortranarray(D[:, :, :n3]); C0 = np.asfortranarray(C0[:, :, :n3])
     o = dict(o, maxIter=iters, tol=0.0)
     A, B, C, O, eh = orc.triple_decomp_ADMM(D, r, o, A0, B0, C0)
     parts = [np.load(os.path.join(str(tmp_path), f"rank{g}.npz")) for g in range(world)]
-    assert [int(p["t1"] - p["t0"]) for p in parts] == ([12, 12] if n3 == 24 else [5, 4])     # uneven split covered
+    # contiguous slabs, the first n3 % world ranks one slice longer (tritd_slab_bounds): 12+12, 5+4, 8+8+7, 3+2+2+2
+    sizes = [int(p["t1"] - p["t0"]) for p in parts]
+    assert sizes == {(2, 24): [12, 12], (2, 9): [5, 4], (3, 23): [8, 8, 7], (4, 9): [3, 2, 2, 2]}[(world, n3)]
+    assert [int(p["t0"]) for p in parts] == [sum(sizes[:g]) for g in range(world)]
+    assert [tuple(b) for b in synth.slab_bounds(n3, world)] == [(int(p["t0"]), int(p["t1"])) for p in parts]
     for p in parts:
         assert rel_err(p["eh"], eh) < 1e-10                                                 # identical on every rank
         assert rel_err(p["A1"], orc.unfold(A, 1)) < 1e-9 and rel_err(p["B2"], orc.unfold(B, 2)) < 1e-9   # replicated
     if exchange == "mailbox":          # rank-ordered sums: replicas are bitwise equal, no broadcast needed
-        assert np.array_equal(parts[0]["A1"], parts[1]["A1"]) and np.array_equal(parts[0]["B2"], parts[1]["B2"])
-        assert np.array_equal(parts[0]["eh"], parts[1]["eh"])
+        for p in parts[1:]:
+            assert np.array_equal(parts[0]["A1"], p["A1"]) and np.array_equal(parts[0]["B2"], p["B2"])
+            assert np.array_equal(parts[0]["eh"], p["eh"])
     C3 = np.concatenate([p["C3"] for p in parts], axis=0)
     Ocat = np.concatenate([p["O"] for p in parts], axis=2)
     assert rel_err(C3, orc.unfold(C, 3)) < 1e-9 and rel_err(Ocat, O) < 1e-9                  # slabs tile the tensor
