@@ -21,6 +21,10 @@ Prints ONE JSON line (rank 0):
             and `fp64` carry the FP64-tensor fractions against the DMMA peak measured in this run;
   parity_vs_fixture  max relative deviation of the first errHist values of this very run (any N) from the committed
             CPU-oracle fixture tests/golden/fullsize_errhist.json;
+  time_to_tol  the reference's own call (tol 1e-5, maxIter 100) timed from entry until the outputs are on the host;
+  final_rre (N=1) outcome of that full run on the headline config and on cfg1: RRE = ||triple_product(A,B,C) - L0|| / ||L0||
+            (the drivers' evaluate(), traffic_triple_comparison.m:194-199; formed on the device), iteration count and last
+            errHist value, next to the CPU oracle's numbers for the same run (fixture tests/golden/final_rre.json);
   cpu_baseline  the multi-threaded CPU port of the oracle timed on this box's host cores (rank 0, N=1);
   configs   (N=1) device-resident iterations/s of the other BASELINE configs; secondary = cfg5, the shape the north
             star's scaling target names (every N).
@@ -514,6 +518,39 @@ def main():
             except Exception as exc:
                 secondary["cpu_baseline"] = {"skipped": f"{type(exc).__name__}: {exc}"}
 
+    # ---------------- final RRE of the reference's full run (north_star: "the final RRE reported"), N=1 ----------------
+    # Last thing before the line is printed, every case on its own: nothing above can be affected by a failure here.
+    # The CPU oracle's numbers for the same runs come from a committed fixture (tests/golden/make_final_rre.py).
+    final_rre = None
+    if world == 1 and not args.no_e2e:
+        final_rre = []
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "final_rre.json")) as f:
+                rre_fixture = json.load(f)
+        except Exception:
+            rre_fixture = {}
+        for cname in dict.fromkeys((name, "cfg1")):
+            try:
+                wt = synth.make_config(cname, with_truth=True)          # the seeded data of the timed runs + the low-rank part it was built from
+                fo = dict(wt["opts"], disp=0)                            # the reference's own options for this kind of data
+                fA, fB, fC, fO, feh = tritd.triple_decomp_ADMM(wt["D"], wt["r"], fo, wt["A0"], wt["B0"], wt["C0"], ctx=ctx)
+                rmse, nrmse = tritd.evaluate(fA, fB, fC, wt["L0"], ctx=ctx)
+                ent = {"workload": f"{cname}: {synth.DESCRIPTIONS[cname]}", "RRE": nrmse, "rmse": rmse, "iterations": len(feh),
+                       "final_errHist": float(feh[-1]), "tol": fo["tol"], "maxIter": int(fo["maxIter"]),
+                       "definition": "nrmse of evaluate(triple_product(A,B,C), L0, all-true mask) = ||Xhat - L0||_F / ||L0||_F "
+                                     "(traffic_triple_comparison.m:194-199) after [A,B,C,O,errHist] = triple_decomp_ADMM(D, r, opts) with the "
+                                     "reference's options; L0 = the low-rank part the synthetic D was built from; reconstruction and norms on the device"}
+                fx = rre_fixture.get(cname)
+                if fx and fx.get("shape") == list(wt["shape"]):
+                    ent["cpu_oracle"] = {"RRE": fx["RRE"], "iterations": fx["iterations"], "final_errHist": fx["final_errHist"],
+                                         "source": "tests/golden/final_rre.json (CPU oracle, same inputs and options)"}
+                    ent["same_iteration_count_as_cpu_oracle"] = bool(fx["iterations"] == len(feh))
+                    ent["RRE_abs_dev_from_cpu_oracle"] = abs(nrmse - fx["RRE"])
+                final_rre.append(ent)
+                ctx.trim()
+            except Exception as exc:
+                final_rre.append({"workload": cname, "error": f"{type(exc).__name__}: {exc}"})
+
     if rank == 0:
         cfg = make_config_dict(name, world)
         line = {
@@ -522,7 +559,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": cfg,
             "opts": {k: opts[k] for k in ("mu", "rho", "lambda", "lambda2")},
             "clocks": m["clocks"], "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "parity_vs_fixture": m["parity"], "time_to_tol": ttt, "configs": others, "secondary": secondary,
+            "parity_vs_fixture": m["parity"], "time_to_tol": ttt, "final_rre": final_rre, "configs": others, "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

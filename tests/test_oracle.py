@@ -180,3 +180,19 @@ def test_sparse_pair_is_a_function_of_R3():
 
     orc.triple_decomp_ADMM(w["D"], w["r"], opts, w["A0"], w["B0"], w["C0"], on_iter=on_iter)
     assert seen["n"] == 12
+
+
+def test_final_rre_fixture_is_the_oracles_outcome():
+    """tests/golden/final_rre.json (what bench.py prints next to the GPU run's final RRE) was produced by the multi-threaded
+    port; the numpy oracle must give the same outcome of the reference's full cfg1 run: same iteration count, same last
+    errHist value and the same RRE = ||triple_product(A,B,C) - L0|| / ||L0|| (traffic_triple_comparison.m:194-199)."""
+    import json
+    import os
+    from tritd import synth
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "final_rre.json")))["cfg1"]
+    w = synth.make_config("cfg1", with_truth=True)
+    A, B, C, O, eh = orc.triple_decomp_ADMM(w["D"], w["r"], dict(w["opts"], disp=0), w["A0"], w["B0"], w["C0"])
+    assert fx["shape"] == list(w["shape"]) and len(eh) == fx["iterations"]
+    assert abs(eh[-1] - fx["final_errHist"]) < 1e-6 * fx["final_errHist"]
+    rre = synth.rre(orc.triple_product(A, B, C), w["L0"])
+    assert abs(rre - fx["RRE"]) < 1e-6 * fx["RRE"] and rre < 1e-7          # the low-rank part is recovered
