@@ -304,6 +304,23 @@ def test_admm_gateway_device_selection(built, field, value, want):
     assert g.fake("fake_ndev").value == len(want) and list(g.fake("fake_devs", ctypes.c_int * 8))[: len(want)] == want
 
 
+def test_admm_gateway_recreates_its_context_when_the_devices_change(built):
+    """INTEGRATION.md's own sequence: a single-GPU call, then `opts.ngpu = 8` -- the cached context must not silently stay on
+    one GPU; an unchanged request reuses the context, and the lock is taken once."""
+    g = _admm(built)
+    D, r = g.double(_problem()), g.double(2)
+    g.randn_source(10000)
+    devs = lambda: list(g.fake("fake_devs", ctypes.c_int * 8))[: g.fake("fake_ndev").value]    # noqa: E731
+    for o, want, created, destroyed in ((OPTS, [0], 1, 0), (dict(OPTS, ngpu=8.0), list(range(8)), 2, 1),
+                                        (dict(OPTS, ngpu=8.0), list(range(8)), 2, 1),
+                                        (dict(OPTS, devices=np.array([[1.0, 3.0]])), [1, 3], 3, 2), (OPTS, [0], 4, 3)):
+        out, err = g.call(5, D, r, g.struct(o))
+        assert err is None
+        assert devs() == want and g.fake("fake_created").value == created and g.fake("fake_destroyed").value == destroyed
+    assert g.lib.mock_locks() == 1
+    assert g.lib.mock_run_atexit() == 1 and g.fake("fake_destroyed").value == 4
+
+
 def test_admm_gateway_mask_option_and_library_errors(built):
     g = _admm(built)
     D = _problem()
@@ -360,6 +377,9 @@ def test_als_gateway(built):
     o = g.fake("fake_opts", _Opts)
     assert (o.maxIter, o.tol, o.disp) == (12, 1e-6, 1)                                        # the reference always prints (:17-19)
     assert g.printed().startswith("Iteration 5, relative error = ")
+    out, err = g.call(4, g.double(X), g.double(r), g.struct(dict(maxIter=12, tol=1e-6, device=3.0)))     # another device: a new context
+    assert err is None and g.fake("fake_created").value == 2 and g.fake("fake_destroyed").value == 1
+    assert list(g.fake("fake_devs", ctypes.c_int * 8))[:1] == [3] and g.lib.mock_locks() == 1
     _, err = g.call(4, g.double(X), g.double(r), g.struct(dict(maxIter=12)))
     assert err == ("MATLAB:nonExistentField", 'Unrecognized field name "tol".')
     _, err = g.call(5, g.double(X), g.double(r), g.struct(dict(maxIter=12, tol=1e-6)))

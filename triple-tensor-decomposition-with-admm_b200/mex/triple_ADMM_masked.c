@@ -14,6 +14,7 @@
 #include "tritd.h"
 
 static tritd_ctx* g_ctx = NULL;
+static int g_dev = 0, g_locked = 0;
 static void at_exit(void) { if (g_ctx) { tritd_destroy(g_ctx); g_ctx = NULL; } }
 static void to_matlab_console(const char* line, void* user) { (void)user; mexPrintf("%s", line); }
 
@@ -79,12 +80,16 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (!B0) { B0m = randn3(r, n2, r); B0 = mxGetPr(B0m); }
     if (!C0) { C0m = randn3(r, r, n3); C0 = mxGetPr(C0m); }
 
-    if (!g_ctx) {
+    {
+        /* the context is cached across calls; a call that names another opts.device gets a new one */
         const mxArray* dv = mxGetField(om, 0, "device");
-        if (tritd_create(dv ? (int)mxGetScalar(dv) : 0, &g_ctx) != TRITD_OK)
-            mexErrMsgIdAndTxt("tritd:cuda", "%s", tritd_last_error());
-        mexLock();
-        mexAtExit(at_exit);
+        const int dev = (dv && !mxIsEmpty(dv)) ? (int)mxGetScalar(dv) : 0;
+        if (g_ctx && dev != g_dev) { tritd_destroy(g_ctx); g_ctx = NULL; }
+        if (!g_ctx) {
+            if (tritd_create(dev, &g_ctx) != TRITD_OK) mexErrMsgIdAndTxt("tritd:cuda", "%s", tritd_last_error());
+            g_dev = dev;
+            if (!g_locked) { mexLock(); mexAtExit(at_exit); g_locked = 1; }
+        }
     }
     tritd_set_print(to_matlab_console, NULL);
 

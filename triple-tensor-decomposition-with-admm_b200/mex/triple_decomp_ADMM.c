@@ -23,6 +23,7 @@
 #include "tritd.h"
 
 static tritd_ctx* g_ctx = NULL;
+static int g_devs[8], g_ndev = 0, g_locked = 0;   /* the devices of the cached context; mexLock taken once */
 
 static void at_exit(void) {
     if (g_ctx) { tritd_destroy(g_ctx); g_ctx = NULL; }
@@ -95,28 +96,37 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     if (!B0) { B0m = randn3(r, n2, r); B0 = mxGetPr(B0m); }
     if (!C0) { C0m = randn3(r, r, n3); C0 = mxGetPr(C0m); }
 
-    if (!g_ctx) {
+    {
         /* opts.devices = [0 1 2 3] (CUDA ordinals) or opts.ngpu = 4 (devices 0..3) or opts.device = 2; default: device 0.
-         * Several devices: one MATLAB process drives them all (tritd_create_devices), D is sharded along mode 3. */
-        int devs[8], nd = 0;
+         * Several devices: one MATLAB process drives them all (tritd_create_devices), D is sharded along mode 3.
+         * The context is cached across calls; a call that asks for OTHER devices than the cached context has
+         * (opts.ngpu = 8 after a single-GPU call) gets a new one. */
+        int devs[8], ndev = 0;
         const mxArray* dl = mxGetField(om, 0, "devices");
         const mxArray* ng = mxGetField(om, 0, "ngpu");
         const mxArray* dv = mxGetField(om, 0, "device");
         if (dl && !mxIsEmpty(dl)) {
             if (!mxIsDouble(dl) || mxGetNumberOfElements(dl) > 8) mexErrMsgIdAndTxt("tritd:opts", "opts.devices must list at most 8 device ordinals.");
-            for (nd = 0; nd < (int)mxGetNumberOfElements(dl); ++nd) devs[nd] = (int)mxGetPr(dl)[nd];
+            for (ndev = 0; ndev < (int)mxGetNumberOfElements(dl); ++ndev) devs[ndev] = (int)mxGetPr(dl)[ndev];
         } else if (ng && !mxIsEmpty(ng)) {
             const int n = (int)mxGetScalar(ng);
             if (n < 1 || n > 8) mexErrMsgIdAndTxt("tritd:opts", "opts.ngpu must be 1..8.");
-            for (nd = 0; nd < n; ++nd) devs[nd] = nd;
+            for (ndev = 0; ndev < n; ++ndev) devs[ndev] = ndev;
         } else {
-            devs[0] = dv ? (int)mxGetScalar(dv) : 0;
-            nd = 1;
+            devs[0] = (dv && !mxIsEmpty(dv)) ? (int)mxGetScalar(dv) : 0;
+            ndev = 1;
         }
-        if (tritd_create_devices(devs, nd, &g_ctx) != TRITD_OK)
-            mexErrMsgIdAndTxt("tritd:cuda", "%s", tritd_last_error());
-        mexLock();
-        mexAtExit(at_exit);
+        if (g_ctx && (ndev != g_ndev || memcmp(devs, g_devs, sizeof(int) * (size_t)ndev) != 0)) {
+            tritd_destroy(g_ctx);
+            g_ctx = NULL;
+        }
+        if (!g_ctx) {
+            if (tritd_create_devices(devs, ndev, &g_ctx) != TRITD_OK)
+                mexErrMsgIdAndTxt("tritd:cuda", "%s", tritd_last_error());
+            memcpy(g_devs, devs, sizeof(int) * (size_t)ndev);
+            g_ndev = ndev;
+            if (!g_locked) { mexLock(); mexAtExit(at_exit); g_locked = 1; }
+        }
     }
     tritd_set_print(to_matlab_console, NULL);
 
